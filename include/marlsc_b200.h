@@ -1,0 +1,227 @@
+/*
+ * marlsc_b200.h - C ABI of the B200-native batched inventory-environment hot path.
+ *
+ * The reference (Jakoebly/marl-sc) is pure Python and has no FFI of its own; its boundary for this
+ * path is three Python contracts. Every entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root). Plain pointers and
+ * sizes only - no torch types. All device pointers must belong to the device the handle was created
+ * on. Every call is asynchronous on the given stream unless stated otherwise; the caller owns all
+ * buffers. Return value: 0 on success, a negative MARLSC_E* code otherwise (text via
+ * marlsc_last_error()). The Python host layer turns these into ValueError / RuntimeError to match
+ * the reference's exception conventions.
+ *
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef MARLSC_B200_H
+#define MARLSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARLSC_ABI_VERSION 1
+
+enum {
+  MARLSC_OK = 0,
+  MARLSC_EINVAL = -1,   /* bad argument / shape (reference raises ValueError) */
+  MARLSC_ECUDA = -2,    /* CUDA runtime error */
+  MARLSC_ENOMEM = -3,
+  MARLSC_EUNSUPPORTED = -4
+};
+
+/* action space (reference: src/environment/envs/multi_env.py:824-846) */
+enum { MARLSC_ACTION_DIRECT = 0, MARLSC_ACTION_DEMAND_CENTERED = 1, MARLSC_ACTION_BASE_STOCK = 2 };
+/* lead-time sampler (reference: src/environment/components/lead_time_sampler.py:97-108,169-197) */
+enum { MARLSC_LEAD_FIXED = 0, MARLSC_LEAD_STOCHASTIC = 1 };
+/* lost-sales handler (reference: src/environment/components/lost_sales_handler.py:71,113,172) */
+enum { MARLSC_LOST_CLOSEST = 0, MARLSC_LOST_SHIPMENT = 1, MARLSC_LOST_COST = 2 };
+/* reward scope (reference: src/environment/components/reward_calculator.py:186-188) */
+enum { MARLSC_SCOPE_AGENT = 0, MARLSC_SCOPE_TEAM = 1 };
+/* observation normalisation done inside the env (reference: multi_env.py:591,607-610,700-702) */
+enum { MARLSC_NORM_OFF = 0, MARLSC_NORM_RATIO = 1, MARLSC_NORM_MEANSTD = 2 };
+/* demand source used by marlsc_env_step (reference: components/demand_sampler.py:105-163) */
+enum { MARLSC_DEMAND_REPLAY = 0, MARLSC_DEMAND_POISSON_DEVICE = 1 };
+
+/* feature toggles, same names as the reference FeatureConfig (src/config/schema.py:598-617);
+ * block order in the observation follows multi_env.py:619-695 */
+enum {
+  MARLSC_F_INVENTORY = 1u << 0,
+  MARLSC_F_INVENTORY_AGG = 1u << 1,
+  MARLSC_F_PIPELINE = 1u << 2,
+  MARLSC_F_PIPELINE_AGG = 1u << 3,
+  MARLSC_F_DEMAND_HOME = 1u << 4,
+  MARLSC_F_DEMAND_HOME_AGG = 1u << 5,
+  MARLSC_F_SHIPPED_HOME = 1u << 6,
+  MARLSC_F_SHIPPED_AWAY = 1u << 7,
+  MARLSC_F_SHIPPED_AWAY_AGG = 1u << 8,
+  MARLSC_F_STOCKOUT = 1u << 9,
+  MARLSC_F_ROLLING_MEAN = 1u << 10,
+  MARLSC_F_ROLLING_MEAN_AGG = 1u << 11,
+  MARLSC_F_FORECAST = 1u << 12,
+  MARLSC_F_FORECAST_AGG = 1u << 13,
+  MARLSC_F_DAYS_OF_SUPPLY = 1u << 14,
+  MARLSC_F_NET_INV_POSITION = 1u << 15,
+  MARLSC_F_DEMAND_VARIABILITY = 1u << 16,
+  MARLSC_F_DEMAND_HISTORY = 1u << 17
+};
+
+#define MARLSC_ROLLING_WINDOW 5 /* multi_env.py:147 */
+
+/*
+ * Static description of one environment family. Replaces the reference's EnvironmentContext
+ * (src/environment/context.py:30-65) plus the constructor state of the five registry components
+ * (src/environment/registry.py:300-308) and of InventoryEnvironment (multi_env.py:58-190).
+ * All table pointers are HOST pointers; marlsc_env_create copies them to the device.
+ */
+typedef struct marlsc_env_spec {
+  int32_t abi_version;          /* MARLSC_ABI_VERSION */
+  int32_t n_warehouses;         /* W (= agents) */
+  int32_t n_skus;               /* S */
+  int32_t n_regions;            /* R, regions the cost tables are defined on */
+  int32_t n_regions_raw;        /* length of region_map (== R when region_map is NULL) */
+  int32_t episode_length;
+  int32_t max_expected_lead;    /* L = max(expected_lead) (lead_time_sampler.py:128-131) */
+  int32_t ring_depth;           /* D > max actual lead time; in-transit ring depth */
+  int32_t action_type;          /* MARLSC_ACTION_* */
+  int32_t lead_mode;            /* MARLSC_LEAD_* */
+  int32_t lost_sales_type;      /* MARLSC_LOST_* */
+  int32_t reward_scope;         /* MARLSC_SCOPE_* */
+  int32_t max_splits;           /* demand_allocator.py:113-116 ("default" resolved to W-1) */
+  int32_t obs_norm;             /* MARLSC_NORM_* */
+  int32_t include_warehouse_id; /* one-hot id prepended (multi_env.py:705-708) */
+  uint32_t feature_mask;        /* MARLSC_F_* */
+  double scale_factor;          /* reward_calculator.py:179-180 */
+  double lost_alpha;            /* softmax temperature of the "cost" handler */
+  const double* action_max;     /* [S] max_order_quantities | max_quantity_adjustment | max_stock_level */
+  const double* out_fixed;      /* [W,R] */
+  const double* out_var;        /* [W,R] */
+  const double* in_fixed;       /* [W,S] */
+  const double* in_var;         /* [W,S] */
+  const double* hold_rate;      /* [S] per-unit holding rate (list value, or scalar * sku weight) */
+  const double* pen_rate;       /* [S] per-unit penalty rate (same rule) */
+  const double* sku_weights;    /* [S] */
+  const int32_t* expected_lead; /* [W,S] */
+  const int32_t* home_region;   /* [W] argmin_r distances[w,r] (multi_env.py:144) */
+  const int32_t* closest_wh;    /* [R] argmin_w distances[w,r] (lost_sales_handler.py:36) */
+  const int32_t* region_map;    /* [n_regions_raw] raw -> included region (preprocessor.py:382-441) or NULL */
+  const float* obs_mean;        /* [obs_dim without id] or NULL (multi_env.py:700-702) */
+  const float* obs_std;         /* idem */
+} marlsc_env_spec_t;
+
+typedef struct marlsc_env marlsc_env_t; /* opaque handle */
+
+/*
+ * Struct-of-arrays state of E environments, all DEVICE pointers owned by the caller
+ * (reference state: multi_env.py:175-186). Layout is env-major so one environment's slice of
+ * every array is contiguous.
+ */
+typedef struct marlsc_env_state {
+  int64_t num_envs;
+  int32_t* inventory;    /* [E,W,S] on-hand stock (integer valued float64 in the reference) */
+  int32_t* ring_qty;     /* [E,D,W,S] order placed at step tau lives in plane tau % D */
+  uint8_t* ring_lead;    /* [E,D,W,S] actual lead of that order; NULL when lead_mode is FIXED */
+  int32_t* demand_hist;  /* [E,5,W,S] home-region demand of the last 5 steps, plane t % 5; may be NULL
+                            when marlsc_env_needs_history() == 0 */
+  float* forecast;       /* [E,W,S] EMA demand forecast; may be NULL when marlsc_env_needs_forecast() == 0 */
+} marlsc_env_state_t;
+
+/*
+ * Inputs and outputs of one step. Demand is a CSR list of orders per environment in the order the
+ * reference sampler emits them (demand_sampler.py:128-163): order j of env e is row
+ * order_offsets[e] + j; an all-zero row is a legal no-op order.
+ */
+typedef struct marlsc_step_io {
+  const float* actions;          /* [E,W,S] in [-1,1] (multi_env.py:253) */
+  const int32_t* order_offsets;  /* [E+1] */
+  const int16_t* order_region;   /* [n_orders] raw region ids */
+  const void* order_qty;         /* [n_orders,S] uint8 or uint16, see order_qty_bytes */
+  int32_t order_qty_bytes;       /* 1 or 2 */
+  const uint8_t* actual_lead;    /* [E,W,S] this step's sampled lead times (stochastic) or NULL */
+  float* rewards;                /* [E,W] */
+  float* obs;                    /* [E,W,obs_dim] local observations == centralised-critic state */
+  uint8_t* truncated;            /* [E] or NULL (multi_env.py:327) */
+  /* optional diagnostics (reference: collect_step_info, multi_env.py:330-362); NULL to skip.
+   * The d_* accumulators must be zeroed by the caller before the step. */
+  float* cost_breakdown;         /* [E,W,4] holding, penalty, outbound, inbound (unscaled) */
+  int32_t* d_ordered;            /* [E,W,S] */
+  int32_t* d_ship;               /* [E,W,R,S] units shipped per warehouse-region-SKU */
+  int32_t* d_ship_count;         /* [E,W,R] */
+  int32_t* d_unfulfilled;        /* [E,R,S] */
+  int32_t* d_lost_orders;        /* [E,R] */
+  float* d_lost_sales;           /* [E,W,S] needs d_unfulfilled */
+} marlsc_step_io_t;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Replaces InventoryEnvironment.__init__ + create_environment_context + get_* registry calls
+ * (multi_env.py:58-190, context.py:143-209, registry.py:26-289). Synchronous. */
+int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** out);
+void marlsc_env_destroy(marlsc_env_t* env);
+
+/* Width of one warehouse's observation (multi_env.py:444-502). */
+int32_t marlsc_env_obs_dim(const marlsc_env_t* env);
+int32_t marlsc_env_needs_history(const marlsc_env_t* env);
+int32_t marlsc_env_needs_forecast(const marlsc_env_t* env);
+/* Threads cooperating on one environment (1..256, power of two). 0 restores the automatic choice. */
+int marlsc_env_set_team_size(marlsc_env_t* env, int32_t threads_per_env);
+int32_t marlsc_env_team_size(const marlsc_env_t* env);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+
+/* Replaces InventoryEnvironment.reset (multi_env.py:192-251): state cleared, inventory set from
+ * init_inventory (device int32, [E,W,S], or [W,S] broadcast when per_env == 0), first observation
+ * written to obs [E,W,obs_dim]. */
+int marlsc_env_reset(marlsc_env_t* env, const marlsc_env_state_t* state, const int32_t* init_inventory,
+                     int32_t per_env, float* obs, void* stream);
+
+/* Replaces InventoryEnvironment.step (multi_env.py:253-366) for all E environments at timestep t
+ * (the pre-increment timestep of the reference; all environments share it, multi_env.py:325-327). */
+int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* io,
+                    int32_t t, void* stream);
+
+/* Same step driven from HOST buffers (the reference-facing call: numpy in, numpy out): copies
+ * actions / demand / lead times host->device into caller-provided device staging, steps, and copies
+ * rewards (and obs when obs_host != NULL) back. host pointers should be pinned. Returns after the
+ * device->host copies are complete. */
+typedef struct marlsc_host_step {
+  const float* actions;          /* host [E,W,S] */
+  const int32_t* order_offsets;  /* host [E+1] */
+  const int16_t* order_region;   /* host [n_orders] */
+  const void* order_qty;         /* host [n_orders,S] */
+  int64_t n_orders;
+  const uint8_t* actual_lead;    /* host [E,W,S] or NULL */
+  float* rewards;                /* host [E,W] */
+  float* obs;                    /* host [E,W,obs_dim] or NULL */
+} marlsc_host_step_t;
+int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* dev_staging,
+                         const marlsc_host_step_t* host, int32_t t, void* stream);
+
+/* Reverse-time GAE(lambda) / value-target scan over a rollout segment, one column per
+ * (environment, agent). Replaces RLlib's GeneralAdvantageEstimation connector that the reference
+ * configures through use_gae / lambda_ / gamma (src/algorithms/ippo.py:145-160, mappo.py:142-157).
+ *   rewards [T,N], values [T+1,N] (values[T] = bootstrap V(s_T)), N = E*W columns
+ *   cut [T] host-side flags: cut[t] != 0 means an episode ended (truncation) after step t; the scan
+ *   restarts there and bootstraps from cut_values[t,:] (V of the final observation), or from 0 when
+ *   cut_values is NULL (termination semantics).
+ *   adv, targets [T,N] out. */
+int marlsc_gae(const float* rewards, const float* values, const uint8_t* cut, const float* cut_values,
+               int32_t T, int64_t N, float gamma, float lam, float* adv, float* targets, void* stream);
+
+/* Per-policy advantage standardisation (x - mean) / max(1e-4, std) in place over n values
+ * (RLlib learner connector). workspace: device, >= marlsc_standardize_workspace_bytes(). */
+size_t marlsc_standardize_workspace_bytes(void);
+int marlsc_standardize(float* x, int64_t n, void* workspace, void* stream);
+
+/* ---- misc ----------------------------------------------------------------------------------- */
+const char* marlsc_last_error(void);
+int32_t marlsc_abi_version(void);
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+int64_t marlsc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLSC_B200_H */

@@ -1,0 +1,177 @@
+// spec_build.h - host-side translation of a marlsc_env_spec_t into the kernel's DevSpec:
+// validation, observation block offsets (reference: multi_env.py:444-502, 619-695), the static
+// warehouse priority table of the greedy allocator (demand_allocator.py:168-173) and the per-team
+// shared-memory scratch layout. Pure C++ (no CUDA) so the test-only host emulation shares it.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "env_core.cuh"
+
+namespace marlsc {
+
+struct HostTables {
+  std::vector<double> action_max, out_fixed, out_var, in_fixed, in_var, hold_rate, pen_rate, skw;
+  std::vector<int32_t> lead_exp, home, closest, region_map;
+  std::vector<uint8_t> prio, prio_static;
+  std::vector<float> obs_mean, obs_std;
+};
+
+inline int auto_team_size(int S) {
+  if (S <= 4) return 1;
+  if (S <= 8) return 4;
+  if (S <= 16) return 8;
+  if (S <= 32) return 16;
+  if (S <= 64) return 32;
+  return 128;
+}
+
+// Fills ds (pointers left null) and tabs. Returns an empty string on success, else the error text.
+inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostTables& tb) {
+  std::memset(&ds, 0, sizeof(ds));
+  if (sp.abi_version != MARLSC_ABI_VERSION) return "abi_version mismatch";
+  const int W = sp.n_warehouses, S = sp.n_skus, R = sp.n_regions;
+  if (W < 1 || S < 1 || R < 1) return "n_warehouses, n_skus and n_regions must be positive";
+  if (W > 255) return "n_warehouses > 255 is not supported";
+  if (R > 32767) return "n_regions > 32767 is not supported";
+  if (sp.episode_length < 1) return "episode_length must be positive";
+  if (sp.max_expected_lead < 1) return "max_expected_lead must be >= 1";
+  if (sp.ring_depth < sp.max_expected_lead || sp.ring_depth > 255) return "ring_depth must be in [max_expected_lead, 255]";
+  if (sp.action_type < 0 || sp.action_type > 2) return "unknown action_type";
+  if (sp.lead_mode < 0 || sp.lead_mode > 1) return "unknown lead_mode";
+  if (sp.lost_sales_type < 0 || sp.lost_sales_type > 2) return "unknown lost_sales_type";
+  if (sp.reward_scope < 0 || sp.reward_scope > 1) return "unknown reward_scope";
+  if (sp.obs_norm < 0 || sp.obs_norm > 2) return "unknown obs_norm";
+  if (sp.max_splits < 0) return "max_splits must be >= 0";
+  if (!(sp.feature_mask & MARLSC_F_INVENTORY) || !(sp.feature_mask & MARLSC_F_PIPELINE))
+    return "inventory and pipeline features must always be enabled";   // schema.py:624-630
+  const uint32_t F = sp.feature_mask;
+  const struct { uint32_t parent, agg; const char* name; } pairs[] = {   // schema.py:632-639
+      {MARLSC_F_INVENTORY, MARLSC_F_INVENTORY_AGG, "inventory_aggregate"},
+      {MARLSC_F_PIPELINE, MARLSC_F_PIPELINE_AGG, "pipeline_aggregate"},
+      {MARLSC_F_DEMAND_HOME, MARLSC_F_DEMAND_HOME_AGG, "incoming_demand_home_aggregate"},
+      {MARLSC_F_SHIPPED_AWAY, MARLSC_F_SHIPPED_AWAY_AGG, "units_shipped_away_aggregate"},
+      {MARLSC_F_ROLLING_MEAN, MARLSC_F_ROLLING_MEAN_AGG, "rolling_demand_mean_aggregate"},
+      {MARLSC_F_FORECAST, MARLSC_F_FORECAST_AGG, "demand_forecast_aggregate"}};
+  for (const auto& pr : pairs)
+    if ((F & pr.agg) && !(F & pr.parent)) return std::string(pr.name) + " needs its parent feature";
+  if (!sp.action_max || !sp.out_fixed || !sp.out_var || !sp.in_fixed || !sp.in_var || !sp.hold_rate ||
+      !sp.pen_rate || !sp.sku_weights || !sp.expected_lead || !sp.home_region || !sp.closest_wh)
+    return "a required table pointer is NULL";
+  if (sp.lost_sales_type == MARLSC_LOST_COST && !(sp.lost_alpha > 0.0)) return "lost_alpha must be > 0";
+  const int Rraw = sp.region_map ? sp.n_regions_raw : R;
+  if (Rraw < 1 || Rraw > 32767) return "n_regions_raw out of range";
+
+  tb.action_max.assign(sp.action_max, sp.action_max + S);
+  tb.out_fixed.assign(sp.out_fixed, sp.out_fixed + W * R);
+  tb.out_var.assign(sp.out_var, sp.out_var + W * R);
+  tb.in_fixed.assign(sp.in_fixed, sp.in_fixed + W * S);
+  tb.in_var.assign(sp.in_var, sp.in_var + W * S);
+  tb.hold_rate.assign(sp.hold_rate, sp.hold_rate + S);
+  tb.pen_rate.assign(sp.pen_rate, sp.pen_rate + S);
+  tb.skw.assign(sp.sku_weights, sp.sku_weights + S);
+  tb.lead_exp.assign(sp.expected_lead, sp.expected_lead + W * S);
+  tb.home.assign(sp.home_region, sp.home_region + W);
+  tb.closest.assign(sp.closest_wh, sp.closest_wh + R);
+  tb.region_map.clear();
+  if (sp.region_map) tb.region_map.assign(sp.region_map, sp.region_map + Rraw);
+  int lmax = 0;
+  for (int v : tb.lead_exp) {
+    if (v < 1) return "expected lead times must be >= 1";
+    lmax = std::max(lmax, v);
+  }
+  if (lmax != sp.max_expected_lead) return "max_expected_lead does not match expected_lead";
+  for (int v : tb.home) if (v < 0 || v >= R) return "home_region out of range";
+  for (int v : tb.closest) if (v < 0 || v >= W) return "closest_wh out of range";
+  for (int v : tb.region_map) if (v < 0 || v >= R) return "region_map entry out of range";
+
+  // static priority: when the fixed cost column is constant the order never depends on the weight
+  tb.prio.assign((size_t)R * W, 0);
+  tb.prio_static.assign(R, 0);
+  for (int r = 0; r < R; ++r) {
+    bool constant = true;
+    for (int w = 1; w < W; ++w) constant = constant && tb.out_fixed[w * R + r] == tb.out_fixed[r];
+    tb.prio_static[r] = constant ? 1 : 0;
+    std::vector<int> idx(W);
+    for (int w = 0; w < W; ++w) idx[w] = w;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return tb.out_var[a * R + r] < tb.out_var[b * R + r]; });
+    for (int w = 0; w < W; ++w) tb.prio[(size_t)r * W + w] = (uint8_t)idx[w];
+  }
+
+  ds.W = W; ds.S = S; ds.R = R; ds.Rraw = Rraw;
+  ds.L = sp.max_expected_lead; ds.D = sp.ring_depth; ds.episode_length = sp.episode_length;
+  ds.action_type = sp.action_type; ds.lead_mode = sp.lead_mode; ds.lost_type = sp.lost_sales_type;
+  ds.scope = sp.reward_scope; ds.max_splits = sp.max_splits; ds.norm = sp.obs_norm;
+  ds.id_off = sp.include_warehouse_id ? W : 0;
+  ds.feat = F; ds.scale = sp.scale_factor; ds.alpha = sp.lost_alpha > 0.0 ? sp.lost_alpha : 1.0;
+  ds.need_ship = (F & (MARLSC_F_SHIPPED_HOME | MARLSC_F_SHIPPED_AWAY | MARLSC_F_STOCKOUT)) ? 1 : 0;
+  ds.need_hist = ((F & (MARLSC_F_ROLLING_MEAN | MARLSC_F_DAYS_OF_SUPPLY | MARLSC_F_DEMAND_VARIABILITY |
+                        MARLSC_F_DEMAND_HISTORY)) || sp.action_type != MARLSC_ACTION_DIRECT) ? 1 : 0;
+  ds.need_fcst = (F & (MARLSC_F_FORECAST | MARLSC_F_NET_INV_POSITION)) ? 1 : 0;
+
+  // observation layout, block order of multi_env.py:619-695
+  int o = 0;
+  auto block = [&](bool on, int n, bool agg) { int at = -1; if (on) { at = o; o += n + (agg ? 1 : 0); } return at; };
+  ds.off_inv = block(true, S, F & MARLSC_F_INVENTORY_AGG);
+  ds.off_pipe = block(true, ds.L * S, F & MARLSC_F_PIPELINE_AGG);
+  ds.off_dh = block(F & MARLSC_F_DEMAND_HOME, S, F & MARLSC_F_DEMAND_HOME_AGG);
+  ds.off_sh = block(F & MARLSC_F_SHIPPED_HOME, S, false);
+  ds.off_sa = block(F & MARLSC_F_SHIPPED_AWAY, S, F & MARLSC_F_SHIPPED_AWAY_AGG);
+  ds.off_so = block(F & MARLSC_F_STOCKOUT, S, false);
+  ds.off_rm = block(F & MARLSC_F_ROLLING_MEAN, S, F & MARLSC_F_ROLLING_MEAN_AGG);
+  ds.off_fc = block(F & MARLSC_F_FORECAST, S, F & MARLSC_F_FORECAST_AGG);
+  ds.off_dos = block(F & MARLSC_F_DAYS_OF_SUPPLY, S, false);
+  ds.off_nip = block(F & MARLSC_F_NET_INV_POSITION, S, false);
+  ds.off_dv = block(F & MARLSC_F_DEMAND_VARIABILITY, S, false);
+  ds.off_hist = block(F & MARLSC_F_DEMAND_HISTORY, kWindow * S, false);
+  const int dim_noid = o;
+  ds.obs_dim = o + ds.id_off;
+  tb.obs_mean.clear();
+  tb.obs_std.clear();
+  if (sp.obs_norm == MARLSC_NORM_MEANSTD) {
+    if (!sp.obs_mean || !sp.obs_std) return "obs_norm MEANSTD needs obs_mean and obs_std";
+    tb.obs_mean.assign(sp.obs_mean, sp.obs_mean + dim_noid);
+    tb.obs_std.assign(sp.obs_std, sp.obs_std + dim_noid);
+  }
+
+  // scratch layout
+  ds.och = S <= 16 ? 16 : std::max(8, std::min(64, (4096 / S) & ~1));
+  int d = 0;
+  ds.d_lostW = d; d += R;
+  ds.d_lostP = d; d += R;
+  ds.d_cout = d; d += W;
+  ds.d_ctot = d; d += W;
+  ds.d_words = d | 1;
+  int w = 0;
+  const int WS = W * S;
+  ds.w_inv = w; w += WS;
+  ds.w_q = w; w += WS;
+  ds.w_dh = w; w += WS;
+  ds.w_sh = w; if (ds.need_ship) w += WS;
+  ds.w_st = w; if (ds.need_ship) w += WS;
+  ds.w_rm = w; if (ds.need_hist) w += WS;
+  ds.w_fc = w; if (ds.need_fcst) w += WS;
+  ds.w_shipq = w; w += W * R;
+  ds.w_lostN = w; w += R;
+  ds.w_rem = w; w += S;
+  ds.w_prio = w; w += (W + 3) / 4;
+  ds.w_sreg = w; w += (ds.och + 1) / 2;
+  ds.w_sqty = w; w += (ds.och * S + 8 + 3) / 4;
+  ds.w_words = w | 1;
+  return std::string();
+}
+
+inline void bind_tables(DevSpec& ds, const double* action_max, const double* out_fixed, const double* out_var,
+                        const double* in_fixed, const double* in_var, const double* hold_rate,
+                        const double* pen_rate, const double* skw, const int32_t* lead_exp, const int32_t* home,
+                        const int32_t* closest, const int32_t* region_map, const uint8_t* prio,
+                        const uint8_t* prio_static, const float* obs_mean, const float* obs_std) {
+  ds.action_max = action_max; ds.out_fixed = out_fixed; ds.out_var = out_var; ds.in_fixed = in_fixed;
+  ds.in_var = in_var; ds.hold_rate = hold_rate; ds.pen_rate = pen_rate; ds.skw = skw; ds.lead_exp = lead_exp;
+  ds.home = home; ds.closest = closest; ds.region_map = region_map; ds.prio = prio; ds.prio_static = prio_static;
+  ds.obs_mean = obs_mean; ds.obs_std = obs_std;
+}
+
+}  // namespace marlsc

@@ -1,0 +1,310 @@
+"""BatchedInventoryEnv - E independent inventory environments advanced by one fused CUDA kernel per
+timestep (csrc/env_step.cu). Tensor-in / tensor-out counterpart of the reference's
+``InventoryEnvironment`` (src/environment/envs/multi_env.py:38-366); the dict-based single-env API of
+the reference is provided on top of it by ``marlsc_b200.envs.InventoryEnvironment``.
+
+State is struct-of-arrays on the device, env-major (include/marlsc_b200.h ``marlsc_env_state``):
+``inventory [E,W,S]``, ``ring_qty [E,D,W,S]`` (+ ``ring_lead`` for stochastic lead times),
+``demand_hist [E,5,W,S]``, ``forecast [E,W,S]``. Observations are written once per warehouse as
+``obs [E,W,obs_dim]``; flattened over W this *is* the centralised-critic global state, so the
+reference's per-agent ``[local_i | global]`` vector is only materialised on request
+(``agent_observations``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _capi
+from ..config.schema import (EnvironmentConfig, InitialInventoryCustom, InitialInventoryUniform,
+                             InitialInventoryZero)
+from ..demand import OrderBatch, pack_orders
+from ..seeds import ENVIRONMENT_SEEDS, STOCHASTIC_SEEDS, SeedManager
+from ..spec import EnvSpec, build_env_spec
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class DeviceOrders:
+    """One step of demand resident on the device (CSR, see marlsc_b200.demand)."""
+
+    def __init__(self, offsets: torch.Tensor, region: torch.Tensor, qty: torch.Tensor, n_orders: int):
+        self.offsets, self.region, self.qty, self.n_orders = offsets, region, qty, n_orders
+
+    @property
+    def qty_bytes(self) -> int:
+        return self.qty.element_size()
+
+    @staticmethod
+    def from_host(batch: OrderBatch, device) -> "DeviceOrders":
+        region = batch.region if batch.region.size else np.zeros(1, np.int16)
+        qty = torch.from_numpy(batch.qty.view(np.uint8)).to(device)
+        if batch.qty_bytes == 2:
+            qty = qty.view(torch.int16)   # 2-byte rows; only the element size matters to the kernel
+        return DeviceOrders(torch.from_numpy(batch.offsets).to(device), torch.from_numpy(region).to(device),
+                            qty, batch.n_orders)
+
+
+class BatchedInventoryEnv:
+    metadata = {"render_modes": ["human"], "name": "multi_env"}
+
+    def __init__(self, env_config: EnvironmentConfig, num_envs: int, device: Union[str, torch.device, None] = None,
+                 seed: Optional[int] = None, env_meta: Optional[Dict[str, Any]] = None,
+                 region_map: Optional[Sequence[int]] = None, env_seeds: Optional[Sequence[int]] = None,
+                 host_samplers: bool = True, diagnostics: bool = False, team_size: int = 0):
+        if num_envs < 1:
+            raise ValueError("num_envs must be positive")
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedInventoryEnv needs a CUDA device: this path has no CPU implementation")
+        meta = env_meta or {}
+        self.env_config = env_config
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_warehouses, self.n_skus, self.n_regions = env_config.n_warehouses, env_config.n_skus, env_config.n_regions
+        self.episode_length = env_config.episode_length
+        self.feature_config = env_config.features
+        self.rolling_window = 5
+        self.obs_normalization = meta.get("obs_normalization", "off")
+        self.obs_stats = meta.get("obs_stats", None)
+        self.include_warehouse_id = bool(meta.get("include_warehouse_id", False))
+        self._num_eval_episodes = meta.get("num_eval_episodes", None)
+        self.agents = [f"warehouse_{i}" for i in range(self.n_warehouses)]
+        self.possible_agents = list(self.agents)
+        self.diagnostics = diagnostics
+
+        self.spec: EnvSpec = build_env_spec(env_config, self.obs_normalization, self.obs_stats, self.include_warehouse_id,
+                                            region_map=region_map, data_mode=meta.get("data_mode", "train"))
+        s = self.spec.scalars
+        self.max_expected_lead_time = s["max_expected_lead"]
+        self.ring_depth = s["ring_depth"]
+        self.stochastic_lead = s["lead_mode"] == 1
+        self.expected_lead_times = self.spec.tables["expected_lead"].copy()
+        self.home_regions = self.spec.tables["home_region"].copy()
+
+        L = _capi.lib()
+        self._spec_c = self.spec.to_c()
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(L.marlsc_env_create(C.byref(self._spec_c), self.device.index, C.byref(handle)))
+        self._h = handle
+        if team_size:
+            _capi.check(L.marlsc_env_set_team_size(self._h, team_size))
+        self.obs_dim = int(L.marlsc_env_obs_dim(self._h))            # local_obs_dim of the reference
+        self.global_obs_dim = self.n_warehouses * self.obs_dim
+
+        E, W, S, D, dev = self.num_envs, self.n_warehouses, self.n_skus, self.ring_depth, self.device
+        self.inventory = torch.zeros((E, W, S), dtype=torch.int32, device=dev)
+        self.ring_qty = torch.zeros((E, D, W, S), dtype=torch.int32, device=dev)
+        self.ring_lead = torch.zeros((E, D, W, S), dtype=torch.uint8, device=dev) if self.stochastic_lead else None
+        self.demand_hist = (torch.zeros((E, 5, W, S), dtype=torch.int32, device=dev)
+                            if L.marlsc_env_needs_history(self._h) else None)
+        self.forecast = torch.zeros((E, W, S), dtype=torch.float32, device=dev) if L.marlsc_env_needs_forecast(self._h) else None
+        self._state = _capi.EnvStateC(E, _ptr(self.inventory), _ptr(self.ring_qty), _ptr(self.ring_lead),
+                                      _ptr(self.demand_hist), _ptr(self.forecast))
+        self.obs = torch.zeros((E, W, self.obs_dim), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((E, W), dtype=torch.float32, device=dev)
+        self.truncated = torch.zeros((E,), dtype=torch.uint8, device=dev)
+        self._empty_orders = DeviceOrders(torch.zeros(E + 1, dtype=torch.int32, device=dev),
+                                          torch.zeros(1, dtype=torch.int16, device=dev),
+                                          torch.zeros(16, dtype=torch.uint8, device=dev), 0)
+        self.diag: Dict[str, torch.Tensor] = {}
+        if diagnostics:
+            R = self.n_regions
+            self.diag = dict(
+                cost_breakdown=torch.zeros((E, W, 4), dtype=torch.float32, device=dev),
+                ordered=torch.zeros((E, W, S), dtype=torch.int32, device=dev),
+                ship_by_sku=torch.zeros((E, W, R, S), dtype=torch.int32, device=dev),
+                ship_counts=torch.zeros((E, W, R), dtype=torch.int32, device=dev),
+                unfulfilled=torch.zeros((E, R, S), dtype=torch.int32, device=dev),
+                lost_orders=torch.zeros((E, R), dtype=torch.int32, device=dev),
+                lost_sales=torch.zeros((E, W, S), dtype=torch.float32, device=dev))
+        self.timestep = 0
+
+        # host-side seeding / sampling that replays the reference's NumPy streams (optional)
+        self.seed_managers: List[SeedManager] = []
+        self.demand_samplers: List[Any] = []
+        self.lead_time_samplers: List[Any] = []
+        self._host_samplers = host_samplers
+        if host_samplers:
+            from ..registry import get_demand_sampler, get_lead_time_sampler
+            if env_seeds is None:
+                env_seeds = [None if seed is None else SeedManager.derive_env_seed(seed, 0, i) for i in range(E)]
+            if len(env_seeds) != E:
+                raise ValueError("env_seeds must have one entry per environment")
+            self._seeded_at_construction = all(sd is not None for sd in env_seeds)
+            for sd in env_seeds:
+                self.seed_managers.append(SeedManager(root_seed=sd, seed_registry=ENVIRONMENT_SEEDS))
+                self.demand_samplers.append(get_demand_sampler(env_config, context=self.spec.context))
+                self.lead_time_samplers.append(get_lead_time_sampler(env_config, context=self.spec.context))
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _capi.lib().marlsc_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def team_size(self) -> int:
+        return int(_capi.lib().marlsc_env_team_size(self._h))
+
+    def _compute_local_obs_dim(self) -> int:
+        return self.obs_dim
+
+    def agent_observations(self, obs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[E,W,(1+W)*obs_dim]: the reference's per-agent vector ``[local_i | local_0..local_{W-1}]``
+        (multi_env.py:560-573). Materialises W copies of the global state - use only for compatibility."""
+        o = self.obs if obs is None else obs
+        E, W, D = o.shape
+        return torch.cat([o, o.reshape(E, 1, W * D).expand(E, W, W * D)], dim=2)
+
+    def global_state(self, obs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        o = self.obs if obs is None else obs
+        return o.reshape(o.shape[0], -1)
+
+    def pending_matrix(self) -> torch.Tensor:
+        """Units in transit per (env, warehouse, SKU) (reference ``_compute_pending_matrix``)."""
+        t = self.timestep
+        D = self.ring_depth
+        tau = torch.tensor([t - 1 - ((t - 1 - d) % D) for d in range(D)], device=self.device).view(1, D, 1, 1)
+        if self.stochastic_lead:
+            lead = self.ring_lead.to(torch.int64)
+        else:
+            lead = torch.from_numpy(self.expected_lead_times).to(self.device).view(1, 1, *self.expected_lead_times.shape).to(torch.int64)
+        live = (tau >= 0) & (self.ring_qty > 0) & (tau + lead >= t)
+        return (self.ring_qty * live).sum(dim=1).to(torch.float32)
+
+    # ------------------------------------------------------------------ reset
+    def _initial_inventory(self) -> Tuple[torch.Tensor, int]:
+        """(int32 device tensor, per_env flag) following multi_env.py:504-539."""
+        W, S = self.n_warehouses, self.n_skus
+        ic = self.env_config.initial_inventory
+        if isinstance(ic, InitialInventoryUniform):
+            lo, hi = ic.params["min"], ic.params["max"]
+            if self._host_samplers:
+                vals = np.stack([sm.get_rng("inventory").integers(lo, hi + 1, size=(W, S)) for sm in self.seed_managers])
+                return torch.from_numpy(vals.astype(np.int32)).to(self.device), 1
+            return torch.randint(lo, hi + 1, (self.num_envs, W, S), dtype=torch.int32, device=self.device), 1
+        if isinstance(ic, InitialInventoryCustom):
+            v = ic.params["values"]
+            arr = np.full((W, S), v, dtype=np.int32) if isinstance(v, int) else np.array(v, dtype=np.int32)
+            return torch.from_numpy(arr).to(self.device), 0
+        assert isinstance(ic, InitialInventoryZero)
+        return torch.zeros((W, S), dtype=torch.int32, device=self.device), 0
+
+    def reset(self, seed: Optional[int] = None, init_inventory: Optional[torch.Tensor] = None,
+              obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._host_samplers:
+            for i, sm in enumerate(self.seed_managers):   # multi_env.py:218-231
+                if self._seeded_at_construction:
+                    if self._num_eval_episodes is not None and (seed is not None or sm._episode_counter >= self._num_eval_episodes):
+                        sm._episode_counter = 0
+                    sm.advance_episode()
+                elif seed is not None:
+                    sm.update_root_seed(SeedManager.derive_env_seed(seed, 0, i))
+                else:
+                    sm.advance_episode()
+                for name, comp in (("demand_sampler", self.demand_samplers[i]), ("lead_time_sampler", self.lead_time_samplers[i])):
+                    comp.reset(rng=sm.get_rng(name))
+        if init_inventory is None:
+            init, per_env = self._initial_inventory()
+        else:
+            init = init_inventory.to(device=self.device, dtype=torch.int32).contiguous()
+            if init.shape == (self.num_envs, self.n_warehouses, self.n_skus):
+                per_env = 1
+            elif init.shape == (self.n_warehouses, self.n_skus):
+                per_env = 0
+            else:
+                raise ValueError(f"init_inventory must be [E,W,S] or [W,S], got {tuple(init.shape)}")
+        out = self._check_obs_out(obs_out)
+        _capi.check(_capi.lib().marlsc_env_reset(self._h, C.byref(self._state), init.data_ptr(), per_env, out.data_ptr(), self._stream()))
+        self._keep = init
+        self.timestep = 0
+        return out
+
+    def _check_obs_out(self, obs_out: Optional[torch.Tensor]) -> torch.Tensor:
+        if obs_out is None:
+            return self.obs
+        if (obs_out.shape != self.obs.shape or obs_out.dtype != torch.float32 or obs_out.device != self.device
+                or not obs_out.is_contiguous()):
+            raise ValueError(f"obs_out must be a contiguous float32 tensor of shape {tuple(self.obs.shape)} on {self.device}")
+        return obs_out
+
+    # ------------------------------------------------------------------ step
+    def sample_host_demand(self) -> Tuple[OrderBatch, Optional[np.ndarray]]:
+        """Draw this step's orders (and lead times) from the per-environment host samplers, in the
+        reference's call order: lead times first (multi_env.py:866), then demand (:295)."""
+        if not self._host_samplers:
+            raise RuntimeError("host samplers are disabled for this environment")
+        leads = None
+        if self.stochastic_lead:
+            leads = np.stack([lt.sample() for lt in self.lead_time_samplers]).astype(np.uint8)
+        per_env = [ds.sample(self.timestep) for ds in self.demand_samplers]
+        return pack_orders(per_env, self.n_skus), leads
+
+    def step(self, actions: torch.Tensor, orders: Union[DeviceOrders, OrderBatch, None] = None,
+             actual_lead: Union[torch.Tensor, np.ndarray, None] = None, obs_out: Optional[torch.Tensor] = None,
+             rewards_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, bool]:
+        """Advance every environment by one timestep.
+
+        actions: float32 [E,W,S] in [-1,1] on the device. orders: this step's demand; ``None`` draws
+        from the host samplers (reference-identical NumPy streams; slow, meant for parity and the
+        single-env adapter). Returns ``(obs [E,W,obs_dim], rewards [E,W], truncated)``; all
+        environments truncate together at ``episode_length`` and never terminate (multi_env.py:325-327).
+        The returned tensors are reused by the next call unless ``obs_out`` / ``rewards_out`` are given.
+        """
+        E, W, S = self.num_envs, self.n_warehouses, self.n_skus
+        if actions.shape != (E, W, S) or actions.dtype != torch.float32 or actions.device != self.device:
+            raise ValueError(f"actions must be a float32 tensor of shape {(E, W, S)} on {self.device}")
+        actions = actions.contiguous()
+        if orders is None:
+            host_orders, host_leads = self.sample_host_demand()
+            orders = host_orders
+            if actual_lead is None:
+                actual_lead = host_leads
+        if isinstance(orders, OrderBatch):
+            orders = DeviceOrders.from_host(orders, self.device)
+        lead_t = None
+        if self.stochastic_lead:
+            if actual_lead is None:
+                raise ValueError("actual_lead [E,W,S] is required with a stochastic lead-time sampler")
+            lead_t = (torch.from_numpy(np.ascontiguousarray(actual_lead, dtype=np.uint8)).to(self.device)
+                      if isinstance(actual_lead, np.ndarray) else actual_lead.to(device=self.device, dtype=torch.uint8).contiguous())
+            if lead_t.shape != (E, W, S):
+                raise ValueError(f"actual_lead must have shape {(E, W, S)}")
+        if orders.offsets.shape != (E + 1,) or orders.offsets.dtype != torch.int32:
+            raise ValueError("orders.offsets must be int32 [E+1]")
+        out = self._check_obs_out(obs_out)
+        rew = self.rewards if rewards_out is None else rewards_out
+        if rew.shape != (E, W) or rew.dtype != torch.float32 or not rew.is_contiguous():
+            raise ValueError("rewards_out must be a contiguous float32 [E,W] tensor")
+        d = self.diag
+        if d:
+            for k in ("ship_by_sku", "ship_counts", "unfulfilled", "lost_orders"):
+                d[k].zero_()
+        io = _capi.StepIOC(
+            actions.data_ptr(), orders.offsets.data_ptr(), orders.region.data_ptr(), orders.qty.data_ptr(),
+            orders.qty_bytes, _ptr(lead_t), rew.data_ptr(), out.data_ptr(), self.truncated.data_ptr(),
+            _ptr(d.get("cost_breakdown")), _ptr(d.get("ordered")), _ptr(d.get("ship_by_sku")), _ptr(d.get("ship_counts")),
+            _ptr(d.get("unfulfilled")), _ptr(d.get("lost_orders")), _ptr(d.get("lost_sales")))
+        _capi.check(_capi.lib().marlsc_env_step(self._h, C.byref(self._state), C.byref(io), self.timestep, self._stream()))
+        self._keep = (actions, orders, lead_t)   # keep inputs alive until the stream has consumed them
+        self.timestep += 1
+        return out, rew, self.timestep >= self.episode_length

@@ -1,0 +1,71 @@
+// emu.cpp - TEST-ONLY host emulation of the K1 step logic.
+//
+// Compiles marl-sc_b200/csrc/env_core.cuh as plain C++ with one "thread" per environment
+// (-DMARLSC_HOST_EMU, Team<1>) so that the indexing / arithmetic of the CUDA kernel's per-env code can
+// be checked against the oracle in a container that has no GPU. It is built by the tests into
+// tests/emu/_build/ and is never loaded by the product package, bench.py or smoke().
+#define MARLSC_HOST_EMU 1
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../marl-sc_b200/csrc/spec_build.h"
+
+using namespace marlsc;
+
+struct EmuEnv {
+  DevSpec ds;
+  HostTables tb;
+  std::vector<double> sd;
+  std::vector<int32_t> sw;
+};
+
+static std::string g_err;
+
+extern "C" {
+
+const char* emu_last_error() { return g_err.c_str(); }
+
+int emu_env_create(const marlsc_env_spec_t* spec, void** out) {
+  EmuEnv* e = new (std::nothrow) EmuEnv();
+  if (!e) return MARLSC_ENOMEM;
+  g_err = build_devspec(*spec, e->ds, e->tb);
+  if (!g_err.empty()) {
+    delete e;
+    return MARLSC_EINVAL;
+  }
+  const HostTables& t = e->tb;
+  bind_tables(e->ds, t.action_max.data(), t.out_fixed.data(), t.out_var.data(), t.in_fixed.data(), t.in_var.data(),
+              t.hold_rate.data(), t.pen_rate.data(), t.skw.data(), t.lead_exp.data(), t.home.data(),
+              t.closest.data(), t.region_map.empty() ? nullptr : t.region_map.data(), t.prio.data(),
+              t.prio_static.data(), t.obs_mean.empty() ? nullptr : t.obs_mean.data(),
+              t.obs_std.empty() ? nullptr : t.obs_std.data());
+  e->sd.assign(e->ds.d_words, 0.0);
+  e->sw.assign(e->ds.w_words, 0);
+  *out = e;
+  return MARLSC_OK;
+}
+
+void emu_env_destroy(void* h) { delete static_cast<EmuEnv*>(h); }
+int emu_env_obs_dim(void* h) { return static_cast<EmuEnv*>(h)->ds.obs_dim; }
+int emu_env_needs_history(void* h) { return static_cast<EmuEnv*>(h)->ds.need_hist; }
+int emu_env_needs_forecast(void* h) { return static_cast<EmuEnv*>(h)->ds.need_fcst; }
+
+int emu_env_reset(void* h, const marlsc_env_state_t* st, const int32_t* init, int per_env, float* obs) {
+  EmuEnv* e = static_cast<EmuEnv*>(h);
+  Team<1> tm;
+  tm.init(0);
+  Scratch sc{e->sd.data(), e->sw.data()};
+  for (int64_t i = 0; i < st->num_envs; ++i) reset_env<1>(e->ds, tm, sc, *st, init, per_env, obs, i);
+  return MARLSC_OK;
+}
+
+int emu_env_step(void* h, const marlsc_env_state_t* st, const marlsc_step_io_t* io, int t) {
+  EmuEnv* e = static_cast<EmuEnv*>(h);
+  Team<1> tm;
+  tm.init(0);
+  Scratch sc{e->sd.data(), e->sw.data()};
+  for (int64_t i = 0; i < st->num_envs; ++i) step_env<1>(e->ds, tm, sc, *st, *io, i, t);
+  return MARLSC_OK;
+}
+}

@@ -1,0 +1,155 @@
+"""-m gpu: the CUDA library (through its C ABI via marlsc_b200) against the reference's golden
+trajectories and the oracle. Integer quantities bit-exact; costs / rewards / observations / GAE to
+rtol 1e-5 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_io import NAMES, Golden
+from parity_common import compare_step, spec_for, step_orders
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(g, team_size=0, region_map=None, region_shift=None, steps=None):
+    from marlsc_b200.envs import BatchedInventoryEnv
+    cfg, _ = spec_for(g)
+    meta = dict(obs_normalization=g.meta["obs_normalization"], obs_stats=g.obs_stats,
+                include_warehouse_id=g.meta["include_warehouse_id"])
+    env = BatchedInventoryEnv(cfg, g.N, device="cuda:0", env_meta=meta, host_samplers=False, diagnostics=True,
+                              team_size=team_size, region_map=region_map)
+    # poison the state so reset has to clear it
+    env.ring_qty.fill_(-5)
+    env.inventory.fill_(123)
+    obs0 = env.reset(init_inventory=torch.from_numpy(g["init_inventory"]))
+    np.testing.assert_allclose(obs0.cpu().numpy(), g["obs0_local"], rtol=1e-5, atol=1e-6)
+    stochastic = g.meta["stochastic_lead"]
+    for t in range(steps or g.T):
+        act = torch.from_numpy(g["actions"][:, t]).to("cuda:0")
+        lead = g["lead_times"][:, t].astype(np.uint8) if stochastic else None
+        obs, rew, trunc = env.step(act, orders=step_orders(g, t, region_shift), actual_lead=lead)
+        out = {k: v.cpu().numpy() for k, v in env.diag.items()}
+        out.update(inventory=env.inventory.cpu().numpy(), rewards=rew.cpu().numpy(), obs=obs.cpu().numpy(),
+                   trunc=env.truncated.cpu().numpy())
+        assert bool(trunc) == bool(g["trunc"][0, t])
+        compare_step(g, t, out, what=f"cuda team={env.team_size} ")
+    env.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_matches_reference_auto_team(name):
+    _run(Golden(name))
+
+
+@pytest.mark.parametrize("team", [1, 2, 4, 8, 16, 32, 64, 128, 256])
+@pytest.mark.parametrize("name", ["allfeat_ratio_stochastic", "basestock_cost_meanstd"])
+def test_cuda_team_sizes_small(name, team):
+    _run(Golden(name), team_size=team)
+
+
+@pytest.mark.parametrize("team", [32, 64, 256])
+def test_cuda_team_sizes_large(team):
+    _run(Golden("large_network"), team_size=team, steps=6)
+
+
+def test_cuda_region_map():
+    g = Golden("small_default")
+    R = g.R
+    _run(g, region_map=list(range(R)) * 2, region_shift=lambda i, t, j: R * ((i + t + j) % 2), steps=20)
+
+
+def test_host_samplers_replay_reference_streams():
+    """Seeded like the reference (derive_env_seed), the host-side samplers draw the same initial
+    inventory, orders and lead times, so no demand has to be fed in to land on the golden trajectory."""
+    from marlsc_b200.envs import BatchedInventoryEnv
+    for name in ("small_default", "allfeat_ratio_stochastic"):
+        g = Golden(name)
+        cfg, _ = spec_for(g)
+        meta = dict(obs_normalization=g.meta["obs_normalization"], obs_stats=g.obs_stats,
+                    include_warehouse_id=g.meta["include_warehouse_id"])
+        env = BatchedInventoryEnv(cfg, g.N, device="cuda:0", env_meta=meta, seed=g.meta["base_seed"], diagnostics=True)
+        env.reset()
+        assert np.array_equal(env.inventory.cpu().numpy(), g["init_inventory"])
+        for t in range(min(g.T, 25)):
+            obs, rew, _ = env.step(torch.from_numpy(g["actions"][:, t]).to("cuda:0"))
+            assert np.array_equal(env.inventory.cpu().numpy(), g["inventory"][:, t])
+            np.testing.assert_allclose(rew.cpu().numpy(), g["rewards"][:, t], rtol=1e-5, atol=1e-6)
+        env.close()
+
+
+def test_dict_adapter_matches_reference():
+    from marlsc_b200.envs import InventoryEnvironment
+    g = Golden("small_default")
+    cfg, _ = spec_for(g)
+    env = InventoryEnvironment(cfg, seed=int(g["env_seeds"][3]))
+    obs, infos = env.reset()
+    D = env._compute_local_obs_dim()
+    assert set(obs) == {"warehouse_0", "warehouse_1", "warehouse_2"} and obs["warehouse_0"].shape == ((1 + g.W) * D,)
+    env.collect_step_info = True
+    for t in range(10):
+        act = {a: g["actions"][3, t, i] for i, a in enumerate(env.agents)}
+        obs, rew, term, trunc, infos = env.step(act)
+        np.testing.assert_allclose([rew[a] for a in env.agents], g["rewards"][3, t], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(env.inventory, g["inventory"][3, t])
+        assert np.array_equal(env._compute_pending_matrix(), g["pending"][3, t])
+        info = infos["warehouse_0"]
+        assert np.array_equal(info["shipment_quantities_by_sku"], g["ship_by_sku"][3, t])
+        np.testing.assert_allclose(info["lost_sales"], g["lost_sales"][3, t], rtol=1e-5, atol=1e-6)
+        loc = np.stack([obs[a][:D] for a in env.agents])
+        np.testing.assert_allclose(loc, g["obs_local"][3, t], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(obs["warehouse_1"][D:], loc.reshape(-1))
+        assert not any(term.values()) and not any(trunc.values())
+
+
+def test_errors_are_loud():
+    from marlsc_b200.envs import BatchedInventoryEnv
+    g = Golden("small_default")
+    cfg, _ = spec_for(g)
+    env = BatchedInventoryEnv(cfg, 4, device="cuda:0", host_samplers=False)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((4, 3, 3), device="cuda:0"))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((4, 3, 2), dtype=torch.float64, device="cuda:0"))
+    with pytest.raises(RuntimeError):
+        env.step(torch.zeros((4, 3, 2), device="cuda:0"))      # no demand source configured
+    env.close()
+
+
+@pytest.mark.parametrize("T,N,cuts", [(1, 5, False), (7, 1, False), (37, 1000, True), (100, 12288, True), (33, 333, True)])
+def test_gae_matches_oracle(T, N, cuts):
+    from marlsc_b200.rollout import compute_gae
+    from oracle.gae_oracle import gae_targets
+    rng = np.random.default_rng(T * 7 + N)
+    r = rng.normal(-1.5, 1.0, (T, N)).astype(np.float32)
+    v = rng.normal(-30, 5.0, (T + 1, N)).astype(np.float32)
+    cut = np.zeros(T, np.uint8)
+    cv = rng.normal(-30, 5.0, (T, N)).astype(np.float32)
+    if cuts:
+        cut[rng.integers(0, T, size=3)] = 1
+    for gamma, lam, use_cv in ((0.99, 0.95, True), (0.95, 0.9, False), (1.0, 1.0, True)):
+        a_ref, t_ref = gae_targets(r, v, gamma, lam, cut.astype(bool) if cuts else None, cv if (cuts and use_cv) else None)
+        a, tg = compute_gae(torch.from_numpy(r).cuda(), torch.from_numpy(v).cuda(), gamma, lam,
+                            torch.from_numpy(cut).cuda() if cuts else None,
+                            torch.from_numpy(cv).cuda() if (cuts and use_cv) else None)
+        np.testing.assert_allclose(tg.cpu().numpy(), t_ref, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(a.cpu().numpy(), a_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_gae_shapes_env_agent():
+    from marlsc_b200.rollout import compute_gae
+    r = torch.randn(8, 16, 3, device="cuda")
+    v = torch.randn(9, 16, 3, device="cuda")
+    a, tg = compute_gae(r, v, 0.99, 0.95)
+    assert a.shape == r.shape and tg.shape == r.shape
+    a2, _ = compute_gae(r.reshape(8, 48), v.reshape(9, 48), 0.99, 0.95)
+    assert torch.equal(a.reshape(8, 48), a2)
+
+
+def test_standardize_matches_oracle():
+    from marlsc_b200.rollout import standardize_
+    from oracle.gae_oracle import standardize
+    for n in (1, 31, 4097, 1 << 20):
+        x = np.random.default_rng(n).normal(2.0, 3.0, n).astype(np.float32)
+        y = standardize_(torch.from_numpy(x).cuda()).cpu().numpy()
+        np.testing.assert_allclose(y, standardize(x), rtol=1e-4, atol=2e-5)
