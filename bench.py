@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py - agent-steps/s of the hot path (fused env step K1 + GAE scan K2) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload large|small]
+
+One bench "step" is one rollout segment: SEG env steps of all E environments (one K1 launch each,
+plus a reset launch when an episode ends) followed by one K2 launch over the segment's
+[SEG, E, W] rewards/values. agent-steps per bench step = E * W * SEG. Workload (default): BASELINE.json
+configs[2], the large network (10 warehouses x 100 SKUs x 50 regions, lead times 1..10) with 65,536
+envs per GPU - the config the 1e9 agent-steps/s target is quoted on. Environments are independent,
+so N GPUs run N shards with no communication on the path (weak scaling).
+
+Printed JSON (rank 0): the driver's contract plus
+  roofline     - K1 achieved HBM GB/s (algorithmic bytes / CUDA-event launch time) against MEASURED_PEAKS.json
+  cpu_baseline - the CPU oracle port (oracle/inventory_oracle.py + gae_oracle.py) on a bounded sample
+  e2e          - same metric through the host-buffer C-ABI call (marlsc_env_step_host): pinned host
+                 actions/demand copied in, rewards (and the segment's advantages/targets) copied out
+  clocks       - nvidia-smi SM clock / throttle reasons sampled during the timed region
+`--impl reference` times the reference's CPU algorithm (the oracle port; the reference is pure Python and
+cannot be compiled into oracle/_ref) on all host cores for the same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "agent_steps_per_sec_env_step_plus_gae"
+UNIT = "agent-steps/s"
+SEG = 20                # env steps per rollout segment (episode_length 100 = 5 segments)
+GAMMA, LAM = 0.99, 0.95
+ACTION_RANGE = (-1.0, -0.5)   # direct action space, max 40: mean order 5/cell/step = mean demand
+
+
+# --------------------------------------------------------------------------------------- workloads
+def workload(name: str):
+    from golden.scenarios import large_network, small_default
+    if name == "large":
+        env = large_network()
+        return env, dict(workload="large_network_10wh_100sku_50reg_lead1-10 (BASELINE configs[2])",
+                         envs_per_gpu=65536, mean_orders_per_env_step=50.0)
+    env = small_default()
+    return env, dict(workload="env_symmetric_3WH2SKU (BASELINE configs[1] shape)", envs_per_gpu=4096,
+                     mean_orders_per_env_step=12.0)
+
+
+def algorithmic_bytes_per_env_step(W, S, L, obs_dim, mean_orders, qty_bytes=1):
+    """int32 state, fp32 actions/obs/rewards, dense demand rows + region id.
+    reads: actions 4WS + inventory 4WS + pipeline 4WSL + history (sum + oldest) 8WS + demand
+    writes: inventory 4WS + new pipeline slot 4WS + history 8WS + obs 4*W*obs_dim + rewards 4W + trunc 1"""
+    return 4 * W * S * (L + 8) + mean_orders * (S * qty_bytes + 2) + 4 * W * obs_dim + 4 * W + 1
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, val in zip(self.NAMES, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------- synthetic data (device)
+def synth_demand(env_dict, E, steps, device, seed):
+    """Per step CSR orders drawn on the device with the reference sampler's distribution
+    (demand_sampler.py:105-163): Poisson order counts per region, Bernoulli SKU masks,
+    max(1, Poisson) quantities. Synthetic input generation, outside every timed region."""
+    import torch
+    from marlsc_b200.envs import DeviceOrders
+    p = env_dict["components"]["demand_sampler"]["params"]
+    R, S = env_dict["n_regions"], env_dict["n_skus"]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lam_o = torch.tensor(p["lambda_orders"], dtype=torch.float32, device=device)
+    prob = torch.tensor(p["probability_skus"], dtype=torch.float32, device=device)
+    lam_q = torch.tensor(p["lambda_quantity"], dtype=torch.float32, device=device)
+    out = []
+    for _ in range(steps):
+        counts = torch.poisson(lam_o.expand(E, R).contiguous(), generator=g).to(torch.int64)
+        offsets = torch.zeros(E + 1, dtype=torch.int32, device=device)
+        offsets[1:] = counts.sum(1).cumsum(0).to(torch.int32)
+        region = torch.repeat_interleave(torch.arange(R, device=device).repeat(E), counts.reshape(-1))
+        n = int(region.numel())
+        mask = torch.rand((n, S), device=device, generator=g) < prob[region][:, None]
+        qty = torch.clamp(torch.poisson(lam_q[region], generator=g), min=1.0, max=255.0)
+        rows = (qty * mask).to(torch.uint8)
+        pad = (-(n * S)) % 16 + (16 if n == 0 else 0)
+        flat = torch.cat([rows.reshape(-1), torch.zeros(pad, dtype=torch.uint8, device=device)])
+        out.append(DeviceOrders(offsets, region.to(torch.int16) if n else torch.zeros(1, dtype=torch.int16, device=device), flat, n))
+    return out
+
+
+# --------------------------------------------------------------------------------------- CPU port timing
+def _cpu_worker(args):
+    env_dict, n_envs, steps, seed = args
+    import numpy as np
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.context import create_environment_context
+    from marlsc_b200.registry import get_demand_sampler
+    from oracle.gae_oracle import gae_targets
+    from oracle.inventory_oracle import OracleEnv
+    d = dict(env_dict)
+    d["allow_region_mismatch"] = True
+    cfg = environment_config_from_dict(d)
+    W, S = cfg.n_warehouses, cfg.n_skus
+    rng = np.random.default_rng(seed)
+    init = np.full((W, S), 60)
+    envs, demand = [], []
+    for i in range(n_envs):
+        smp = get_demand_sampler(cfg, context=create_environment_context(cfg))
+        smp.reset(np.random.default_rng(seed * 1000 + i))
+        demand.append([[(o.region_id, o.sku_demands) for o in smp.sample(t)] for t in range(steps)])
+        o = OracleEnv(env_dict)
+        o.reset(init)
+        envs.append(o)
+    acts = rng.uniform(ACTION_RANGE[0], ACTION_RANGE[1], (n_envs, steps, W, S)).astype(np.float32)
+    vals = rng.normal(-30, 5, (steps + 1, n_envs * W)).astype(np.float32)
+    t0 = time.perf_counter()
+    rew = np.zeros((steps, n_envs, W), np.float32)
+    for i, o in enumerate(envs):
+        for t in range(steps):
+            rew[t, i] = o.step(acts[i, t], demand[i][t])["rewards"]
+    gae_targets(rew.reshape(steps, -1), vals, GAMMA, LAM)
+    return time.perf_counter() - t0, n_envs * W * steps
+
+
+def cpu_port(env_dict, n_envs_per_worker, steps, workers):
+    import multiprocessing as mp
+    jobs = [(env_dict, n_envs_per_worker, steps, 17 + k) for k in range(workers)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    agent_steps = sum(r[1] for r in res)
+    busy = max(r[0] for r in res)
+    return agent_steps / busy, agent_steps, wall
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    env_dict, cfg = workload(args.workload)
+    large = args.workload == "large"
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    n_env, seg = (1, 4) if large else (8, SEG)
+    values = []
+    for _ in range(args.warmup):
+        cpu_port(env_dict, n_env, seg, workers)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        v, n, _ = cpu_port(env_dict, n_env, seg, workers)
+        values.append(v)
+        total += n
+    wall = time.perf_counter() - t0
+    value = statistics.mean(values)
+    sample = f"{workers} processes x {n_env} envs x {seg} env steps + NumPy GAE per bench step (pre-sampled demand)"
+    W = env_dict["n_warehouses"]
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * wall / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", config=dict(cfg, segment_env_steps=seg, gamma=GAMMA, lam=LAM),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=workers, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note="reference is pure Python (no C sources to build into oracle/_ref); timed: the CPU oracle port of its "
+                     "algorithm, pinned to the reference by tests/golden")
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import marlsc_b200  # noqa: F401
+    from marlsc_b200 import _capi
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from marlsc_b200.rollout import compute_gae
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    env_dict, cfg_desc = workload(args.workload)
+    d = dict(env_dict)
+    d["allow_region_mismatch"] = True
+    cfg = environment_config_from_dict(d)
+    E = args.envs or cfg_desc["envs_per_gpu"]
+    W, S = cfg.n_warehouses, cfg.n_skus
+    env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False, team_size=args.team)
+    L = _capi.lib()
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    lo, hi = ACTION_RANGE
+    n_in = args.distinct_steps
+    actions = [(torch.rand((E, W, S), device=dev, generator=gen) * (hi - lo) + lo) for _ in range(n_in)]
+    demand = synth_demand(env_dict, E, n_in, dev, 99 + rank)
+    mean_orders = float(np.mean([dm.n_orders for dm in demand])) / E
+    values = torch.randn((SEG + 1, E, W), device=dev, generator=gen) * 5 - 30
+    rewards = torch.empty((SEG, E, W), device=dev)
+    adv = torch.empty_like(rewards)
+    tgt = torch.empty_like(rewards)
+    obs_buf = [torch.empty_like(env.obs), torch.empty_like(env.obs)]
+    k1_events = []
+
+    def segment(time_k1: bool, counter: list):
+        for i in range(SEG):
+            if env.timestep >= env.episode_length or counter[0] == 0:
+                env.reset(obs_out=obs_buf[0])
+            j = counter[0] % n_in
+            if time_k1:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            env.step(actions[j], orders=demand[j], obs_out=obs_buf[counter[0] & 1], rewards_out=rewards[i])
+            if time_k1:
+                b.record()
+                k1_events.append((a, b))
+            counter[0] += 1
+        compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    counter = [0]
+    for _ in range(args.warmup):
+        segment(False, counter)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.marlsc_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        segment(True, counter)
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = L.marlsc_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    agent_steps = E * W * SEG * args.steps * world
+    value = agent_steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (marlsc_env_step_host) --------------------
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        n_host = min(n_in, 4)
+        h_act = [a.cpu().pin_memory() for a in actions[:n_host]]
+        h_off = [dm.offsets.cpu().pin_memory() for dm in demand[:n_host]]
+        h_reg = [dm.region.cpu().pin_memory() for dm in demand[:n_host]]
+        h_qty = [dm.qty.cpu().pin_memory() for dm in demand[:n_host]]
+        h_rew = torch.empty((SEG, E, W)).pin_memory()
+        h_val = values.cpu().pin_memory()
+        h_adv, h_tgt = torch.empty((SEG, E, W)).pin_memory(), torch.empty((SEG, E, W)).pin_memory()
+        max_orders = max(dm.n_orders for dm in demand[:n_host])
+        s_act = torch.empty((E, W, S), device=dev)
+        s_off = torch.empty(E + 1, dtype=torch.int32, device=dev)
+        s_reg = torch.empty(max(1, max_orders), dtype=torch.int16, device=dev)
+        s_qty = torch.empty(max(16, max_orders * S + 16), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        h2d = d2h = 0
+
+        def host_segment(cnt):
+            nonlocal h2d, d2h
+            for i in range(SEG):
+                if env.timestep >= env.episode_length:
+                    env.reset(obs_out=obs_buf[0])
+                j = cnt[0] % n_host
+                io = _capi.StepIOC(s_act.data_ptr(), s_off.data_ptr(), s_reg.data_ptr(), s_qty.data_ptr(), 1, None,
+                                   rewards[i].data_ptr(), obs_buf[cnt[0] & 1].data_ptr(), env.truncated.data_ptr(),
+                                   None, None, None, None, None, None, None)
+                hs = _capi.HostStepC(h_act[j].data_ptr(), h_off[j].data_ptr(), h_reg[j].data_ptr(), h_qty[j].data_ptr(),
+                                     demand[j].n_orders, None, h_rew[i].data_ptr(), None)
+                _capi.check(L.marlsc_env_step_host(env._h, C.byref(env._state), C.byref(io), C.byref(hs), env.timestep, stream))
+                env.timestep += 1
+                cnt[0] += 1
+                h2d += h_act[j].numel() * 4 + h_off[j].numel() * 4 + demand[j].n_orders * (2 + S)
+                d2h += E * W * 4
+            values.copy_(h_val, non_blocking=True)
+            compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
+            h_adv.copy_(adv, non_blocking=True)
+            h_tgt.copy_(tgt, non_blocking=True)
+            torch.cuda.synchronize()
+            h2d += h_val.numel() * 4
+            d2h += 2 * h_adv.numel() * 4
+
+        cnt = [0]
+        e2e_steps = max(1, min(args.steps, 3))
+        host_segment(cnt)
+        h2d = d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_segment(cnt)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tm = torch.tensor([dt], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dt = float(tm.item())
+        e2e = dict(value=E * W * SEG * e2e_steps * world / dt, unit=UNIT, h2d_bytes_per_step=h2d // e2e_steps,
+                   d2h_bytes_per_step=d2h // e2e_steps, api="marlsc_env_step_host (pinned host actions+orders in, rewards out) "
+                   "+ marlsc_gae, advantages/targets copied out", segments=e2e_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K1) ------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    b_env = algorithmic_bytes_per_env_step(W, S, env.max_expected_lead_time, env.obs_dim, mean_orders)
+    k1_avg_ms = statistics.mean(k1_ms)
+    achieved = b_env * E / (k1_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("envs") == E and tj.get("workload") == args.workload:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = dict(bound="hbm", kernel="env_step_kernel (K1)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_env_step=b_env, k1_ms_per_launch=k1_avg_ms,
+                    k1_share_of_step=sum(k1_ms) / elapsed_ms)
+
+    # ---- CPU baseline: the oracle port on a bounded sample, one core -------------------------------
+    cpu = None
+    if not args.no_cpu:
+        large = args.workload == "large"
+        n_env, seg = (2, 6) if large else (64, SEG)
+        v, n, wall = cpu_port(env_dict, n_env, seg, 1)
+        cpu = dict(value=v, unit=UNIT, cores=1, kind="port",
+                   sample=f"{n_env} envs x {seg} env steps + NumPy GAE, oracle/inventory_oracle.py, 1 process, {wall:.1f}s")
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="int32 state / fp32 obs+GAE / fp64 cost sums", data="synthetic",
+                config=dict(cfg_desc, envs_per_gpu=E, segment_env_steps=SEG, gamma=GAMMA, lam=LAM, team_size=env.team_size,
+                            mean_orders_per_env_step=mean_orders, actions=f"uniform{ACTION_RANGE} (mean order = mean demand)",
+                            l2="inputs larger than L2 (per-step state+obs far exceeds 126 MB)" if args.workload == "large"
+                            else "small working set; L2 resident (launch-latency bound)",
+                            distinct_input_steps=n_in),
+                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="large", choices=["large", "small"])
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--team", type=int, default=0, help="threads per env (0 = auto)")
+    ap.add_argument("--distinct-steps", type=int, default=8, help="distinct pre-sampled input steps cycled through")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
