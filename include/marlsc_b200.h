@@ -168,6 +168,9 @@ int32_t marlsc_env_needs_forecast(const marlsc_env_t* env);
 /* Threads cooperating on one environment (1..256, power of two). 0 restores the automatic choice. */
 int marlsc_env_set_team_size(marlsc_env_t* env, int32_t threads_per_env);
 int32_t marlsc_env_team_size(const marlsc_env_t* env);
+/* The library holds a lean and a generic instantiation of the step kernel and picks the lean one when
+ * the configuration allows it; on != 0 forces the generic one (used by the parity tests). */
+int marlsc_env_set_generic(marlsc_env_t* env, int32_t on);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

@@ -1,0 +1,13 @@
+// env_inst_g2.cu - K1 instantiations for teams of 2 lanes (SKUs per lane: 1 2 4).
+#include "env_kernels.cuh"
+#define STEP_CASES \
+  MARLSC_SPL_CASE(2, 1, launch_step_t, a, io, t, s) \
+  MARLSC_SPL_CASE(2, 2, launch_step_t, a, io, t, s) \
+  MARLSC_SPL_CASE(2, 4, launch_step_t, a, io, t, s) \
+
+#define RESET_CASES \
+  MARLSC_SPL_CASE(2, 1, launch_reset_t, a, init, per_env, obs, s) \
+  MARLSC_SPL_CASE(2, 2, launch_reset_t, a, init, per_env, obs, s) \
+  MARLSC_SPL_CASE(2, 4, launch_reset_t, a, init, per_env, obs, s) \
+
+MARLSC_DEFINE_G(2, STEP_CASES, RESET_CASES)

@@ -1,0 +1,165 @@
+// env_kernels.cuh - K1 kernels (step / reset) and their templated launchers. Included by one
+// translation unit per team width G (env_inst_g*.cu) so the instantiations compile in parallel.
+//
+// CTA layout: kBlock threads = kBlock/G teams, one environment each. Dynamic shared memory:
+//   [ lookup tables shared by the CTA | per-team double scratch ... | per-team word scratch ... ]
+#pragma once
+#include "lib_common.h"
+#include "spec_build.h"
+
+namespace marlsc {
+
+constexpr int kBlock = 128;
+
+struct LaunchArgs {
+  DevSpec ds;
+  marlsc_env_state_t st;
+  int max_smem_optin;
+  bool lean;   // every capability this launch needs is in kCapsLean
+};
+
+__device__ __forceinline__ Tables stage_tables(const DevSpec& sp, unsigned char* smem) {
+  // cooperative copy of the per-CTA lookup tables (a few KB, L2 resident) into shared memory
+  auto copy = [&](int at, const void* src, int bytes) {
+    const unsigned char* s = static_cast<const unsigned char*>(src);
+    if ((bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
+      const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s);
+      uint32_t* d4 = reinterpret_cast<uint32_t*>(smem + at);
+      for (int i = threadIdx.x; i < (bytes >> 2); i += blockDim.x) d4[i] = s4[i];
+    } else {
+      for (int i = threadIdx.x; i < bytes; i += blockDim.x) smem[at + i] = s[i];
+    }
+  };
+  copy(sp.t_skw, sp.skw, sp.S * 8);
+  copy(sp.t_pen, sp.pen_rate, sp.S * 8);
+  copy(sp.t_hold, sp.hold_rate, sp.S * 8);
+  copy(sp.t_prio, sp.prio, sp.R * sp.W);
+  copy(sp.t_pstat, sp.prio_static, sp.R);
+  if (sp.home_mask) copy(sp.t_hmask, sp.home_mask, sp.R * 4);
+  copy(sp.t_lead, sp.lead_u8, sp.W * sp.S);
+  Tables tb;
+  tb.skw = reinterpret_cast<const double*>(smem + sp.t_skw);
+  tb.pen = reinterpret_cast<const double*>(smem + sp.t_pen);
+  tb.hold = reinterpret_cast<const double*>(smem + sp.t_hold);
+  tb.prio = smem + sp.t_prio;
+  tb.pstat = smem + sp.t_pstat;
+  tb.hmask = sp.home_mask ? reinterpret_cast<const uint32_t*>(smem + sp.t_hmask) : nullptr;
+  tb.lead = smem + sp.t_lead;
+  return tb;
+}
+
+// Geometries for which the lean instantiation is built (the automatic choices of auto_team_size()).
+constexpr bool has_lean(int G, int SPL) {
+  return (G == 1 && (SPL == 2 || SPL == 4 || SPL == 8)) || (G == 4 && SPL == 4) || (G == 8 && SPL == 4) ||
+         (G == 16 && SPL == 4) || (G == 32 && (SPL == 4 || SPL == 8 || SPL == 16));
+}
+
+template <int G, int SPL, uint32_t CAPS>
+__global__ void __launch_bounds__(kBlock)
+env_step_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
+                const __grid_constant__ marlsc_step_io_t io, int t) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int TEAMS = kBlock / G;
+  const Tables tb = stage_tables(sp, smem);
+  __syncthreads();
+  const int team = threadIdx.x / G;
+  const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
+  if (e >= st.num_envs) return;   // whole teams leave together; everything below is team-local
+  Team<G> tm;
+  tm.init();
+  Scratch sc;
+  unsigned char* base = smem + sp.t_bytes;
+  sc.d = reinterpret_cast<double*>(base) + (size_t)team * sp.d_words;
+  sc.w = reinterpret_cast<int32_t*>(base + (size_t)TEAMS * sp.d_words * sizeof(double)) + (size_t)team * sp.w_words;
+  step_env<G, SPL, CAPS>(sp, tb, tm, sc, st, io, e, t);
+}
+
+template <int G, int SPL, uint32_t CAPS>
+__global__ void __launch_bounds__(kBlock)
+env_reset_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
+                 const int32_t* __restrict__ init_inventory, int per_env, float* __restrict__ obs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int TEAMS = kBlock / G;
+  const Tables tb = stage_tables(sp, smem);
+  __syncthreads();
+  const int team = threadIdx.x / G;
+  const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
+  if (e >= st.num_envs) return;
+  Team<G> tm;
+  tm.init();
+  reset_env<G, SPL, CAPS>(sp, tb, tm, st, init_inventory, per_env, obs, e);
+}
+
+inline size_t step_smem_bytes(const DevSpec& ds, int G) {
+  const int teams = kBlock / G;
+  return (size_t)ds.t_bytes + (size_t)teams * ((size_t)ds.d_words * sizeof(double) + (size_t)ds.w_words * sizeof(int32_t));
+}
+
+template <int G, int SPL, uint32_t CAPS>
+int launch_step_caps(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s) {
+  const int teams = kBlock / G;
+  const size_t smem = step_smem_bytes(a.ds, G);
+  if ((int)smem > a.max_smem_optin)
+    return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_kernel<G, SPL, CAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const unsigned grid = (unsigned)((a.st.num_envs + teams - 1) / teams);
+  env_step_kernel<G, SPL, CAPS><<<grid, kBlock, smem, s>>>(a.ds, a.st, io, t);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+template <int G, int SPL>
+int launch_step_t(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s) {
+  if constexpr (has_lean(G, SPL)) {
+    if (a.lean) return launch_step_caps<G, SPL, kCapsLean>(a, io, t, s);
+  }
+  return launch_step_caps<G, SPL, kCapsAll>(a, io, t, s);
+}
+
+template <int G, int SPL, uint32_t CAPS>
+int launch_reset_caps(const LaunchArgs& a, const int32_t* init, int per_env, float* obs, cudaStream_t s) {
+  const int teams = kBlock / G;
+  const size_t smem = (size_t)a.ds.t_bytes;
+  const unsigned grid = (unsigned)((a.st.num_envs + teams - 1) / teams);
+  env_reset_kernel<G, SPL, CAPS><<<grid, kBlock, smem, s>>>(a.ds, a.st, init, per_env, obs);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+template <int G, int SPL>
+int launch_reset_t(const LaunchArgs& a, const int32_t* init, int per_env, float* obs, cudaStream_t s) {
+  return launch_reset_caps<G, SPL, kCapsAll>(a, init, per_env, obs, s);   // reset is not a hot kernel
+}
+
+// One pair of entry points per team width, defined in env_inst_g*.cu; spl selects the instantiation.
+#define MARLSC_DECLARE_G(G)                                                                                   \
+  int launch_step_g##G(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s);      \
+  int launch_reset_g##G(int spl, const LaunchArgs& a, const int32_t* init, int per_env, float* obs, cudaStream_t s);
+MARLSC_DECLARE_G(1)
+MARLSC_DECLARE_G(2)
+MARLSC_DECLARE_G(4)
+MARLSC_DECLARE_G(8)
+MARLSC_DECLARE_G(16)
+MARLSC_DECLARE_G(32)
+
+#define MARLSC_SPL_CASE(G, SPL, FN, ...) case SPL: return FN<G, SPL>(__VA_ARGS__);
+#define MARLSC_DEFINE_G(G, CASES_STEP, CASES_RESET)                                                           \
+  namespace marlsc {                                                                                          \
+  int launch_step_g##G(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s) {     \
+    switch (spl) { CASES_STEP default: break; }                                                               \
+    return set_error(MARLSC_EUNSUPPORTED, "no kernel instantiated for this team size / SKU count");           \
+  }                                                                                                           \
+  int launch_reset_g##G(int spl, const LaunchArgs& a, const int32_t* init, int per_env, float* obs,           \
+                        cudaStream_t s) {                                                                     \
+    switch (spl) { CASES_RESET default: break; }                                                              \
+    return set_error(MARLSC_EUNSUPPORTED, "no kernel instantiated for this team size / SKU count");           \
+  }                                                                                                           \
+  }
+
+}  // namespace marlsc

@@ -1,19 +1,13 @@
-// env_step.cu - K1: fused environment step / reset kernels for sm_100a and their C-ABI launchers.
-//
-// Mapping: one team of TPE threads per environment (env_core.cuh), BLOCK/TPE teams per CTA, each
-// team with a private shared-memory scratch. Large shapes (S > 64) use a 4-warp team so the
-// streaming phases move 128 elements per instruction while warp 0 walks the order list; tiny shapes
-// use one thread per environment.
+// env_step.cu - C-ABI entry points of K1 (fused environment step / reset) and the dispatch onto the
+// per-team-width kernel instantiations (env_kernels.cuh, env_inst_g*.cu).
 #include <cuda_runtime.h>
 
 #include <atomic>
 #include <cstdio>
-#include <mutex>
 #include <new>
 #include <string>
 
-#include "lib_common.h"
-#include "spec_build.h"
+#include "env_kernels.cuh"
 
 namespace marlsc {
 
@@ -33,116 +27,72 @@ struct marlsc_env {
   DevSpec ds;
   HostTables tb;
   int device = 0;
-  int team = 1;        // threads per environment in use
+  int team = 1;        // lanes per environment in use
   int team_auto = 1;
+  int spl = 1;         // SKUs per lane of the instantiation in use
   void* d_blob = nullptr;  // one allocation holding every device table
   int max_smem_optin = 0;
+  int force_generic = 0;   // tests: always run the generic instantiation
 };
 
 namespace {
 
-template <int TPE>
-struct Block {
-  static constexpr int kThreads = TPE > 128 ? TPE : 128;
-  static constexpr int kTeams = kThreads / TPE;
-};
-
-template <int TPE>
-__global__ void __launch_bounds__(Block<TPE>::kThreads)
-env_step_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
-                const __grid_constant__ marlsc_step_io_t io, int t, int d_stride, int w_stride) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int TEAMS = Block<TPE>::kTeams;
-  const int team_in_block = threadIdx.x / TPE;
-  const int64_t e = (int64_t)blockIdx.x * TEAMS + team_in_block;
-  if (e >= st.num_envs) return;   // whole teams leave together; barriers below are per team
-  Team<TPE> tm;
-  tm.init(team_in_block);
-  Scratch sc;
-  sc.d = reinterpret_cast<double*>(smem) + (size_t)team_in_block * d_stride;
-  sc.w = reinterpret_cast<int32_t*>(smem + (size_t)TEAMS * d_stride * sizeof(double)) + (size_t)team_in_block * w_stride;
-  step_env<TPE>(sp, tm, sc, st, io, e, t);
+// SKUs-per-lane values instantiated for each team width (env_inst_g*.cu)
+int pick_spl(int G, int S) {
+  static const int k1[] = {1, 2, 4, 8, 0}, k2[] = {1, 2, 4, 0}, k4[] = {1, 2, 4, 0}, k8[] = {1, 4, 0},
+                   k16[] = {1, 4, 8, 0}, k32[] = {1, 4, 8, 16, 0};
+  const int* tbl = G == 1 ? k1 : G == 2 ? k2 : G == 4 ? k4 : G == 8 ? k8 : G == 16 ? k16 : G == 32 ? k32 : nullptr;
+  if (!tbl) return 0;
+  const int need = skus_per_lane(S, G);
+  for (; *tbl; ++tbl)
+    if (*tbl >= need) return *tbl;
+  return 0;
 }
 
-template <int TPE>
-__global__ void __launch_bounds__(Block<TPE>::kThreads)
-env_reset_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
-                 const int32_t* __restrict__ init_inventory, int per_env, float* __restrict__ obs, int d_stride,
-                 int w_stride) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int TEAMS = Block<TPE>::kTeams;
-  const int team_in_block = threadIdx.x / TPE;
-  const int64_t e = (int64_t)blockIdx.x * TEAMS + team_in_block;
-  if (e >= st.num_envs) return;
-  Team<TPE> tm;
-  tm.init(team_in_block);
-  Scratch sc;
-  sc.d = reinterpret_cast<double*>(smem) + (size_t)team_in_block * d_stride;
-  sc.w = reinterpret_cast<int32_t*>(smem + (size_t)TEAMS * d_stride * sizeof(double)) + (size_t)team_in_block * w_stride;
-  reset_env<TPE>(sp, tm, sc, st, init_inventory, per_env, obs, e);
+// Capabilities (env_core.cuh C_*) a launch needs; the lean kernel is used when they all fit kCapsLean.
+uint32_t required_caps(const DevSpec& ds, const HostTables& tb, const marlsc_step_io_t* io) {
+  uint32_t c = 0;
+  const uint32_t F = ds.feat;
+  if (ds.lead_mode == MARLSC_LEAD_STOCHASTIC) c |= C_STOCH;
+  if (ds.norm == MARLSC_NORM_RATIO) c |= C_RATIO;
+  if (ds.norm == MARLSC_NORM_MEANSTD) c |= C_MEANSTD;
+  if (ds.need_ship) c |= C_SHIP;
+  if (ds.need_fcst) c |= C_FCST;
+  if (F & (MARLSC_F_DAYS_OF_SUPPLY | MARLSC_F_NET_INV_POSITION | MARLSC_F_DEMAND_VARIABILITY | MARLSC_F_DEMAND_HISTORY)) c |= C_XFEAT;
+  if (F & (MARLSC_F_PIPELINE_AGG | MARLSC_F_DEMAND_HOME_AGG | MARLSC_F_ROLLING_MEAN_AGG)) c |= C_AGGX;
+  if (ds.action_type != MARLSC_ACTION_DIRECT) c |= C_ACTX;
+  if (!ds.unit_weights) c |= C_WEIGHT;
+  for (uint8_t v : tb.prio_static) if (!v) c |= C_DYNPRIO;
+  if (!tb.region_map.empty()) c |= C_REGMAP;
+  if (ds.id_off) c |= C_IDHOT;
+  if (ds.W > 32) c |= C_BIGW;
+  if (io) {
+    if (io->order_qty_bytes == 2) c |= C_QTY16;
+    if (io->cost_breakdown || io->d_ordered || io->d_ship || io->d_ship_count || io->d_unfulfilled || io->d_lost_orders ||
+        io->d_lost_sales) c |= C_DIAG;
+  }
+  return c;
 }
 
-struct LaunchGeom {
-  int block, teams, d_stride, w_stride;
-  size_t smem;
-  unsigned grid;
-};
-
-template <int TPE>
-LaunchGeom geom(const DevSpec& ds, int64_t num_envs) {
-  LaunchGeom g;
-  g.block = Block<TPE>::kThreads;
-  g.teams = g.block / TPE;
-  g.d_stride = ds.d_words;   // odd strides keep same-offset accesses of neighbouring teams on distinct banks
-  g.w_stride = ds.w_words;
-  g.smem = (size_t)g.teams * ((size_t)g.d_stride * sizeof(double) + (size_t)g.w_stride * sizeof(int32_t));
-  g.grid = (unsigned)((num_envs + g.teams - 1) / g.teams);
-  return g;
-}
-
-template <int TPE>
-int prepare(marlsc_env* env, const void* kernel, const LaunchGeom& g) {
-  if ((int)g.smem > env->max_smem_optin)
-    return set_error(MARLSC_EUNSUPPORTED, "team scratch of " + std::to_string(g.smem) + " bytes exceeds shared memory; use a larger team size");
-  if (g.smem > 48 * 1024) MARLSC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+int set_team(marlsc_env* env, int G) {
+  const int spl = pick_spl(G, env->ds.S);
+  if (!spl)
+    return set_error(MARLSC_EUNSUPPORTED, "team size " + std::to_string(G) + " cannot hold " + std::to_string(env->ds.S) +
+                                              " SKUs (at most 16 per lane, 512 SKUs in total); use a wider team");
+  env->team = G;
+  env->spl = spl;
   return MARLSC_OK;
 }
 
-template <int TPE>
-int launch_step(marlsc_env* env, const marlsc_env_state_t& st, const marlsc_step_io_t& io, int t, cudaStream_t s) {
-  const LaunchGeom g = geom<TPE>(env->ds, st.num_envs);
-  int rc = prepare<TPE>(env, (const void*)env_step_kernel<TPE>, g);
-  if (rc) return rc;
-  env_step_kernel<TPE><<<g.grid, g.block, g.smem, s>>>(env->ds, st, io, t, g.d_stride, g.w_stride);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  MARLSC_CUDA(cudaGetLastError());
-  return MARLSC_OK;
-}
-
-template <int TPE>
-int launch_reset(marlsc_env* env, const marlsc_env_state_t& st, const int32_t* init, int per_env, float* obs,
-                 cudaStream_t s) {
-  const LaunchGeom g = geom<TPE>(env->ds, st.num_envs);
-  int rc = prepare<TPE>(env, (const void*)env_reset_kernel<TPE>, g);
-  if (rc) return rc;
-  env_reset_kernel<TPE><<<g.grid, g.block, g.smem, s>>>(env->ds, st, init, per_env, obs, g.d_stride, g.w_stride);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  MARLSC_CUDA(cudaGetLastError());
-  return MARLSC_OK;
-}
-
-#define MARLSC_DISPATCH_TEAM(team, CALL)                                                   \
+#define MARLSC_DISPATCH_G(team, FN, ...)                                                   \
   switch (team) {                                                                          \
-    case 1: return CALL(1);                                                                \
-    case 2: return CALL(2);                                                                \
-    case 4: return CALL(4);                                                                \
-    case 8: return CALL(8);                                                                \
-    case 16: return CALL(16);                                                              \
-    case 32: return CALL(32);                                                              \
-    case 64: return CALL(64);                                                              \
-    case 128: return CALL(128);                                                            \
-    case 256: return CALL(256);                                                            \
-    default: return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,256]"); \
+    case 1: return FN##1(__VA_ARGS__);                                                     \
+    case 2: return FN##2(__VA_ARGS__);                                                     \
+    case 4: return FN##4(__VA_ARGS__);                                                     \
+    case 8: return FN##8(__VA_ARGS__);                                                     \
+    case 16: return FN##16(__VA_ARGS__);                                                   \
+    case 32: return FN##32(__VA_ARGS__);                                                   \
+    default: return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,32]"); \
   }
 
 int check_state(const marlsc_env* env, const marlsc_env_state_t* st) {
@@ -179,7 +129,12 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
     return set_error(MARLSC_EINVAL, err);
   }
   env->device = device;
-  env->team = env->team_auto = auto_team_size(env->ds.S);
+  env->team_auto = auto_team_size(env->ds.S);
+  if (set_team(env, env->team_auto) != MARLSC_OK) {
+    const std::string msg = g_last_error;
+    delete env;
+    return set_error(MARLSC_EUNSUPPORTED, msg);
+  }
   cudaError_t ce = cudaSetDevice(device);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&env->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (ce != cudaSuccess) {
@@ -194,7 +149,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
                o_pr = blob_add(off, t.pen_rate), o_sw = blob_add(off, t.skw), o_le = blob_add(off, t.lead_exp),
                o_hm = blob_add(off, t.home), o_cl = blob_add(off, t.closest), o_rm = blob_add(off, t.region_map),
                o_pp = blob_add(off, t.prio), o_ps = blob_add(off, t.prio_static), o_om = blob_add(off, t.obs_mean),
-               o_os = blob_add(off, t.obs_std);
+               o_os = blob_add(off, t.obs_std), o_hk = blob_add(off, t.home_mask), o_l8 = blob_add(off, t.lead_u8);
   std::vector<unsigned char> host(off + 16, 0);
   auto put = [&](size_t at, const void* src, size_t n) { if (n) std::memcpy(host.data() + at, src, n); };
   put(o_amax, t.action_max.data(), t.action_max.size() * 8); put(o_of, t.out_fixed.data(), t.out_fixed.size() * 8);
@@ -205,6 +160,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   put(o_cl, t.closest.data(), t.closest.size() * 4); put(o_rm, t.region_map.data(), t.region_map.size() * 4);
   put(o_pp, t.prio.data(), t.prio.size()); put(o_ps, t.prio_static.data(), t.prio_static.size());
   put(o_om, t.obs_mean.data(), t.obs_mean.size() * 4); put(o_os, t.obs_std.data(), t.obs_std.size() * 4);
+  put(o_hk, t.home_mask.data(), t.home_mask.size() * 4); put(o_l8, t.lead_u8.data(), t.lead_u8.size());
   ce = cudaMalloc(&env->d_blob, host.size());
   if (ce == cudaSuccess) ce = cudaMemcpy(env->d_blob, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) {
@@ -217,6 +173,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   auto I = [&](size_t at) { return reinterpret_cast<const int32_t*>(b + at); };
   bind_tables(env->ds, D(o_amax), D(o_of), D(o_ov), D(o_if), D(o_iv), D(o_hr), D(o_pr), D(o_sw), I(o_le), I(o_hm),
               I(o_cl), t.region_map.empty() ? nullptr : I(o_rm), b + o_pp, b + o_ps,
+              t.home_mask.empty() ? nullptr : reinterpret_cast<const uint32_t*>(b + o_hk), b + o_l8,
               t.obs_mean.empty() ? nullptr : reinterpret_cast<const float*>(b + o_om),
               t.obs_std.empty() ? nullptr : reinterpret_cast<const float*>(b + o_os));
   *out = env;
@@ -236,12 +193,14 @@ int32_t marlsc_env_team_size(const marlsc_env_t* env) { return env ? env->team :
 
 int marlsc_env_set_team_size(marlsc_env_t* env, int32_t tpe) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
-  if (tpe == 0) {
-    env->team = env->team_auto;
-    return MARLSC_OK;
-  }
-  if (tpe < 1 || tpe > 256 || (tpe & (tpe - 1))) return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,256]");
-  env->team = tpe;
+  if (tpe == 0) return set_team(env, env->team_auto);
+  if (tpe < 1 || tpe > 32 || (tpe & (tpe - 1))) return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,32]");
+  return set_team(env, tpe);
+}
+
+int marlsc_env_set_generic(marlsc_env_t* env, int32_t on) {
+  if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  env->force_generic = on ? 1 : 0;
   return MARLSC_OK;
 }
 
@@ -252,9 +211,8 @@ int marlsc_env_reset(marlsc_env_t* env, const marlsc_env_state_t* state, const i
   if (!init_inventory || !obs) return set_error(MARLSC_EINVAL, "init_inventory and obs must not be NULL");
   MARLSC_CUDA(cudaSetDevice(env->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CALL(T) launch_reset<T>(env, *state, init_inventory, per_env, obs, s)
-  MARLSC_DISPATCH_TEAM(env->team, CALL)
-#undef CALL
+  const LaunchArgs la{env->ds, *state, env->max_smem_optin, false};
+  MARLSC_DISPATCH_G(env->team, launch_reset_g, env->spl, la, init_inventory, per_env, obs, s)
 }
 
 int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* io, int32_t t, void* stream) {
@@ -270,9 +228,9 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
   MARLSC_CUDA(cudaSetDevice(env->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CALL(T) launch_step<T>(env, *state, *io, t, s)
-  MARLSC_DISPATCH_TEAM(env->team, CALL)
-#undef CALL
+  const bool lean = !env->force_generic && (required_caps(env->ds, env->tb, io) & ~kCapsLean) == 0;
+  const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
+  MARLSC_DISPATCH_G(env->team, launch_step_g, env->spl, la, *io, t, s)
 }
 
 int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* dev,

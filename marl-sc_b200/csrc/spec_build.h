@@ -15,18 +15,28 @@ namespace marlsc {
 struct HostTables {
   std::vector<double> action_max, out_fixed, out_var, in_fixed, in_var, hold_rate, pen_rate, skw;
   std::vector<int32_t> lead_exp, home, closest, region_map;
-  std::vector<uint8_t> prio, prio_static;
+  std::vector<uint8_t> prio, prio_static, lead_u8;
+  std::vector<uint32_t> home_mask;
   std::vector<float> obs_mean, obs_std;
 };
 
-inline int auto_team_size(int S) {
-  if (S <= 4) return 1;
-  if (S <= 8) return 4;
-  if (S <= 16) return 8;
-  if (S <= 32) return 16;
-  if (S <= 64) return 32;
-  return 128;
+inline int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
 }
+
+// Lanes per environment chosen for S SKUs: one thread for tiny SKU counts, a warp slice otherwise.
+inline int auto_team_size(int S) {
+  if (S <= 8) return 1;
+  if (S <= 16) return 4;
+  if (S <= 32) return 8;
+  if (S <= 64) return 16;
+  return 32;
+}
+
+// SKUs per lane (power of two) for a team of G lanes.
+inline int skus_per_lane(int S, int G) { return pow2ceil((S + G - 1) / G); }
 
 // Fills ds (pointers left null) and tabs. Returns an empty string on success, else the error text.
 inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostTables& tb) {
@@ -100,7 +110,21 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     for (int w = 0; w < W; ++w) tb.prio[(size_t)r * W + w] = (uint8_t)idx[w];
   }
 
+  tb.home_mask.clear();
+  if (W <= 32) {
+    tb.home_mask.assign(R, 0u);
+    for (int w = 0; w < W; ++w) tb.home_mask[tb.home[w]] |= (1u << w);
+  }
+  tb.lead_u8.resize((size_t)W * S);
+  for (int i = 0; i < W * S; ++i) {
+    if (tb.lead_exp[i] > 255) return "expected lead times above 255 are not supported";
+    tb.lead_u8[i] = (uint8_t)tb.lead_exp[i];
+  }
+  bool unit = true;
+  for (double v : tb.skw) unit = unit && (v == 1.0);
+
   ds.W = W; ds.S = S; ds.R = R; ds.Rraw = Rraw;
+  ds.unit_weights = unit ? 1 : 0;
   ds.L = sp.max_expected_lead; ds.D = sp.ring_depth; ds.episode_length = sp.episode_length;
   ds.action_type = sp.action_type; ds.lead_mode = sp.lead_mode; ds.lost_type = sp.lost_sales_type;
   ds.scope = sp.reward_scope; ds.max_splits = sp.max_splits; ds.norm = sp.obs_norm;
@@ -136,26 +160,36 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     tb.obs_std.assign(sp.obs_std, sp.obs_std + dim_noid);
   }
 
-  // scratch layout
+  // per-CTA lookup tables staged in shared memory (byte offsets, 16-byte aligned blocks)
+  {
+    int o = 0;
+    auto blk = [&](int bytes) { const int at = o; o = (o + bytes + 15) & ~15; return at; };
+    ds.t_skw = blk(S * 8);
+    ds.t_pen = blk(S * 8);
+    ds.t_hold = blk(S * 8);
+    ds.t_prio = blk(R * W);
+    ds.t_pstat = blk(R);
+    ds.t_hmask = blk(W <= 32 ? R * 4 : 0);
+    ds.t_lead = blk(W * S);
+    ds.t_bytes = o;
+  }
+  // per-team scratch
   ds.och = S <= 16 ? 16 : std::max(8, std::min(64, (4096 / S) & ~1));
   int d = 0;
   ds.d_lostW = d; d += R;
   ds.d_lostP = d; d += R;
-  ds.d_cout = d; d += W;
   ds.d_ctot = d; d += W;
+  ds.d_shipw = d; if (!unit) d += W * R;
   ds.d_words = d | 1;
   int w = 0;
   const int WS = W * S;
   ds.w_inv = w; w += WS;
-  ds.w_q = w; w += WS;
   ds.w_dh = w; w += WS;
   ds.w_sh = w; if (ds.need_ship) w += WS;
   ds.w_st = w; if (ds.need_ship) w += WS;
-  ds.w_rm = w; if (ds.need_hist) w += WS;
-  ds.w_fc = w; if (ds.need_fcst) w += WS;
   ds.w_shipq = w; w += W * R;
+  ds.w_cnt = w; w += W * R;
   ds.w_lostN = w; w += R;
-  ds.w_rem = w; w += S;
   ds.w_prio = w; w += (W + 3) / 4;
   ds.w_sreg = w; w += (ds.och + 1) / 2;
   ds.w_sqty = w; w += (ds.och * S + 8 + 3) / 4;
@@ -167,10 +201,11 @@ inline void bind_tables(DevSpec& ds, const double* action_max, const double* out
                         const double* in_fixed, const double* in_var, const double* hold_rate,
                         const double* pen_rate, const double* skw, const int32_t* lead_exp, const int32_t* home,
                         const int32_t* closest, const int32_t* region_map, const uint8_t* prio,
-                        const uint8_t* prio_static, const float* obs_mean, const float* obs_std) {
+                        const uint8_t* prio_static, const uint32_t* home_mask, const uint8_t* lead_u8,
+                        const float* obs_mean, const float* obs_std) {
   ds.action_max = action_max; ds.out_fixed = out_fixed; ds.out_var = out_var; ds.in_fixed = in_fixed;
   ds.in_var = in_var; ds.hold_rate = hold_rate; ds.pen_rate = pen_rate; ds.skw = skw; ds.lead_exp = lead_exp;
-  ds.home = home; ds.closest = closest; ds.region_map = region_map; ds.prio = prio; ds.prio_static = prio_static;
+  ds.home = home; ds.closest = closest; ds.region_map = region_map; ds.prio = prio; ds.prio_static = prio_static; ds.home_mask = home_mask; ds.lead_u8 = lead_u8;
   ds.obs_mean = obs_mean; ds.obs_std = obs_std;
 }
 

@@ -56,7 +56,8 @@ class BatchedInventoryEnv:
     def __init__(self, env_config: EnvironmentConfig, num_envs: int, device: Union[str, torch.device, None] = None,
                  seed: Optional[int] = None, env_meta: Optional[Dict[str, Any]] = None,
                  region_map: Optional[Sequence[int]] = None, env_seeds: Optional[Sequence[int]] = None,
-                 host_samplers: bool = True, diagnostics: bool = False, team_size: int = 0):
+                 host_samplers: bool = True, diagnostics: bool = False, team_size: int = 0,
+                 generic_kernel: bool = False):
         if num_envs < 1:
             raise ValueError("num_envs must be positive")
         if not torch.cuda.is_available():
@@ -98,6 +99,8 @@ class BatchedInventoryEnv:
         self._h = handle
         if team_size:
             _capi.check(L.marlsc_env_set_team_size(self._h, team_size))
+        if generic_kernel:      # tests: bypass the lean instantiation of the step kernel
+            _capi.check(L.marlsc_env_set_generic(self._h, 1))
         self.obs_dim = int(L.marlsc_env_obs_dim(self._h))            # local_obs_dim of the reference
         self.global_obs_dim = self.n_warehouses * self.obs_dim
 

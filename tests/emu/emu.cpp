@@ -1,7 +1,7 @@
 // emu.cpp - TEST-ONLY host emulation of the K1 step logic.
 //
 // Compiles marl-sc_b200/csrc/env_core.cuh as plain C++ with one "thread" per environment
-// (-DMARLSC_HOST_EMU, Team<1>) so that the indexing / arithmetic of the CUDA kernel's per-env code can
+// (-DMARLSC_HOST_EMU, Team<1>, up to 128 SKUs per lane) so that the indexing / arithmetic of the CUDA kernel's per-env code can
 // be checked against the oracle in a container that has no GPU. It is built by the tests into
 // tests/emu/_build/ and is never loaded by the product package, bench.py or smoke().
 #define MARLSC_HOST_EMU 1
@@ -13,9 +13,12 @@
 
 using namespace marlsc;
 
+constexpr int kEmuSpl = 128;   // SKUs handled by the single emulated lane
+
 struct EmuEnv {
   DevSpec ds;
   HostTables tb;
+  Tables tabs;
   std::vector<double> sd;
   std::vector<int32_t> sw;
 };
@@ -38,8 +41,15 @@ int emu_env_create(const marlsc_env_spec_t* spec, void** out) {
   bind_tables(e->ds, t.action_max.data(), t.out_fixed.data(), t.out_var.data(), t.in_fixed.data(), t.in_var.data(),
               t.hold_rate.data(), t.pen_rate.data(), t.skw.data(), t.lead_exp.data(), t.home.data(),
               t.closest.data(), t.region_map.empty() ? nullptr : t.region_map.data(), t.prio.data(),
-              t.prio_static.data(), t.obs_mean.empty() ? nullptr : t.obs_mean.data(),
-              t.obs_std.empty() ? nullptr : t.obs_std.data());
+              t.prio_static.data(), t.home_mask.empty() ? nullptr : t.home_mask.data(), t.lead_u8.data(),
+              t.obs_mean.empty() ? nullptr : t.obs_mean.data(), t.obs_std.empty() ? nullptr : t.obs_std.data());
+  if (e->ds.S > kEmuSpl) {
+    g_err = "emulation supports at most 128 SKUs";
+    delete e;
+    return MARLSC_EUNSUPPORTED;
+  }
+  e->tabs = Tables{t.skw.data(), t.pen_rate.data(), t.hold_rate.data(), t.prio.data(), t.prio_static.data(),
+                   t.home_mask.empty() ? nullptr : t.home_mask.data(), t.lead_u8.data()};
   e->sd.assign(e->ds.d_words, 0.0);
   e->sw.assign(e->ds.w_words, 0);
   *out = e;
@@ -54,18 +64,17 @@ int emu_env_needs_forecast(void* h) { return static_cast<EmuEnv*>(h)->ds.need_fc
 int emu_env_reset(void* h, const marlsc_env_state_t* st, const int32_t* init, int per_env, float* obs) {
   EmuEnv* e = static_cast<EmuEnv*>(h);
   Team<1> tm;
-  tm.init(0);
-  Scratch sc{e->sd.data(), e->sw.data()};
-  for (int64_t i = 0; i < st->num_envs; ++i) reset_env<1>(e->ds, tm, sc, *st, init, per_env, obs, i);
+  tm.init();
+  for (int64_t i = 0; i < st->num_envs; ++i) reset_env<1, kEmuSpl, kCapsAll>(e->ds, e->tabs, tm, *st, init, per_env, obs, i);
   return MARLSC_OK;
 }
 
 int emu_env_step(void* h, const marlsc_env_state_t* st, const marlsc_step_io_t* io, int t) {
   EmuEnv* e = static_cast<EmuEnv*>(h);
   Team<1> tm;
-  tm.init(0);
+  tm.init();
   Scratch sc{e->sd.data(), e->sw.data()};
-  for (int64_t i = 0; i < st->num_envs; ++i) step_env<1>(e->ds, tm, sc, *st, *io, i, t);
+  for (int64_t i = 0; i < st->num_envs; ++i) step_env<1, kEmuSpl, kCapsAll>(e->ds, e->tabs, tm, sc, *st, *io, i, t);
   return MARLSC_OK;
 }
 }
