@@ -53,6 +53,42 @@ def workload(name: str):
                      mean_orders_per_env_step=12.0)
 
 
+def base_stock_levels(env_dict, spec, z):
+    """S[w,k] = L*E[D] + z*sqrt(L*E[D]) (reference run_baselines.py:188-196), with E[D] summed over the
+    regions a warehouse serves first (its cheapest-priority regions) so that it also makes sense when
+    there are more regions than warehouses; for R == W symmetric configs this is the home region."""
+    import numpy as np
+    p = env_dict["components"]["demand_sampler"]["params"]
+    W, S, R = env_dict["n_warehouses"], env_dict["n_skus"], env_dict["n_regions"]
+    lam_o, prob = np.asarray(p["lambda_orders"], float), np.asarray(p["probability_skus"], float)
+    lam_q = np.asarray(p["lambda_quantity"], float)
+    out_var = spec.tables["out_var"]
+    first = np.argsort(out_var, axis=0, kind="stable")[0]            # cheapest warehouse per region
+    ed = np.zeros((W, S))
+    for r in range(R):
+        ed[first[r]] += lam_o[r] * prob[r] * lam_q[r]
+    lead = spec.tables["expected_lead"].astype(float)
+    return lead * ed + z * np.sqrt(lead * ed)
+
+
+def record_base_stock_actions(env, env_dict, demand, z):
+    import numpy as np
+    import torch
+    dev = env.device
+    level = torch.from_numpy(base_stock_levels(env_dict, env.spec, z)).to(dev)
+    maxq = torch.tensor(env_dict["action_space"]["params"]["max_order_quantities"], dtype=torch.float64, device=dev)
+    actions = []
+    env.reset()
+    for t in range(len(demand)):
+        qty = torch.clamp(level - env.inventory.to(torch.float64) - env.pending_matrix().to(torch.float64), min=0.0)
+        qty = torch.minimum(qty, maxq)
+        act = (2.0 * qty / maxq - 1.0).to(torch.float32)
+        actions.append(act)
+        env.step(act, orders=demand[t])
+    torch.cuda.synchronize()
+    return actions
+
+
 def algorithmic_bytes_per_env_step(W, S, L, obs_dim, mean_orders, qty_bytes=1):
     """int32 state, fp32 actions/obs/rewards, dense demand rows + region id.
     reads: actions 4WS + inventory 4WS + pipeline 4WSL + history (sum + oldest) 8WS + demand
@@ -245,11 +281,17 @@ def run_ours(args):
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    lo, hi = ACTION_RANGE
-    n_in = args.distinct_steps
-    actions = [(torch.rand((E, W, S), device=dev, generator=gen) * (hi - lo) + lo) for _ in range(n_in)]
+    n_in = args.distinct_steps if args.policy == "uniform" else cfg.episode_length
     demand = synth_demand(env_dict, E, n_in, dev, 99 + rank)
     mean_orders = float(np.mean([dm.n_orders for dm in demand])) / E
+    if args.policy == "uniform":
+        lo, hi = ACTION_RANGE
+        actions = [(torch.rand((E, W, S), device=dev, generator=gen) * (hi - lo) + lo) for _ in range(n_in)]
+    else:
+        # Pre-sampled actions of the reference's heuristic base-stock baseline (BASELINE configs[0];
+        # reference run_baselines.py:133-207): one untimed recording episode on the same demand, then
+        # the timed passes replay demand + actions, so every timed episode is the same trajectory.
+        actions = record_base_stock_actions(env, env_dict, demand, args.z)
     values = torch.randn((SEG + 1, E, W), device=dev, generator=gen) * 5 - 30
     rewards = torch.empty((SEG, E, W), device=dev)
     adv = torch.empty_like(rewards)
@@ -261,7 +303,7 @@ def run_ours(args):
         for i in range(SEG):
             if env.timestep >= env.episode_length or counter[0] == 0:
                 env.reset(obs_out=obs_buf[0])
-            j = counter[0] % n_in
+            j = env.timestep % n_in if args.policy == "base_stock" else counter[0] % n_in
             if time_k1:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -405,7 +447,9 @@ def run_ours(args):
                 ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="int32 state / fp32 obs+GAE / fp64 cost sums", data="synthetic",
                 config=dict(cfg_desc, envs_per_gpu=E, segment_env_steps=SEG, gamma=GAMMA, lam=LAM, team_size=env.team_size,
-                            mean_orders_per_env_step=mean_orders, actions=f"uniform{ACTION_RANGE} (mean order = mean demand)",
+                            mean_orders_per_env_step=mean_orders,
+                            actions=(f"pre-sampled base-stock heuristic z={args.z} (recorded once, replayed)" if args.policy == "base_stock"
+                                     else f"uniform{ACTION_RANGE}"),
                             l2="inputs larger than L2 (per-step state+obs far exceeds 126 MB)" if args.workload == "large"
                             else "small working set; L2 resident (launch-latency bound)",
                             distinct_input_steps=n_in),
@@ -424,7 +468,10 @@ def main():
     ap.add_argument("--workload", default="large", choices=["large", "small"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--team", type=int, default=0, help="threads per env (0 = auto)")
-    ap.add_argument("--distinct-steps", type=int, default=8, help="distinct pre-sampled input steps cycled through")
+    ap.add_argument("--distinct-steps", type=int, default=8, help="uniform policy: distinct pre-sampled input steps cycled through")
+    ap.add_argument("--policy", default="base_stock", choices=["base_stock", "uniform"],
+                    help="pre-sampled actions: recorded base-stock heuristic (default) or uniform noise")
+    ap.add_argument("--z", type=float, default=2.0, help="base-stock safety factor")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

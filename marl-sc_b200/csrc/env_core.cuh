@@ -140,6 +140,12 @@ struct Team {
     if (G == 1) return p;
     return __ballot_sync(gmask, p) != 0u;
   }
+  // lanes of the team for which p holds, as a bit mask relative to the team's first lane
+  __device__ __forceinline__ unsigned ballot(bool p) const {
+    if (G == 1) return p ? 1u : 0u;
+    const unsigned b = __ballot_sync(gmask, p) & gmask;
+    return G == 32 ? b : (b >> ((threadIdx.x & 31) & ~(G - 1)));
+  }
   __device__ __forceinline__ int sum(int v) const {
     if (G == 1) return v;
 #pragma unroll
@@ -160,6 +166,7 @@ struct Team {
   void init() { gl = 0; }
   void sync() const {}
   bool any(bool p) const { return p; }
+  unsigned ballot(bool p) const { return p ? 1u : 0u; }
   int sum(int v) const { return v; }
   float sum(float v) const { return v; }
   double sum(double v) const { return v; }
@@ -173,20 +180,26 @@ MDEV float f_sub(float a, float b) { return __fsub_rn(a, b); }
 MDEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
 MDEV float f_div(float a, float b) { return __fdiv_rn(a, b); }
 MDEV float f_sqrt(float a) { return __fsqrt_rn(a); }
+MDEV float f_fastdiv(float a, float b) { return __fdividef(a, b); }
 MDEV double d_add(double a, double b) { return __dadd_rn(a, b); }
 MDEV double d_mul(double a, double b) { return __dmul_rn(a, b); }
 MDEV double d_rint(double a) { return rint(a); }
 MDEV int lowest_bit(uint32_t m) { return __ffs((int)m) - 1; }
+MDEV void smem_add(int32_t* addr, int v) { atomicAdd(addr, v); }
+MDEV void smem_add(double* addr, double v) { atomicAdd(addr, v); }
 #else
 MDEV float f_add(float a, float b) { volatile float r = a + b; return r; }
 MDEV float f_sub(float a, float b) { volatile float r = a - b; return r; }
 MDEV float f_mul(float a, float b) { volatile float r = a * b; return r; }
 MDEV float f_div(float a, float b) { volatile float r = a / b; return r; }
 MDEV float f_sqrt(float a) { return std::sqrt(a); }
+MDEV float f_fastdiv(float a, float b) { return a / b; }
 MDEV double d_add(double a, double b) { volatile double r = a + b; return r; }
 MDEV double d_mul(double a, double b) { volatile double r = a * b; return r; }
 MDEV double d_rint(double a) { return std::nearbyint(a); }
 MDEV int lowest_bit(uint32_t m) { return __builtin_ctz(m); }
+MDEV void smem_add(int32_t* addr, int v) { *addr += v; }
+MDEV void smem_add(double* addr, double v) { *addr += v; }
 #endif
 MDEV int imin(int a, int b) { return a < b ? a : b; }
 MDEV int imax(int a, int b) { return a > b ? a : b; }
@@ -196,7 +209,8 @@ MDEV int pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 // mean/std normalisation of multi_env.py:700-702 applied when enabled.
 template <uint32_t CAPS>
 MDEV void emit(const DevSpec& sp, float* MARLSC_RESTRICT obs_w, int j, float x) {
-  if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD) x = f_div(f_sub(x, sp.obs_mean[j]), sp.obs_std[j]);
+  // (x - mean) / std: the quotient uses the 2-ulp fast divide, far inside the 1e-5 parity tolerance
+  if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD) x = f_fastdiv(f_sub(x, sp.obs_mean[j]), sp.obs_std[j]);
   obs_w[((CAPS & C_IDHOT) ? sp.id_off : 0) + j] = x;
 }
 
@@ -404,13 +418,14 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
     const bool need_total = ratio || (F & MARLSC_F_PIPELINE_AGG);
     const bool need_cell_total = off_nip >= 0;
     const int tm1 = (t + 1) % D;
-    int le[SPL], row0[SPL];
+    int le[SPL], row0[SPL], lim[SPL];
     MARLSC_UNROLL
     for (int j = 0; j < SPL; ++j) {
       const int s = tm.gl + G * j;
-      le[j] = s < S ? (int)tb.lead[base + s] : 0;
+      le[j] = s < S ? (int)tb.lead[base + s] : 0;   // 0 for lanes beyond S: every "k < le" test fails
       const int r0 = tm1 - le[j];
       row0[j] = r0 < 0 ? r0 + D : r0;          // ring plane of slot 0
+      lim[j] = s < S ? L : 0;                  // slots this lane writes
     }
     float den = 1.0f;
     int total = 0;
@@ -425,16 +440,14 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
           for (int kk = 0; kk < kPipeBatch; ++kk) {
             const int k = k0 + kk;
             int val = 0;
-            if (s < S && k < L) {
-              if (fixed_lead) {
-                if (k < le[j] && t + k + 1 - le[j] >= 0) {
-                  int row = row0[j] + k;
-                  if (row >= D) row -= D;
-                  val = p.ring_q[row * WS + base + s];
-                }
-              } else {
-                if (CAPS & C_STOCH) val = pipeline_value_stoch(sp, p, t, base + s, le[j], k);
+            if (fixed_lead) {
+              if (k < le[j]) {   // planes of placement steps < 0 have not been written since reset: they read 0
+                int row = row0[j] + k;
+                if (row >= D) row -= D;
+                val = p.ring_q[row * WS + base + s];
               }
+            } else if ((CAPS & C_STOCH) && k < lim[j]) {
+              val = pipeline_value_stoch(sp, p, t, base + s, le[j], k);
             }
             v[j][kk] = val;
           }
@@ -445,7 +458,7 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
           MARLSC_UNROLL
           for (int kk = 0; kk < kPipeBatch; ++kk) {
             const int k = k0 + kk;
-            if (s < S && k < L) {
+            if (k < lim[j]) {
               if (pass == 0) {
                 total += v[j][kk];
               } else {
@@ -586,7 +599,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         if (fixed_lead) {
           int row = slot_new - le[j];               // plane of the order placed at t - le
           if (row < 0) row += D;
-          if (t - le[j] >= 0) arr_in[j] = p.ring_q[row * WS + i];
+          arr_in[j] = p.ring_q[row * WS + i];        // t < le: plane not written since reset, reads 0
         }
       }
     }
@@ -734,31 +747,32 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         double wsum = 0.0;
         MARLSC_UNROLL
         for (int jj = 0; jj < SPL; ++jj) {
-          const int s = tm.gl + G * jj;
-          if (s < S && rem[jj] > 0) {
-            const int a = inv_w[s];
-            const int f = imin(rem[jj], a);
-            if (f > 0) {
-              inv_w[s] = a - f;
-              rem[jj] -= f;
-              fsum += f;
-              if (!unit_w) wsum += (double)f * tb.skw[s];
-              if (need_ship) {
-                s_st[w * S + s] += f;
-                if (is_home) s_sh[w * S + s] += f;
-              }
-              if (kDiag && io.d_ship) io.d_ship[((e * W + w) * R + r) * S + s] += f;
+          const int s = tm.gl + G * jj;            // rem[jj] > 0 implies s < S (rows beyond S were loaded as 0)
+          const int a = rem[jj] > 0 ? inv_w[s] : 0;
+          const int f = imin(rem[jj], a);
+          if (f > 0) inv_w[s] = a - f;
+          rem[jj] -= f;
+          fsum += f;
+          rsum += rem[jj];
+          if ((CAPS & (C_WEIGHT | C_SHIP | C_DIAG)) && f > 0) {
+            if (!unit_w) wsum += (double)f * tb.skw[s];
+            if (need_ship) {
+              s_st[w * S + s] += f;
+              if (is_home) s_sh[w * S + s] += f;
             }
-            rsum += rem[jj];
+            if (kDiag && io.d_ship) io.d_ship[((e * W + w) * R + r) * S + s] += f;
           }
         }
-        const int fs = tm.sum(fsum);
-        if (fs == 0) continue;                                 // this warehouse had nothing the order needs
-        if (!unit_w) wsum = tm.sum(wsum);
-        if (tm.gl == 0) {
-          s_shipq[w * R + r] += fs;
+        // Only two votes sit on the order's critical path; the shipped totals go to shared memory
+        // with (warp-aggregated) atomic adds that nobody waits for.
+        const unsigned shipped = tm.ballot(fsum > 0);
+        if (shipped == 0u) continue;                           // this warehouse had nothing the order needs
+        if (fsum > 0) {
+          smem_add(&s_shipq[w * R + r], fsum);
+          if (!unit_w) smem_add(&s_shipw[w * R + r], wsum);
+        }
+        if (tm.gl == lowest_bit(shipped)) {
           s_cnt[w * R + r] += 1;
-          if (!unit_w) s_shipw[w * R + r] += wsum;
           if (kDiag && io.d_ship_count) io.d_ship_count[(e * W + w) * R + r] += 1;
         }
         ++used;
@@ -786,7 +800,6 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
           if (kDiag && io.d_lost_orders) io.d_lost_orders[e * R + r] += 1;
         }
       }
-      tm.sync();
     }
     tm.sync();
   }
