@@ -201,17 +201,27 @@ MDEV int lowest_bit(uint32_t m) { return __builtin_ctz(m); }
 MDEV void smem_add(int32_t* addr, int v) { *addr += v; }
 MDEV void smem_add(double* addr, double v) { *addr += v; }
 #endif
+// Keep a derived pointer in registers: without this the compiler re-derives per-environment bases
+// from the kernel parameters (constant-bank load + 64-bit adds) at every access.
+template <typename T>
+MDEV T* pinned(T* p) {
+#ifndef MARLSC_HOST_EMU
+  asm volatile("" : "+l"(p));
+#endif
+  return p;
+}
 MDEV int imin(int a, int b) { return a < b ? a : b; }
 MDEV int imax(int a, int b) { return a > b ? a : b; }
 MDEV int pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
 // Write one observation element (index j inside the un-prefixed local vector) with the fixed
 // mean/std normalisation of multi_env.py:700-702 applied when enabled.
+// ``out`` points at the first element after the optional one-hot id prefix.
 template <uint32_t CAPS>
-MDEV void emit(const DevSpec& sp, float* MARLSC_RESTRICT obs_w, int j, float x) {
+MDEV void emit(const DevSpec& sp, float* MARLSC_RESTRICT out, unsigned j, float x) {
   // (x - mean) / std: the quotient uses the 2-ulp fast divide, far inside the 1e-5 parity tolerance
   if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD) x = f_fastdiv(f_sub(x, sp.obs_mean[j]), sp.obs_std[j]);
-  obs_w[((CAPS & C_IDHOT) ? sp.id_off : 0) + j] = x;
+  out[j] = x;
 }
 
 // Per-environment global pointers.
@@ -226,11 +236,11 @@ struct EnvPtrs {
 MDEV EnvPtrs env_ptrs(const DevSpec& sp, const marlsc_env_state_t& st, int64_t e) {
   const int64_t ws = (int64_t)sp.W * sp.S;
   EnvPtrs p;
-  p.inv = st.inventory + e * ws;
-  p.ring_q = st.ring_qty + e * ws * sp.D;
-  p.ring_l = st.ring_lead ? st.ring_lead + e * ws * sp.D : nullptr;
-  p.hist = st.demand_hist ? st.demand_hist + e * ws * kWindow : nullptr;
-  p.fcst = st.forecast ? st.forecast + e * ws : nullptr;
+  p.inv = pinned(st.inventory + e * ws);
+  p.ring_q = pinned(st.ring_qty + e * ws * sp.D);
+  p.ring_l = st.ring_lead ? pinned(st.ring_lead + e * ws * sp.D) : nullptr;
+  p.hist = st.demand_hist ? pinned(st.demand_hist + e * ws * kWindow) : nullptr;
+  p.fcst = st.forecast ? pinned(st.forecast + e * ws) : nullptr;
   return p;
 }
 
@@ -376,6 +386,7 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
   if ((CAPS & C_IDHOT) && sp.id_off) {
     for (int j = tm.gl; j < W; j += G) obs_w[j] = (j == w) ? 1.0f : 0.0f;
   }
+  float* MARLSC_RESTRICT const out = pinned(obs_w + ((CAPS & C_IDHOT) ? sp.id_off : 0));
 
   // team totals (ratio denominators and aggregates)
   int sumI = 0, sumDh = 0, sumSh = 0, sumSt = 0;
@@ -404,9 +415,9 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
     MARLSC_UNROLL
     for (int j = 0; j < SPL; ++j) {
       const int s = tm.gl + G * j;
-      if (s < S) emit<CAPS>(sp, obs_w, sp.off_inv + s, ratio ? (float)((double)vI[j] / ((double)sumI + 1e-8)) : (float)vI[j]);
+      if (s < S) emit<CAPS>(sp, out, sp.off_inv + s, ratio ? (float)((double)vI[j] / ((double)sumI + 1e-8)) : (float)vI[j]);
     }
-    if ((F & MARLSC_F_INVENTORY_AGG) && tm.gl == 0) emit<CAPS>(sp, obs_w, sp.off_inv + S, (float)sumI);
+    if ((F & MARLSC_F_INVENTORY_AGG) && tm.gl == 0) emit<CAPS>(sp, out, sp.off_inv + S, (float)sumI);
   }
 
   // 2. pipeline, slot-major (L,S) ravel. Fixed leads: the order placed at tau sits in slot
@@ -419,6 +430,10 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
     const bool need_cell_total = off_nip >= 0;
     const int tm1 = (t + 1) % D;
     int le[SPL], row0[SPL], lim[SPL];
+    unsigned cell[SPL];
+    const int32_t* const ring = p.ring_q;      // warp-uniform base; cells are addressed by 32-bit offsets
+    const unsigned WSu = (unsigned)WS, Su = (unsigned)S;
+    float* MARLSC_RESTRICT const pout = pinned(out + sp.off_pipe);
     MARLSC_UNROLL
     for (int j = 0; j < SPL; ++j) {
       const int s = tm.gl + G * j;
@@ -426,6 +441,7 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
       const int r0 = tm1 - le[j];
       row0[j] = r0 < 0 ? r0 + D : r0;          // ring plane of slot 0
       lim[j] = s < S ? L : 0;                  // slots this lane writes
+      cell[j] = (unsigned)(base + s);
     }
     float den = 1.0f;
     int total = 0;
@@ -443,8 +459,8 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
             if (fixed_lead) {
               if (k < le[j]) {   // planes of placement steps < 0 have not been written since reset: they read 0
                 int row = row0[j] + k;
-                if (row >= D) row -= D;
-                val = p.ring_q[row * WS + base + s];
+                row -= row >= D ? D : 0;
+                val = ring[(unsigned)row * WSu + cell[j]];
               }
             } else if ((CAPS & C_STOCH) && k < lim[j]) {
               val = pipeline_value_stoch(sp, p, t, base + s, le[j], k);
@@ -462,8 +478,13 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
               if (pass == 0) {
                 total += v[j][kk];
               } else {
-                if (need_cell_total) ptot_f[j] += (float)v[j][kk];
-                emit<CAPS>(sp, obs_w, sp.off_pipe + k * S + s, ratio ? f_div((float)v[j][kk], den) : (float)v[j][kk]);
+                if ((CAPS & C_XFEAT) && need_cell_total) ptot_f[j] += (float)v[j][kk];
+                float x = (float)v[j][kk];
+                if (ratio) x = f_div(x, den);
+                const unsigned idx = (unsigned)k * Su + (unsigned)s;
+                if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD)
+                  x = f_fastdiv(f_sub(x, sp.obs_mean[sp.off_pipe + idx]), sp.obs_std[sp.off_pipe + idx]);
+                pout[idx] = x;
               }
             }
           }
@@ -474,7 +495,7 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
         den = (float)((double)total + 1e-8);
       }
     }
-    if ((F & MARLSC_F_PIPELINE_AGG) && tm.gl == 0) emit<CAPS>(sp, obs_w, sp.off_pipe + L * S, (float)total);
+    if ((F & MARLSC_F_PIPELINE_AGG) && tm.gl == 0) emit<CAPS>(sp, out, sp.off_pipe + L * S, (float)total);
   }
 
   MARLSC_UNROLL
@@ -482,30 +503,30 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
     const int s = tm.gl + G * j;
     if (s >= S) continue;
     // 3. incoming home-region demand
-    if (off_dh >= 0) emit<CAPS>(sp, obs_w, off_dh + s, ratio ? f_div((float)vdh[j], dhDen) : (float)vdh[j]);
+    if (off_dh >= 0) emit<CAPS>(sp, out, off_dh + s, ratio ? f_div((float)vdh[j], dhDen) : (float)vdh[j]);
     // 4. units shipped to the home region (float64 in the reference)
-    if (off_sh >= 0) emit<CAPS>(sp, obs_w, off_sh + s, ratio ? (float)((double)vsh[j] / (double)dhDen) : (float)vsh[j]);
+    if (off_sh >= 0) emit<CAPS>(sp, out, off_sh + s, ratio ? (float)((double)vsh[j] / (double)dhDen) : (float)vsh[j]);
     // 5. units shipped to other regions
     if (off_sa >= 0) {
       const int v = vst[j] - vsh[j];
-      emit<CAPS>(sp, obs_w, off_sa + s, ratio ? (float)((double)v / ((double)sumSt + 1e-8)) : (float)v);
+      emit<CAPS>(sp, out, off_sa + s, ratio ? (float)((double)v / ((double)sumSt + 1e-8)) : (float)v);
     }
     // 6. stockout = max(home demand - shipped home, 0)
     if (off_so >= 0) {
       const float v = (float)imax(vdh[j] - vsh[j], 0);
-      emit<CAPS>(sp, obs_w, off_so + s, ratio ? f_div(v, dhDen) : v);
+      emit<CAPS>(sp, out, off_so + s, ratio ? f_div(v, dhDen) : v);
     }
     // 7. rolling mean of home demand
-    if (off_rm >= 0) emit<CAPS>(sp, obs_w, off_rm + s, ratio ? f_div(vrm[j], f_add(sumRm, 1e-8f)) : vrm[j]);
+    if (off_rm >= 0) emit<CAPS>(sp, out, off_rm + s, ratio ? f_div(vrm[j], f_add(sumRm, 1e-8f)) : vrm[j]);
     // 8. EMA forecast
-    if (off_fc >= 0) emit<CAPS>(sp, obs_w, off_fc + s, ratio ? f_div(vfc[j], f_add(sumFc, 1e-8f)) : vfc[j]);
+    if (off_fc >= 0) emit<CAPS>(sp, out, off_fc + s, ratio ? f_div(vfc[j], f_add(sumFc, 1e-8f)) : vfc[j]);
     // 9. days of supply
     if (off_dos >= 0)
-      emit<CAPS>(sp, obs_w, off_dos + s, (float)((double)vI[j] / (double)(vrm[j] > 1.0f ? vrm[j] : 1.0f)));
+      emit<CAPS>(sp, out, off_dos + s, (float)((double)vI[j] / (double)(vrm[j] > 1.0f ? vrm[j] : 1.0f)));
     // 10. net inventory position = on hand + in transit - forecast * expected lead
     if (off_nip >= 0) {
       const double v = ((double)vI[j] + (double)ptot_f[j]) - (double)vfc[j] * (double)tb.lead[base + s];
-      emit<CAPS>(sp, obs_w, off_nip + s, (float)v);
+      emit<CAPS>(sp, out, off_nip + s, (float)v);
     }
     // 11. demand variability: population std over the history window, float32 like np.std
     if (off_dv >= 0) {
@@ -526,23 +547,23 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
         }
         v = f_sqrt(f_div(acc, (float)hist_n));
       }
-      emit<CAPS>(sp, obs_w, off_dv + s, v);
+      emit<CAPS>(sp, out, off_dv + s, v);
     }
     // 12. demand history, most recent first, zero padded
     if (off_hist >= 0) {
       for (int a = 0; a < kWindow; ++a) {
         float v = 0.f;
         if (a < hist_n) v = a == 0 ? (float)vdh[j] : (float)p.hist[pmod(t - a, kWindow) * WS + base + s];
-        emit<CAPS>(sp, obs_w, off_hist + a * S + s, v);
+        emit<CAPS>(sp, out, off_hist + a * S + s, v);
       }
     }
   }
   if (tm.gl == 0) {
-    if (off_dh >= 0 && (F & MARLSC_F_DEMAND_HOME_AGG)) emit<CAPS>(sp, obs_w, off_dh + S, (float)sumDh);
+    if (off_dh >= 0 && (F & MARLSC_F_DEMAND_HOME_AGG)) emit<CAPS>(sp, out, off_dh + S, (float)sumDh);
     if (off_sa >= 0 && (F & MARLSC_F_SHIPPED_AWAY_AGG))
-      emit<CAPS>(sp, obs_w, off_sa + S, (float)((double)(sumSt - sumSh) / ((double)sumSt + 1e-8)));
-    if (off_rm >= 0 && (F & MARLSC_F_ROLLING_MEAN_AGG)) emit<CAPS>(sp, obs_w, off_rm + S, sumRm);
-    if (off_fc >= 0 && (F & MARLSC_F_FORECAST_AGG)) emit<CAPS>(sp, obs_w, off_fc + S, sumFc);
+      emit<CAPS>(sp, out, off_sa + S, (float)((double)(sumSt - sumSh) / ((double)sumSt + 1e-8)));
+    if (off_rm >= 0 && (F & MARLSC_F_ROLLING_MEAN_AGG)) emit<CAPS>(sp, out, off_rm + S, sumRm);
+    if (off_fc >= 0 && (F & MARLSC_F_FORECAST_AGG)) emit<CAPS>(sp, out, off_fc + S, sumFc);
   }
 }
 
@@ -570,7 +591,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   double* s_ctot = sc.d + sp.d_ctot;
   double* s_shipw = sc.d + sp.d_shipw;
 
-  const float* act = io.actions + e * WS;
+  const float* act = pinned(io.actions + e * WS);
   const bool fixed_lead = !(CAPS & C_STOCH) || sp.lead_mode == MARLSC_LEAD_FIXED;
   const bool need_ship = (CAPS & C_SHIP) && sp.need_ship;
   const bool need_fcst = (CAPS & C_FCST) && sp.need_fcst;
@@ -579,7 +600,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   constexpr bool kDiag = (CAPS & C_DIAG) != 0;
   const uint8_t* lead_new = fixed_lead ? nullptr : io.actual_lead + e * WS;
   const int slot_new = t % D;
-  int32_t* ring_new = p.ring_q + slot_new * WS;
+  int32_t* ring_new = pinned(p.ring_q + slot_new * WS);
 
   // ---- phase 1: orders in, arrivals in (multi_env.py:287-292) ------------------------------------
   for (int w = 0; w < W; ++w) {
