@@ -64,6 +64,7 @@ enum : uint32_t {
   C_IDHOT = 1u << 12,    // one-hot warehouse id prefix
   C_AGGX = 1u << 13,     // pipeline / home-demand / rolling-mean aggregates
   C_BIGW = 1u << 14,     // more than 32 warehouses (no home bitmask)
+  C_DHSMEM = 1u << 15,   // home demand needed without a history plane (kept in shared memory)
 };
 constexpr uint32_t kCapsAll = 0xffffffffu;
 constexpr uint32_t kCapsLean = C_MEANSTD | C_IDHOT;
@@ -75,6 +76,8 @@ struct DevSpec {
   int action_type, lead_mode, lost_type, scope, max_splits, norm, id_off, obs_dim;
   uint32_t feat;
   int need_hist, need_fcst, need_ship, unit_weights;
+  int dh_mode;     // home-demand accumulator: 0 not needed, 1 the history plane of step t (global, L1 resident), 2 shared memory
+  int has_fixed;   // some outbound fixed cost is non-zero (shipment counts matter)
   double scale, alpha;
   const double* action_max;
   const double* out_fixed;
@@ -601,6 +604,10 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   const uint8_t* lead_new = fixed_lead ? nullptr : io.actual_lead + e * WS;
   const int slot_new = t % D;
   int32_t* ring_new = pinned(p.ring_q + slot_new * WS);
+  // accumulator of this step's home-region demand per (warehouse, SKU)
+  const int dh_mode = (CAPS & C_DHSMEM) ? sp.dh_mode : (sp.dh_mode == 1 ? 1 : 0);
+  int32_t* const dh_acc = dh_mode == 1 ? pinned(p.hist + (t % kWindow) * WS) : s_dh;
+  const bool has_fixed = sp.has_fixed;
 
   // ---- phase 1: orders in, arrivals in (multi_env.py:287-292) ------------------------------------
   for (int w = 0; w < W; ++w) {
@@ -639,7 +646,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         s_inv[i] = inv_in[j] + arr_in[j];
         ring_new[i] = q;
         if (lead_new) p.ring_l[slot_new * WS + i] = lead_new[i];
-        s_dh[i] = 0;
+        if (dh_mode) dh_acc[i] = 0;
         if (need_ship) {
           s_sh[i] = 0;
           s_st[i] = 0;
@@ -650,7 +657,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   }
   for (int i = tm.gl; i < W * R; i += G) {
     s_shipq[i] = 0;
-    s_cnt[i] = 0;
+    if (has_fixed) s_cnt[i] = 0;
     if (!unit_w) s_shipw[i] = 0.0;
   }
   for (int i = tm.gl; i < R; i += G) {
@@ -706,7 +713,8 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       }
       if (!tm.any(dsum > 0)) continue;                         // all-zero order: nothing can ship or be lost
       // home-region demand of this step (multi_env.py:763-768)
-      if (!(CAPS & C_BIGW) || tb.hmask) {
+      if (!dh_mode) {
+      } else if (!(CAPS & C_BIGW) || tb.hmask) {
         uint32_t hm = tb.hmask[r];
         while (hm) {
           const int w = lowest_bit(hm);
@@ -714,7 +722,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
           MARLSC_UNROLL
           for (int jj = 0; jj < SPL; ++jj) {
             const int s = tm.gl + G * jj;
-            if (s < S && rem[jj] > 0) s_dh[w * S + s] += rem[jj];
+            if (s < S && rem[jj] > 0) dh_acc[w * S + s] += rem[jj];
           }
         }
       } else {
@@ -723,7 +731,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
             MARLSC_UNROLL
             for (int jj = 0; jj < SPL; ++jj) {
               const int s = tm.gl + G * jj;
-              if (s < S && rem[jj] > 0) s_dh[w * S + s] += rem[jj];
+              if (s < S && rem[jj] > 0) dh_acc[w * S + s] += rem[jj];
             }
           }
       }
@@ -792,8 +800,8 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
           smem_add(&s_shipq[w * R + r], fsum);
           if (!unit_w) smem_add(&s_shipw[w * R + r], wsum);
         }
-        if (tm.gl == lowest_bit(shipped)) {
-          s_cnt[w * R + r] += 1;
+        if ((has_fixed || kDiag) && tm.gl == lowest_bit(shipped)) {
+          if (has_fixed) s_cnt[w * R + r] += 1;
           if (kDiag && io.d_ship_count) io.d_ship_count[(e * W + w) * R + r] += 1;
         }
         ++used;
@@ -844,7 +852,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       if (s < S) {
         const int i = base + s;
         vI[j] = s_inv[i];
-        vdh[j] = s_dh[i];
+        if (dh_mode) vdh[j] = dh_acc[i];
         vq[j] = ring_new[i];
         if (need_ship) {
           vsh[j] = s_sh[i];
@@ -870,7 +878,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         if (sp.need_hist) {
           // integer-valued float32 sum over the window is exact in any order (multi_env.py:785-787)
           vrm[j] = f_div((float)(hsum[j] + vdh[j]), (float)hist_n);
-          p.hist[(t % kWindow) * WS + i] = vdh[j];
+          if (dh_mode != 1) p.hist[(t % kWindow) * WS + i] = vdh[j];   // mode 1 accumulated in place
         }
         if (need_fcst) {
           vfc[j] = f_add(f_mul(0.3f, (float)vdh[j]), f_mul(0.7f, vfc[j]));   // multi_env.py:790-793
@@ -886,10 +894,11 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
     for (int r0 = 0; r0 < R; r0 += G) {
       const int r = r0 + tm.gl;
       if (r < R) {
-        const int c = s_cnt[w * R + r];
-        if (c > 0) {
-          const double shw = unit_w ? (double)s_shipq[w * R + r] : s_shipw[w * R + r];
-          outc += (double)c * sp.out_fixed[w * R + r] + shw * sp.out_var[w * R + r];
+        const int sq = s_shipq[w * R + r];
+        if (sq > 0) {
+          const double shw = unit_w ? (double)sq : s_shipw[w * R + r];
+          outc += shw * sp.out_var[w * R + r];
+          if (has_fixed) outc += (double)s_cnt[w * R + r] * sp.out_fixed[w * R + r];
         }
         if (s_lostN[r] > 0) pen += lost_weight(sp, s_shipq, s_lostN, s_lostW, w, r) * s_lostP[r];
       }

@@ -134,6 +134,10 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
   ds.need_hist = ((F & (MARLSC_F_ROLLING_MEAN | MARLSC_F_DAYS_OF_SUPPLY | MARLSC_F_DEMAND_VARIABILITY |
                         MARLSC_F_DEMAND_HISTORY)) || sp.action_type != MARLSC_ACTION_DIRECT) ? 1 : 0;
   ds.need_fcst = (F & (MARLSC_F_FORECAST | MARLSC_F_NET_INV_POSITION)) ? 1 : 0;
+  const bool need_dh = ds.need_hist || (F & (MARLSC_F_DEMAND_HOME | MARLSC_F_STOCKOUT));
+  ds.dh_mode = ds.need_hist ? 1 : (need_dh ? 2 : 0);
+  ds.has_fixed = 0;
+  for (double v : tb.out_fixed) if (v != 0.0) ds.has_fixed = 1;
 
   // observation layout, block order of multi_env.py:619-695
   int o = 0;
@@ -174,7 +178,7 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     ds.t_bytes = o;
   }
   // per-team scratch
-  ds.och = S <= 16 ? 16 : std::max(8, std::min(64, (4096 / S) & ~1));
+  ds.och = S <= 16 ? 16 : std::max(8, std::min(64, (2048 / S) & ~1));
   int d = 0;
   ds.d_lostW = d; d += R;
   ds.d_lostP = d; d += R;
@@ -184,11 +188,11 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
   int w = 0;
   const int WS = W * S;
   ds.w_inv = w; w += WS;
-  ds.w_dh = w; w += WS;
+  ds.w_dh = w; if (ds.dh_mode == 2) w += WS;
   ds.w_sh = w; if (ds.need_ship) w += WS;
   ds.w_st = w; if (ds.need_ship) w += WS;
   ds.w_shipq = w; w += W * R;
-  ds.w_cnt = w; w += W * R;
+  ds.w_cnt = w; if (ds.has_fixed) w += W * R;
   ds.w_lostN = w; w += R;
   ds.w_prio = w; w += (W + 3) / 4;
   ds.w_sreg = w; w += (ds.och + 1) / 2;
