@@ -1,3 +1,6 @@
+from .collector import Rollout, RolloutCollector, shard_envs
 from .gae import compute_gae, standardize_
+from .policy import ActorCritic, mlp
+from .ppo import PPOLearner
 
-__all__ = ["compute_gae", "standardize_"]
+__all__ = ["Rollout", "RolloutCollector", "shard_envs", "compute_gae", "standardize_", "ActorCritic", "mlp", "PPOLearner"]

@@ -1,0 +1,91 @@
+"""On-device rollout collection: policy forward (PyTorch) -> fused env step (CUDA) -> buffer, then the
+GAE scan kernel. Replaces RLlib's EnvRunner / MultiAgentEpisode / learner-connector chain that the
+reference configures (reference: src/algorithms/ippo.py:145-214, mappo.py:142-209).
+
+Buffers are time-major and preallocated; the env writes observations and rewards straight into them.
+Environments never interact, so a multi-GPU run shards them by rank with no communication here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+
+from ..envs import BatchedInventoryEnv, DeviceOrders
+from .gae import compute_gae, standardize_
+from .policy import ActorCritic
+
+
+@dataclass
+class Rollout:
+    obs: torch.Tensor        # [T+1, E, W, D]
+    actions: torch.Tensor    # [T, E, W, S] unclipped samples (what the log-prob refers to)
+    logp: torch.Tensor       # [T, E, W]
+    rewards: torch.Tensor    # [T, E, W]
+    values: torch.Tensor     # [T+1, E, W]
+    advantages: torch.Tensor  # [T, E, W]
+    targets: torch.Tensor    # [T, E, W]
+    cut: torch.Tensor        # [T] uint8, 1 where an episode ended after step t
+
+
+def shard_envs(total_envs: int, rank: int, world_size: int) -> range:
+    """Contiguous env range owned by ``rank``."""
+    base, extra = divmod(total_envs, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+class RolloutCollector:
+    def __init__(self, env: BatchedInventoryEnv, policy: ActorCritic, horizon: int, gamma: float = 0.99,
+                 lam: float = 0.95, demand_fn: Optional[Callable[[int], DeviceOrders]] = None,
+                 standardize_advantages: bool = True, seed: int = 0):
+        self.env, self.policy, self.T = env, policy, int(horizon)
+        self.gamma, self.lam = float(gamma), float(lam)
+        self.demand_fn = demand_fn            # step index -> DeviceOrders; None = env host samplers
+        self.standardize = standardize_advantages
+        E, W, S, D, dev = env.num_envs, env.n_warehouses, env.n_skus, env.obs_dim, env.device
+        T = self.T
+        self.obs = torch.empty((T + 1, E, W, D), device=dev)
+        self.actions = torch.empty((T, E, W, S), device=dev)
+        self.logp = torch.empty((T, E, W), device=dev)
+        self.rewards = torch.empty((T, E, W), device=dev)
+        self.values = torch.empty((T + 1, E, W), device=dev)
+        self.cut_values = torch.zeros((T, E, W), device=dev)
+        self.adv = torch.empty((T, E, W), device=dev)
+        self.targets = torch.empty((T, E, W), device=dev)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+        self._need_reset = True
+        self.total_steps = 0
+
+    @torch.no_grad()
+    def collect(self) -> Rollout:
+        env, pol, T = self.env, self.policy, self.T
+        cut_host = [0] * T
+        if self._need_reset:
+            env.reset(obs_out=self.obs[0])
+            self._need_reset = False
+        else:
+            self.obs[0].copy_(self.obs[T])
+        any_cut = False
+        for t in range(T):
+            act, logp, val = pol.act(self.obs[t], generator=self.gen)
+            self.actions[t], self.logp[t], self.values[t] = act, logp, val
+            orders = self.demand_fn(self.total_steps) if self.demand_fn is not None else None
+            _, _, truncated = env.step(act.contiguous(), orders=orders, obs_out=self.obs[t + 1], rewards_out=self.rewards[t])
+            self.total_steps += 1
+            if truncated:
+                # the final observation bootstraps the value target (RLlib appends it to the episode); the
+                # next episode then starts from a fresh reset
+                cut_host[t] = 1
+                any_cut = True
+                self.cut_values[t] = pol.value(self.obs[t + 1])
+                env.reset(obs_out=self.obs[t + 1])
+        self.values[T] = pol.value(self.obs[T])
+        cut = torch.tensor(cut_host, dtype=torch.uint8, device=env.device)
+        compute_gae(self.rewards, self.values, self.gamma, self.lam, cut if any_cut else None,
+                    self.cut_values if any_cut else None, adv_out=self.adv, targets_out=self.targets)
+        if self.standardize:
+            standardize_(self.adv)
+        return Rollout(self.obs, self.actions, self.logp, self.rewards, self.values, self.adv, self.targets, cut)

@@ -1,0 +1,94 @@
+"""Actor-critic MLPs for the rollout path (plain PyTorch: the dense contractions go to cuBLAS).
+
+Mirrors what the reference's ``ActorCriticRLModule`` does for its shipped IPPO / MAPPO configs
+(reference: src/algorithms/models/rlmodules/base.py:150-275 network setup, :192-194 observation routing,
+:473-478 free log-std with floor, :514-584 forward): an MLP actor on the local observation producing the
+action means, a state-independent ``log_std`` parameter clamped from below, and an MLP critic on the
+local observation (IPPO) or on ``[local_i | global]`` (MAPPO, ``critic_obs_type: global``).
+
+The centralised critic never materialises the W-times duplicated ``[local_i | global]`` vector: its first
+layer is split into a local and a global block, ``W1 [local|global]^T = Wl local_i^T + Wg global^T``,
+and the global term is computed once per environment.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+_ACT = {"relu": nn.ReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid, "elu": nn.ELU, "selu": nn.SELU, "gelu": nn.GELU,
+        "swish": nn.SiLU, "mish": nn.Mish, "hard_swish": nn.Hardswish, "hard_sigmoid": nn.Hardsigmoid}
+
+
+def mlp(in_dim: int, hidden: Sequence[int], out_dim: int, activation: str = "relu",
+        output_activation: Optional[str] = None) -> nn.Sequential:
+    layers: List[nn.Module] = []
+    d = in_dim
+    for h in hidden:
+        layers += [nn.Linear(d, h), _ACT[activation]()]
+        d = h
+    layers.append(nn.Linear(d, out_dim))
+    if output_activation:
+        layers.append(_ACT[output_activation]())
+    return nn.Sequential(*layers)
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, local_obs_dim: int, n_warehouses: int, action_dim: int, actor_hidden: Sequence[int] = (256,),
+                 critic_hidden: Sequence[int] = (256,), activation: str = "relu", critic_obs_type: str = "local",
+                 logstd_init: float = 0.0, logstd_floor: float = -2.0):
+        super().__init__()
+        self.local_obs_dim, self.n_warehouses, self.action_dim = local_obs_dim, n_warehouses, action_dim
+        self.critic_obs_type = critic_obs_type
+        self.logstd_floor = float(logstd_floor)
+        self.actor = mlp(local_obs_dim, actor_hidden, action_dim, activation)
+        self.log_std = nn.Parameter(torch.full((action_dim,), float(logstd_init)))
+        crit_in = local_obs_dim * (1 + n_warehouses) if critic_obs_type == "global" else local_obs_dim
+        self.critic = mlp(crit_in, critic_hidden, 1, activation)
+
+    @classmethod
+    def from_algorithm_config(cls, algo_config, local_obs_dim: int, n_warehouses: int, action_dim: int) -> "ActorCritic":
+        sp = algo_config.algorithm_specific
+        net = sp.networks
+        return cls(local_obs_dim, n_warehouses, action_dim, actor_hidden=net.actor.config.hidden_sizes,
+                   critic_hidden=net.critic.config.hidden_sizes, activation=net.actor.config.activation,
+                   critic_obs_type=getattr(sp, "critic_obs_type", "local"), logstd_init=sp.logstd_init,
+                   logstd_floor=sp.logstd_floor)
+
+    # obs: [E, W, D] local observations (flattened over W this is the global state)
+    def action_mean(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.actor(obs)
+
+    def std(self) -> torch.Tensor:
+        return torch.clamp(self.log_std, min=self.logstd_floor).exp()
+
+    def value(self, obs: torch.Tensor) -> torch.Tensor:
+        if self.critic_obs_type != "global":
+            return self.critic(obs).squeeze(-1)
+        E, W, D = obs.shape
+        first: nn.Linear = self.critic[0]
+        wl, wg = first.weight[:, :D], first.weight[:, D:]
+        h = obs @ wl.t() + (obs.reshape(E, W * D) @ wg.t()).unsqueeze(1) + first.bias
+        return self.critic[1:](h).squeeze(-1)
+
+    def act(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None, deterministic: bool = False
+            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(clipped action in [-1,1], log-prob of the unclipped sample, value) - RLlib samples the diagonal
+        Gaussian, stores its log-prob and clips the action it sends to the env (ippo.py:183-188)."""
+        mean = self.action_mean(obs)
+        std = self.std()
+        if deterministic:
+            raw = mean
+        else:
+            raw = mean + std * torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+        logp = self.log_prob(mean, raw)
+        return raw.clamp(-1.0, 1.0), logp, self.value(obs)
+
+    def log_prob(self, mean: torch.Tensor, raw_action: torch.Tensor) -> torch.Tensor:
+        log_std = torch.clamp(self.log_std, min=self.logstd_floor)
+        z = (raw_action - mean) / log_std.exp()
+        return (-0.5 * z * z - log_std - 0.9189385332046727).sum(-1)
+
+    def entropy(self) -> torch.Tensor:
+        return (torch.clamp(self.log_std, min=self.logstd_floor) + 1.4189385332046727).sum()

@@ -1,0 +1,269 @@
+"""CPU tests of the host-side boundary: YAML/config schema, component registry, seed derivation,
+order packing, spec building, policy modules and the C ABI's exported symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import marlsc_b200  # noqa: F401
+from golden.scenarios import allfeat_ratio_stochastic, large_network, small_default
+from marlsc_b200 import registry
+from marlsc_b200.config import (ConfigFileError, ConfigValidationError, algorithm_config_from_dict,
+                                environment_config_from_dict, load_algorithm_config, load_environment_config)
+from marlsc_b200.demand import pack_orders
+from marlsc_b200.seeds import ENVIRONMENT_SEEDS, SeedManager
+from marlsc_b200.spec import build_env_spec, local_obs_dim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+IPPO = dict(algorithm=dict(
+    name="ippo",
+    shared=dict(num_iterations=300, checkpoint_freq=100, batch_size=8000, num_epochs=20, num_minibatches=10,
+                learning_rate=5e-4, num_env_runners=2, num_envs_per_env_runner=10),
+    algorithm_specific=dict(use_gae=True, lam=0.95, gamma=0.99, clip_param=0.1, vf_clip_param=800.0, logstd_init=-1.15,
+                            logstd_floor=-3.5, obs_normalization="meanstd_custom", parameter_sharing=True,
+                            networks=dict(shared_layers=None, use_mu_sigma_head=False,
+                                          actor=dict(type="mlp", config=dict(hidden_sizes=[256], activation="relu")),
+                                          critic=dict(type="mlp", config=dict(hidden_sizes=[256], activation="relu"))))))
+
+
+# ------------------------------------------------------------------ config
+def test_env_yaml_roundtrip(tmp_path):
+    feats = tmp_path / "features.yaml"
+    env = small_default()
+    feats.write_text(yaml.safe_dump(dict(features=env.pop("features"))))
+    env["feature_config_path"] = str(feats)
+    path = tmp_path / "env.yaml"
+    path.write_text(yaml.safe_dump(dict(environment=env)))
+    cfg = load_environment_config(str(path))
+    assert (cfg.n_warehouses, cfg.n_skus, cfg.n_regions) == (3, 2, 3)
+    assert cfg.components.demand_allocator.params["max_splits"] == 2          # "default" -> W-1
+    assert cfg.features.rolling_demand_mean and not cfg.features.stockout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_reference_yaml_files_load_unmodified():
+    import glob
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        for f in glob.glob("config_files/environments/*.yaml"):
+            cfg = load_environment_config(f)
+            assert cfg.n_regions == cfg.n_warehouses
+        for f in ("ippo", "mappo", "ippo_test", "mappo_test", "cppo"):
+            algo = load_algorithm_config(f"config_files/algorithms/{f}.yaml")
+            assert 0.9 <= algo.algorithm_specific.gamma <= 1.0 and algo.shared.batch_size > 0
+    finally:
+        os.chdir(cwd)
+
+
+def test_legacy_max_order_quantities_migration():
+    env = small_default()
+    env.pop("action_space")
+    env["max_order_quantities"] = 40
+    cfg = environment_config_from_dict(env)
+    assert cfg.action_space.type == "direct" and cfg.action_space.params.max_order_quantities == [40, 40]
+
+
+def test_validation_rules():
+    env = small_default()
+    env["n_regions"] = 5
+    with pytest.raises(ConfigValidationError, match="must equal n_warehouses"):
+        environment_config_from_dict(env)
+    env = small_default()
+    env["features"]["pipeline"] = False
+    with pytest.raises(ConfigValidationError, match="pipeline must always be enabled"):
+        environment_config_from_dict(env)
+    env = small_default()
+    env["features"]["pipeline_aggregate"] = True
+    env["features"]["incoming_demand_home_aggregate"] = True
+    with pytest.raises(ConfigValidationError, match="cannot be enabled"):
+        environment_config_from_dict(env)
+    env = small_default()
+    env["components"]["demand_allocator"]["params"]["max_splits"] = 3
+    with pytest.raises(ConfigValidationError, match="max_splits must be <"):
+        environment_config_from_dict(env)
+    env = small_default()
+    env["components"]["lost_sales_handler"]["type"] = "nearest"
+    with pytest.raises(ConfigValidationError):
+        environment_config_from_dict(env)
+    with pytest.raises(ConfigFileError):
+        load_environment_config("/nonexistent/env.yaml")
+    big = large_network()
+    big["allow_region_mismatch"] = True
+    assert environment_config_from_dict(big).n_regions == 50
+
+
+def test_algorithm_config():
+    algo = algorithm_config_from_dict(IPPO)
+    assert algo.name == "ippo" and algo.algorithm_specific.lam == 0.95
+    assert algo.algorithm_specific.critic_obs_type == "local"
+    bad = algorithm_config_from_dict
+    d = {"algorithm": {**IPPO["algorithm"], "name": "mappo"}}
+    assert bad(d).algorithm_specific.critic_obs_type == "global"
+    d = {"algorithm": {**IPPO["algorithm"], "shared": {**IPPO["algorithm"]["shared"], "num_minibatches": 7}}}
+    with pytest.raises(ConfigValidationError, match="divisible"):
+        bad(d)
+
+
+# ------------------------------------------------------------------ registry / components
+def test_registry_names_and_errors():
+    assert set(registry.DEMAND_SAMPLER_REGISTRY) >= {"poisson", "empirical"}
+    assert set(registry.DEMAND_ALLOCATOR_REGISTRY) == {"greedy"}
+    assert set(registry.LEAD_TIME_SAMPLER_REGISTRY) == {"fixed", "stochastic"}
+    assert set(registry.LOST_SALES_HANDLER_REGISTRY) == {"closest", "shipment", "cost"}
+    assert set(registry.REWARD_CALCULATOR_REGISTRY) == {"cost"}
+    cfg = environment_config_from_dict(small_default())
+    alloc = registry.get_demand_allocator(cfg)
+    assert alloc.max_splits == 2
+    lt = registry.get_lead_time_sampler(cfg)
+    assert lt.get_max_expected() == 3 and np.array_equal(lt.sample(), lt.get_expected())
+    cfg.components.reward_calculator.__dict__["type"] = "profit"
+    with pytest.raises(ValueError, match=r"Unknown reward calculator: profit\. Available: \['cost'\]"):
+        registry.get_reward_calculator(cfg)
+
+
+def test_custom_component_registration():
+    from marlsc_b200.components import ShipmentLostSalesHandler
+
+    class Mine(ShipmentLostSalesHandler):
+        pass
+    registry.register_lost_sales_handler("mine", Mine)
+    try:
+        cfg = environment_config_from_dict(small_default())
+        cfg.components.lost_sales_handler.__dict__["type"] = "mine"
+        assert isinstance(registry.get_lost_sales_handler(cfg), Mine)
+    finally:
+        registry.LOST_SALES_HANDLER_REGISTRY.pop("mine")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_seed_manager_matches_reference():
+    from oracle import ref_harness as H
+    H.activate()
+    from src.utils.seed_manager import SeedManager as RefSM
+    a, b = SeedManager(123, ENVIRONMENT_SEEDS), RefSM(123, ENVIRONMENT_SEEDS)
+    for _ in range(3):
+        a.advance_episode()
+        b.advance_episode()
+        for name in ENVIRONMENT_SEEDS:
+            assert a.get_seed_int(name) == b.get_seed_int(name)
+            assert a.get_rng(name).integers(0, 1 << 30) == b.get_rng(name).integers(0, 1 << 30)
+    assert SeedManager.derive_env_seed(7, 1, 5) == RefSM.derive_env_seed(7, 1, 5)
+    assert a.spawn_child_seeds("inventory", 4) == b.spawn_child_seeds("inventory", 4)
+
+
+def test_seed_manager_basics():
+    sm = SeedManager(None, ENVIRONMENT_SEEDS)
+    assert sm.get_seed_int("inventory") is None
+    with pytest.raises(ValueError, match="not in registry"):
+        SeedManager(1, ENVIRONMENT_SEEDS).get_rng("train")
+    s1, s2 = SeedManager(5, ENVIRONMENT_SEEDS), SeedManager(5, ENVIRONMENT_SEEDS)
+    assert s1.get_rng("demand_sampler").random() == s2.get_rng("demand_sampler").random()
+
+
+def test_poisson_sampler_stream_is_golden():
+    """Seeded like the reference env, the host sampler must emit the orders recorded from the reference."""
+    from golden_io import Golden
+    g = Golden("small_default")
+    cfg = environment_config_from_dict(g.env)
+    for i in (0, 5):
+        sm = SeedManager(int(g["env_seeds"][i]), ENVIRONMENT_SEEDS)
+        sm.advance_episode()
+        smp = registry.get_demand_sampler(cfg)
+        smp.reset(sm.get_rng("demand_sampler"))
+        for t in range(5):
+            got = smp.sample(t)
+            exp = g.orders(i, t)
+            assert len(got) == len(exp)
+            for o, (r, q) in zip(got, exp):
+                assert o.region_id == r and np.array_equal(o.sku_demands, q)
+
+
+# ------------------------------------------------------------------ packing / spec
+def test_pack_orders():
+    b = pack_orders([[(1, [0, 3]), (2, [7, 0])], [], [(0, [1, 1])]], 2)
+    assert b.offsets.tolist() == [0, 2, 2, 3] and b.region.tolist() == [1, 2, 0]
+    assert b.qty.dtype == np.uint8 and b.qty[:3].tolist() == [[0, 3], [7, 0], [1, 1]]
+    assert (b.qty.size * b.qty.itemsize) % 16 == 0
+    assert pack_orders([[(0, [300, 1])]], 2).qty.dtype == np.uint16
+    with pytest.raises(ValueError):
+        pack_orders([[(0, [-1, 1])]], 2)
+    empty = pack_orders([[], []], 4)
+    assert empty.n_orders == 0 and empty.qty.nbytes >= 16
+
+
+def test_spec_tables():
+    cfg = environment_config_from_dict(allfeat_ratio_stochastic())
+    sp = build_env_spec(cfg, "ratio", None, True)
+    s = sp.scalars
+    assert s["lead_mode"] == 1 and s["ring_depth"] == 4 + 2 and s["max_expected_lead"] == 4
+    assert s["action_type"] == 1 and s["lost_sales_type"] == 0 and s["reward_scope"] == 1 and s["max_splits"] == 1
+    assert sp.tables["home_region"].tolist() == [0, 1, 2]
+    assert np.allclose(sp.tables["pen_rate"], 4.0 * np.array([0.5, 1.0, 2.0, 1.5, 0.25]))   # scalar * sku weight
+    assert np.allclose(sp.tables["hold_rate"], [0.5, 1.0, 0.25, 2.0, 1.5])                    # list: as is
+    assert local_obs_dim(cfg.features, 5, 4, 3, True) == 3 + 5 + 1 + 20 + 1 + 6 + 5 + 6 + 5 + 6 + 6 + 5 + 5 + 5 + 25
+    with pytest.raises(ValueError, match="obs_stats must have shape"):
+        build_env_spec(cfg, "meanstd_custom", (np.zeros(3), np.ones(3)), False)
+    with pytest.raises(ValueError, match="Unknown obs_normalization"):
+        build_env_spec(cfg, "zscore")
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    from marlsc_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "marlsc_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(marlsc_[a-z_0-9]+)\s*\(", header)))
+    assert "marlsc_env_step" in declared and "marlsc_gae" in declared and len(declared) >= 14
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/marlsc_b200.h but not exported"
+    assert _capi.lib().marlsc_abi_version() == _capi.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from marlsc_b200.rollout import compute_gae
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        BatchedInventoryEnv(environment_config_from_dict(small_default()), 4)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        compute_gae(torch.zeros(3, 4), torch.zeros(4, 4), 0.99, 0.95)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "marl-sc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "tests/emu" not in text.replace("tests/emu/emu.cpp", "")
+
+
+# ------------------------------------------------------------------ policy modules
+def test_actor_critic_shapes_and_split_critic():
+    from marlsc_b200.rollout import ActorCritic
+    algo = algorithm_config_from_dict({"algorithm": {**IPPO["algorithm"], "name": "mappo"}})
+    pol = ActorCritic.from_algorithm_config(algo, local_obs_dim=14, n_warehouses=3, action_dim=2)
+    obs = torch.randn(7, 3, 14)
+    act, logp, val = pol.act(obs)
+    assert act.shape == (7, 3, 2) and logp.shape == (7, 3) and val.shape == (7, 3)
+    assert float(act.abs().max()) <= 1.0
+    full = torch.cat([obs, obs.reshape(7, 1, 42).expand(7, 3, 42)], dim=2)        # reference layout
+    assert torch.allclose(pol.value(obs), pol.critic(full).squeeze(-1), atol=1e-5)
+    assert torch.allclose(pol.std(), torch.full((2,), float(np.exp(-1.15))), atol=1e-6)
+    pol.log_std.data.fill_(-10.0)
+    assert torch.allclose(pol.std(), torch.full((2,), float(np.exp(-3.5))), atol=1e-7)   # floor
+
+
+def test_shard_envs():
+    from marlsc_b200.rollout import shard_envs
+    parts = [shard_envs(10, r, 4) for r in range(4)]
+    assert [len(p) for p in parts] == [3, 3, 2, 2]
+    assert sorted(i for p in parts for i in p) == list(range(10))
