@@ -227,7 +227,7 @@ def run_reference(args):
     large = args.workload == "large"
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    n_env, seg = (1, 4) if large else (8, SEG)
+    n_env, seg = (4, 25) if large else (32, 100)          # per worker and bench step: a few seconds
     values = []
     for _ in range(args.warmup):
         cpu_port(env_dict, n_env, seg, workers)
@@ -438,7 +438,7 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         large = args.workload == "large"
-        n_env, seg = (2, 6) if large else (64, SEG)
+        n_env, seg = (48, 100) if large else (256, 100)      # ~10-20 s of single-core work
         v, n, wall = cpu_port(env_dict, n_env, seg, 1)
         cpu = dict(value=v, unit=UNIT, cores=1, kind="port",
                    sample=f"{n_env} envs x {seg} env steps + NumPy GAE, oracle/inventory_oracle.py, 1 process, {wall:.1f}s")
