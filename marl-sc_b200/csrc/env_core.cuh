@@ -41,7 +41,7 @@
 namespace marlsc {
 
 constexpr int kWindow = MARLSC_ROLLING_WINDOW;
-constexpr int kPipeBatch = 4;   // pipeline slots loaded together per cell
+constexpr int kPipeBatch = 5;   // pipeline slots loaded together per cell
 
 // Capabilities compiled into a kernel instantiation. The lean instantiation (kCapsLean) covers the
 // common configurations - fixed lead times, direct actions, unit SKU weights, static warehouse
@@ -65,6 +65,7 @@ enum : uint32_t {
   C_AGGX = 1u << 13,     // pipeline / home-demand / rolling-mean aggregates
   C_BIGW = 1u << 14,     // more than 32 warehouses (no home bitmask)
   C_DHSMEM = 1u << 15,   // home demand needed without a history plane (kept in shared memory)
+  C_LOSTCOST = 1u << 16, // softmax ("cost") lost-sales handler
 };
 constexpr uint32_t kCapsAll = 0xffffffffu;
 constexpr uint32_t kCapsLean = C_MEANSTD | C_IDHOT;
@@ -96,7 +97,7 @@ struct DevSpec {
   const uint32_t* home_mask;   // [R] bit w set when region r is warehouse w's home region (W <= 32), else null
   const uint8_t* lead_u8;      // [W*S] expected lead times as bytes
   const float* obs_mean;
-  const float* obs_std;
+  const float* obs_std;        // holds 1/std (precomputed on the host in float32)
   // observation block offsets inside one warehouse's vector (before the id prefix); -1 = block disabled
   int off_inv, off_pipe, off_dh, off_sh, off_sa, off_so, off_rm, off_fc, off_dos, off_nip, off_dv, off_hist;
   // per-CTA shared tables (byte offsets from the start of dynamic shared memory)
@@ -222,8 +223,8 @@ MDEV int pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 // ``out`` points at the first element after the optional one-hot id prefix.
 template <uint32_t CAPS>
 MDEV void emit(const DevSpec& sp, float* MARLSC_RESTRICT out, unsigned j, float x) {
-  // (x - mean) / std: the quotient uses the 2-ulp fast divide, far inside the 1e-5 parity tolerance
-  if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD) x = f_fastdiv(f_sub(x, sp.obs_mean[j]), sp.obs_std[j]);
+  // (x - mean) * (1/std): within 2 ulp of the reference's division, far inside the 1e-5 parity tolerance
+  if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD) x = f_mul(f_sub(x, sp.obs_mean[j]), sp.obs_std[j]);
   out[j] = x;
 }
 
@@ -306,7 +307,7 @@ MDEV int arrivals_stoch(const DevSpec& sp, const EnvPtrs& p, int t, int i) {
 template <uint32_t CAPS>
 MDEV int rescale_action(const DevSpec& sp, float a, double mx, int prev_home_demand, int pending) {
   if (!(CAPS & C_ACTX) || sp.action_type == MARLSC_ACTION_DIRECT) {
-    const float u = f_div(f_add(a, 1.0f), 2.0f);
+    const float u = f_mul(f_add(a, 1.0f), 0.5f);   // == (a + 1) / 2 exactly
     double q = d_rint(d_mul((double)u, mx));
     if (q < 0.0) q = 0.0;
     if (q > mx) q = mx;
@@ -317,7 +318,7 @@ MDEV int rescale_action(const DevSpec& sp, float a, double mx, int prev_home_dem
     const long long q = adj + (long long)prev_home_demand;
     return q < 0 ? 0 : (int)q;
   }
-  const float u = f_div(f_add(a, 1.0f), 2.0f);
+  const float u = f_mul(f_add(a, 1.0f), 0.5f);   // == (a + 1) / 2 exactly
   const double target = d_mul((double)u, mx);
   const double x = d_add(d_add(target, -(double)prev_home_demand), -(double)pending);
   const double q = d_rint(x);
@@ -325,6 +326,7 @@ MDEV int rescale_action(const DevSpec& sp, float a, double mx, int prev_home_dem
 }
 
 // Share of region r's lost volume attributed to warehouse w (lost_sales_handler.py:71-210).
+template <uint32_t CAPS>
 MDEV double lost_weight(const DevSpec& sp, const int32_t* s_shipq, const int32_t* s_lostN, const double* s_lostW,
                         int w, int r) {
   const int W = sp.W, R = sp.R;
@@ -335,6 +337,7 @@ MDEV double lost_weight(const DevSpec& sp, const int32_t* s_shipq, const int32_t
     if (tot > 0) return (double)s_shipq[w * R + r] / (double)tot;
     return sp.closest[r] == w ? 1.0 : 0.0;
   }
+  if (!(CAPS & C_LOSTCOST)) return 0.0;
   const double n = (double)s_lostN[r], lwt = s_lostW[r];
   double zmax = -1e300;
   for (int ww = 0; ww < W; ++ww) {
@@ -424,69 +427,57 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
   }
 
   // 2. pipeline, slot-major (L,S) ravel. Fixed leads: the order placed at tau sits in slot
-  //    tau + le - t, so slot k reads ring plane (t + k + 1 - le) mod D for k < le and is 0 otherwise.
-  float ptot_f[SPL];   // per-cell total in transit (needed by net inventory position)
-  MARLSC_UNROLL
-  for (int j = 0; j < SPL; ++j) ptot_f[j] = 0.f;
+  //    tau + le - t, so slot k reads ring plane (t + k + 1 - le) mod D for k < le and is 0 otherwise
+  //    (planes of placement steps < 0 have not been written since reset and read 0).
   if (sp.off_pipe >= 0) {
     const bool need_total = ratio || (F & MARLSC_F_PIPELINE_AGG);
-    const bool need_cell_total = off_nip >= 0;
     const int tm1 = (t + 1) % D;
-    int le[SPL], row0[SPL], lim[SPL];
-    unsigned cell[SPL];
-    const int32_t* const ring = p.ring_q;      // warp-uniform base; cells are addressed by 32-bit offsets
+    const int32_t* const ring = p.ring_q;      // pinned per-env base; cells are addressed by 32-bit offsets
     const unsigned WSu = (unsigned)WS, Su = (unsigned)S;
     float* MARLSC_RESTRICT const pout = pinned(out + sp.off_pipe);
-    MARLSC_UNROLL
-    for (int j = 0; j < SPL; ++j) {
-      const int s = tm.gl + G * j;
-      le[j] = s < S ? (int)tb.lead[base + s] : 0;   // 0 for lanes beyond S: every "k < le" test fails
-      const int r0 = tm1 - le[j];
-      row0[j] = r0 < 0 ? r0 + D : r0;          // ring plane of slot 0
-      lim[j] = s < S ? L : 0;                  // slots this lane writes
-      cell[j] = (unsigned)(base + s);
-    }
+    const bool ms = (CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD;
     float den = 1.0f;
     int total = 0;
     for (int pass = need_total ? 0 : 1; pass < 2; ++pass) {
       // pass 0 only sums (ratio denominator / aggregate), pass 1 writes
-      for (int k0 = 0; k0 < L; k0 += kPipeBatch) {
-        int v[SPL][kPipeBatch];
-        MARLSC_UNROLL
-        for (int j = 0; j < SPL; ++j) {
-          const int s = tm.gl + G * j;
+#ifndef MARLSC_HOST_EMU
+#pragma unroll 1
+#endif
+      for (int j = 0; j < SPL; ++j) {
+        const int s = tm.gl + G * j;
+        if (s >= S) break;
+        const unsigned cell = (unsigned)(base + s);
+        const int le = (int)tb.lead[cell];
+        int row0 = tm1 - le;                   // ring plane of slot 0
+        row0 += row0 < 0 ? D : 0;
+        for (int k0 = 0; k0 < L; k0 += kPipeBatch) {
+          int v[kPipeBatch];
           MARLSC_UNROLL
-          for (int kk = 0; kk < kPipeBatch; ++kk) {
+          for (int kk = 0; kk < kPipeBatch; ++kk) {       // loads of the batch first
             const int k = k0 + kk;
             int val = 0;
             if (fixed_lead) {
-              if (k < le[j]) {   // planes of placement steps < 0 have not been written since reset: they read 0
-                int row = row0[j] + k;
+              if (k < le) {
+                int row = row0 + k;
                 row -= row >= D ? D : 0;
-                val = ring[(unsigned)row * WSu + cell[j]];
+                val = ring[(unsigned)row * WSu + cell];
               }
-            } else if ((CAPS & C_STOCH) && k < lim[j]) {
-              val = pipeline_value_stoch(sp, p, t, base + s, le[j], k);
+            } else if ((CAPS & C_STOCH) && k < L) {
+              val = pipeline_value_stoch(sp, p, t, (int)cell, le, k);
             }
-            v[j][kk] = val;
+            v[kk] = val;
           }
-        }
-        MARLSC_UNROLL
-        for (int j = 0; j < SPL; ++j) {
-          const int s = tm.gl + G * j;
           MARLSC_UNROLL
           for (int kk = 0; kk < kPipeBatch; ++kk) {
             const int k = k0 + kk;
-            if (k < lim[j]) {
+            if (k < L) {
               if (pass == 0) {
-                total += v[j][kk];
+                total += v[kk];
               } else {
-                if ((CAPS & C_XFEAT) && need_cell_total) ptot_f[j] += (float)v[j][kk];
-                float x = (float)v[j][kk];
+                float x = (float)v[kk];
                 if (ratio) x = f_div(x, den);
                 const unsigned idx = (unsigned)k * Su + (unsigned)s;
-                if ((CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD)
-                  x = f_fastdiv(f_sub(x, sp.obs_mean[sp.off_pipe + idx]), sp.obs_std[sp.off_pipe + idx]);
+                if (ms) x = f_mul(f_sub(x, sp.obs_mean[sp.off_pipe + idx]), sp.obs_std[sp.off_pipe + idx]);
                 pout[idx] = x;
               }
             }
@@ -528,7 +519,18 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
       emit<CAPS>(sp, out, off_dos + s, (float)((double)vI[j] / (double)(vrm[j] > 1.0f ? vrm[j] : 1.0f)));
     // 10. net inventory position = on hand + in transit - forecast * expected lead
     if (off_nip >= 0) {
-      const double v = ((double)vI[j] + (double)ptot_f[j]) - (double)vfc[j] * (double)tb.lead[base + s];
+      const int le = (int)tb.lead[base + s];
+      float ptot = 0.f;                         // units in transit to this cell, summed slot by slot in float32
+      for (int k = 0; k < L; ++k) {
+        int val = 0;
+        if (fixed_lead) {
+          if (k < le) val = p.ring_q[pmod(t + k + 1 - le, D) * WS + base + s];
+        } else if (CAPS & C_STOCH) {
+          val = pipeline_value_stoch(sp, p, t, base + s, le, k);
+        }
+        ptot += (float)val;
+      }
+      const double v = ((double)vI[j] + (double)ptot) - (double)vfc[j] * (double)le;
       emit<CAPS>(sp, out, off_nip + s, (float)v);
     }
     // 11. demand variability: population std over the history window, float32 like np.std
@@ -886,8 +888,10 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         }
       }
     }
-    hold = tm.sum(hold);
-    inb = tm.sum(inb);
+    if (kDiag) {
+      hold = tm.sum(hold);
+      inb = tm.sum(inb);
+    }
 
     // outbound cost and penalty: lanes over regions
     double outc = 0.0, pen = 0.0;
@@ -900,11 +904,16 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
           outc += shw * sp.out_var[w * R + r];
           if (has_fixed) outc += (double)s_cnt[w * R + r] * sp.out_fixed[w * R + r];
         }
-        if (s_lostN[r] > 0) pen += lost_weight(sp, s_shipq, s_lostN, s_lostW, w, r) * s_lostP[r];
+        if (s_lostN[r] > 0) pen += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * s_lostP[r];
       }
     }
-    outc = tm.sum(outc);
-    pen = tm.sum(pen);
+    if (kDiag) {
+      outc = tm.sum(outc);
+      pen = tm.sum(pen);
+    } else {
+      hold = tm.sum((hold + inb) + (outc + pen));              // one reduction for the whole cost
+      inb = outc = pen = 0.0;
+    }
     if (tm.gl == 0) {
       s_ctot[w] = hold + pen + outc + inb;
       if (kDiag && io.cost_breakdown) {
@@ -941,7 +950,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       double acc = 0.0;
       for (int r = 0; r < R; ++r) {
         const int u = io.d_unfulfilled[(e * R + r) * S + s];
-        if (u != 0) acc += lost_weight(sp, s_shipq, s_lostN, s_lostW, w, r) * (double)u;
+        if (u != 0) acc += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * (double)u;
       }
       io.d_lost_sales[e * WS + i] = (float)acc;
     }

@@ -20,23 +20,16 @@ struct LaunchArgs {
 
 __device__ __forceinline__ Tables stage_tables(const DevSpec& sp, unsigned char* smem) {
   // cooperative copy of the per-CTA lookup tables (a few KB, L2 resident) into shared memory
-  auto copy = [&](int at, const void* src, int bytes) {
-    const unsigned char* s = static_cast<const unsigned char*>(src);
-    if ((bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
-      const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s);
-      uint32_t* d4 = reinterpret_cast<uint32_t*>(smem + at);
-      for (int i = threadIdx.x; i < (bytes >> 2); i += blockDim.x) d4[i] = s4[i];
-    } else {
-      for (int i = threadIdx.x; i < bytes; i += blockDim.x) smem[at + i] = s[i];
-    }
-  };
-  copy(sp.t_skw, sp.skw, sp.S * 8);
-  copy(sp.t_pen, sp.pen_rate, sp.S * 8);
-  copy(sp.t_hold, sp.hold_rate, sp.S * 8);
-  copy(sp.t_prio, sp.prio, sp.R * sp.W);
-  copy(sp.t_pstat, sp.prio_static, sp.R);
-  if (sp.home_mask) copy(sp.t_hmask, sp.home_mask, sp.R * 4);
-  copy(sp.t_lead, sp.lead_u8, sp.W * sp.S);
+  const void* src[7] = {sp.skw, sp.pen_rate, sp.hold_rate, sp.prio, sp.prio_static, sp.home_mask, sp.lead_u8};
+  const int at[7] = {sp.t_skw, sp.t_pen, sp.t_hold, sp.t_prio, sp.t_pstat, sp.t_hmask, sp.t_lead};
+  const int bytes[7] = {sp.S * 8, sp.S * 8, sp.S * 8, sp.R * sp.W, sp.R, sp.home_mask ? sp.R * 4 : 0, sp.W * sp.S};
+#pragma unroll 1
+  for (int k = 0; k < 7; ++k) {
+    // every table starts 16-byte aligned in the device blob and in shared memory and is padded to 16
+    const uint32_t* s4 = static_cast<const uint32_t*>(src[k]);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(smem + at[k]);
+    for (int i = threadIdx.x; i < ((bytes[k] + 3) >> 2); i += blockDim.x) d4[i] = s4[i];
+  }
   Tables tb;
   tb.skw = reinterpret_cast<const double*>(smem + sp.t_skw);
   tb.pen = reinterpret_cast<const double*>(smem + sp.t_pen);

@@ -162,6 +162,7 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     if (!sp.obs_mean || !sp.obs_std) return "obs_norm MEANSTD needs obs_mean and obs_std";
     tb.obs_mean.assign(sp.obs_mean, sp.obs_mean + dim_noid);
     tb.obs_std.assign(sp.obs_std, sp.obs_std + dim_noid);
+    for (float& v : tb.obs_std) v = 1.0f / v;                  // kernels multiply by the reciprocal
   }
 
   // per-CTA lookup tables staged in shared memory (byte offsets, 16-byte aligned blocks)
