@@ -48,7 +48,7 @@ constexpr bool has_lean(int G, int SPL) {
 }
 
 template <int G, int SPL, uint32_t CAPS>
-__global__ void __launch_bounds__(kBlock, (CAPS == kCapsLean && G == 32) ? 5 : 1)
+__global__ void __launch_bounds__(kBlock, (CAPS == kCapsLean && G == 32) ? 6 : 1)
 env_step_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                 const __grid_constant__ marlsc_step_io_t io, int t) {
   extern __shared__ __align__(16) unsigned char smem[];

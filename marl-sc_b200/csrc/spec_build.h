@@ -179,7 +179,7 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     ds.t_bytes = o;
   }
   // per-team scratch
-  ds.och = S <= 16 ? 16 : std::max(8, std::min(64, (2048 / S) & ~1));
+  ds.och = S <= 16 ? 16 : std::max(8, std::min(64, (1280 / S) & ~1));
   int d = 0;
   ds.d_lostW = d; d += R;
   ds.d_lostP = d; d += R;
