@@ -348,64 +348,51 @@ def run_ours(args):
     # ---- end to end through the host-buffer C-ABI call (marlsc_env_step_host) --------------------
     e2e = None
     if not args.no_e2e:
-        import ctypes as C
+        from marlsc_b200.envs import HostRollout
         n_host = min(n_in, 4)
         h_act = [a.cpu().pin_memory() for a in actions[:n_host]]
         h_off = [dm.offsets.cpu().pin_memory() for dm in demand[:n_host]]
         h_reg = [dm.region.cpu().pin_memory() for dm in demand[:n_host]]
         h_qty = [dm.qty.cpu().pin_memory() for dm in demand[:n_host]]
+        h_n = [dm.n_orders for dm in demand[:n_host]]
         h_rew = torch.empty((SEG, E, W)).pin_memory()
         h_val = values.cpu().pin_memory()
         h_adv, h_tgt = torch.empty((SEG, E, W)).pin_memory(), torch.empty((SEG, E, W)).pin_memory()
-        max_orders = max(dm.n_orders for dm in demand[:n_host])
-        s_act = torch.empty((E, W, S), device=dev)
-        s_off = torch.empty(E + 1, dtype=torch.int32, device=dev)
-        s_reg = torch.empty(max(1, max_orders), dtype=torch.int16, device=dev)
-        s_qty = torch.empty(max(16, max_orders * S + 16), dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        h2d = d2h = 0
+        hr = HostRollout(env, max(h_n))
+        idx = [i % n_host for i in range(SEG)]
+        seg_in = ([h_act[i] for i in idx], [h_off[i] for i in idx], [h_reg[i] for i in idx], [h_qty[i] for i in idx],
+                  [h_n[i] for i in idx])
+        h2d_seg = sum(h_act[i].numel() * 4 + h_off[i].numel() * 4 + h_n[i] * (2 + S) for i in idx) + h_val.numel() * 4
+        d2h_seg = SEG * E * W * 4 + 2 * h_adv.numel() * 4
 
-        def host_segment(cnt):
-            nonlocal h2d, d2h
-            for i in range(SEG):
-                if env.timestep >= env.episode_length:
-                    env.reset(obs_out=obs_buf[0])
-                j = cnt[0] % n_host
-                io = _capi.StepIOC(s_act.data_ptr(), s_off.data_ptr(), s_reg.data_ptr(), s_qty.data_ptr(), 1, None,
-                                   rewards[i].data_ptr(), obs_buf[cnt[0] & 1].data_ptr(), env.truncated.data_ptr(),
-                                   None, None, None, None, None, None, None)
-                hs = _capi.HostStepC(h_act[j].data_ptr(), h_off[j].data_ptr(), h_reg[j].data_ptr(), h_qty[j].data_ptr(),
-                                     demand[j].n_orders, None, h_rew[i].data_ptr(), None)
-                _capi.check(L.marlsc_env_step_host(env._h, C.byref(env._state), C.byref(io), C.byref(hs), env.timestep, stream))
-                env.timestep += 1
-                cnt[0] += 1
-                h2d += h_act[j].numel() * 4 + h_off[j].numel() * 4 + demand[j].n_orders * (2 + S)
-                d2h += E * W * 4
+        def host_segment():
+            if env.timestep + SEG > env.episode_length:
+                env.reset(obs_out=obs_buf[0])
+            hr.run(*seg_in, h_rew, rewards)                       # SEG steps: host actions+orders in, rewards out
             values.copy_(h_val, non_blocking=True)
             compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
             h_adv.copy_(adv, non_blocking=True)
             h_tgt.copy_(tgt, non_blocking=True)
             torch.cuda.synchronize()
-            h2d += h_val.numel() * 4
-            d2h += 2 * h_adv.numel() * 4
 
-        cnt = [0]
         e2e_steps = max(1, min(args.steps, 3))
-        host_segment(cnt)
-        h2d = d2h = 0
+        host_segment()
+        launches_e2e0 = L.marlsc_launch_count()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            host_segment(cnt)
+            host_segment()
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
             tm = torch.tensor([dt], device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dt = float(tm.item())
-        e2e = dict(value=E * W * SEG * e2e_steps * world / dt, unit=UNIT, h2d_bytes_per_step=h2d // e2e_steps,
-                   d2h_bytes_per_step=d2h // e2e_steps, api="marlsc_env_step_host (pinned host actions+orders in, rewards out) "
-                   "+ marlsc_gae, advantages/targets copied out", segments=e2e_steps)
+        e2e = dict(value=E * W * SEG * e2e_steps * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d_seg),
+                   d2h_bytes_per_step=int(d2h_seg), ms_per_step=1e3 * dt / e2e_steps,
+                   api="marlsc_env_rollout_host (pinned host actions+orders in per env step, copies overlapped with the "
+                       "step kernels, rewards out) + marlsc_gae (host values in, advantages/targets out)",
+                   segments=e2e_steps, gpu_launches=int(L.marlsc_launch_count() - launches_e2e0))
 
     if rank != 0:
         if world > 1:

@@ -202,6 +202,17 @@ typedef struct marlsc_host_step {
 int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* dev_staging,
                          const marlsc_host_step_t* host, int32_t t, void* stream);
 
+/* A rollout segment of n_steps consecutive timesteps t0 .. t0+n_steps-1 driven from HOST buffers, with
+ * the host->device copies of step i+1 overlapped with the kernel of step i (two device staging sets, an
+ * internal copy stream). host[i] describes step i (pinned memory strongly recommended); staging[0..1] are
+ * two device staging sets like the one marlsc_env_step_host takes, except that rewards / obs of step i
+ * are written to rewards_dev + i*E*W (time-major rollout buffer) and obs_dev[i & 1]; rewards are copied
+ * back to host[i].rewards. Returns after everything is on the host. Replaces n_steps calls of
+ * InventoryEnvironment.step (multi_env.py:253-366) made from host-side actions and demand. */
+int marlsc_env_rollout_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t staging[2],
+                            const marlsc_host_step_t* host, int32_t n_steps, int32_t t0, float* rewards_dev,
+                            void* stream);
+
 /* Reverse-time GAE(lambda) / value-target scan over a rollout segment, one column per
  * (environment, agent). Replaces RLlib's GeneralAdvantageEstimation connector that the reference
  * configures through use_gae / lambda_ / gamma (src/algorithms/ippo.py:145-160, mappo.py:142-157).

@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
     L.marlsc_env_step.restype = C.c_int
     L.marlsc_env_step_host.argtypes = [vp, C.POINTER(EnvStateC), C.POINTER(StepIOC), C.POINTER(HostStepC), i32, vp]
     L.marlsc_env_step_host.restype = C.c_int
+    L.marlsc_env_rollout_host.argtypes = [vp, C.POINTER(EnvStateC), C.POINTER(StepIOC), C.POINTER(HostStepC), i32, i32, vp, vp]
+    L.marlsc_env_rollout_host.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.marlsc_gae.restype = C.c_int
     L.marlsc_standardize_workspace_bytes.argtypes = []

@@ -33,6 +33,9 @@ struct marlsc_env {
   void* d_blob = nullptr;  // one allocation holding every device table
   int max_smem_optin = 0;
   int force_generic = 0;   // tests: always run the generic instantiation
+  cudaStream_t copy_stream = nullptr;        // marlsc_env_rollout_host: H2D copies of the next step
+  cudaEvent_t ready[2] = {nullptr, nullptr};  // staging set filled
+  cudaEvent_t done[2] = {nullptr, nullptr};   // staging set consumed by its step kernel
 };
 
 namespace {
@@ -184,6 +187,11 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
 
 void marlsc_env_destroy(marlsc_env_t* env) {
   if (!env) return;
+  if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (env->ready[i]) cudaEventDestroy(env->ready[i]);
+    if (env->done[i]) cudaEventDestroy(env->done[i]);
+  }
   if (env->d_blob) cudaFree(env->d_blob);
   delete env;
 }
@@ -261,6 +269,56 @@ int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, con
   MARLSC_CUDA(cudaMemcpyAsync(host->rewards, dev->rewards, sizeof(float) * E * env->ds.W, cudaMemcpyDeviceToHost, s));
   if (host->obs) MARLSC_CUDA(cudaMemcpyAsync(host->obs, dev->obs, sizeof(float) * E * env->ds.W * env->ds.obs_dim, cudaMemcpyDeviceToHost, s));
   MARLSC_CUDA(cudaStreamSynchronize(s));
+  return MARLSC_OK;
+}
+
+int marlsc_env_rollout_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t staging[2],
+                            const marlsc_host_step_t* host, int32_t n_steps, int32_t t0, float* rewards_dev, void* stream) {
+  int rc = check_state(env, state);
+  if (rc) return rc;
+  if (!staging || !host || !rewards_dev) return set_error(MARLSC_EINVAL, "null staging, host descriptors or rewards_dev");
+  if (n_steps < 1 || t0 < 0) return set_error(MARLSC_EINVAL, "n_steps must be positive and t0 >= 0");
+  MARLSC_CUDA(cudaSetDevice(env->device));
+  if (!env->copy_stream) {
+    MARLSC_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      MARLSC_CUDA(cudaEventCreateWithFlags(&env->ready[i], cudaEventDisableTiming));
+      MARLSC_CUDA(cudaEventCreateWithFlags(&env->done[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t cs = static_cast<cudaStream_t>(stream), cp = env->copy_stream;
+  const int64_t E = state->num_envs, WS = (int64_t)env->ds.W * env->ds.S, W = env->ds.W;
+  const bool stoch = env->ds.lead_mode == MARLSC_LEAD_STOCHASTIC;
+  // the copy stream must not run ahead of work already queued on the caller's stream
+  MARLSC_CUDA(cudaEventRecord(env->done[0], cs));
+  MARLSC_CUDA(cudaEventRecord(env->done[1], cs));
+  for (int i = 0; i < n_steps; ++i) {
+    const int b = i & 1;
+    const marlsc_step_io_t& dv = staging[b];
+    const marlsc_host_step_t& h = host[i];
+    if (!h.actions || !h.order_offsets || !h.rewards) return set_error(MARLSC_EINVAL, "host step with NULL actions / offsets / rewards");
+    MARLSC_CUDA(cudaStreamWaitEvent(cp, env->done[b], 0));      // staging set b is free again
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<float*>(dv.actions), h.actions, sizeof(float) * E * WS, cudaMemcpyHostToDevice, cp));
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(dv.order_offsets), h.order_offsets, sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice, cp));
+    if (h.n_orders > 0) {
+      MARLSC_CUDA(cudaMemcpyAsync(const_cast<int16_t*>(dv.order_region), h.order_region, sizeof(int16_t) * h.n_orders, cudaMemcpyHostToDevice, cp));
+      MARLSC_CUDA(cudaMemcpyAsync(const_cast<void*>(dv.order_qty), h.order_qty, (size_t)h.n_orders * env->ds.S * dv.order_qty_bytes, cudaMemcpyHostToDevice, cp));
+    }
+    if (stoch) {
+      if (!h.actual_lead) return set_error(MARLSC_EINVAL, "host.actual_lead is required with a stochastic lead-time sampler");
+      MARLSC_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(dv.actual_lead), h.actual_lead, (size_t)E * WS, cudaMemcpyHostToDevice, cp));
+    }
+    MARLSC_CUDA(cudaEventRecord(env->ready[b], cp));
+    MARLSC_CUDA(cudaStreamWaitEvent(cs, env->ready[b], 0));
+    marlsc_step_io_t io = dv;
+    io.rewards = rewards_dev + (int64_t)i * E * W;
+    rc = marlsc_env_step(env, state, &io, t0 + i, stream);
+    if (rc) return rc;
+    MARLSC_CUDA(cudaEventRecord(env->done[b], cs));
+    MARLSC_CUDA(cudaMemcpyAsync(h.rewards, io.rewards, sizeof(float) * E * W, cudaMemcpyDeviceToHost, cs));
+    if (h.obs) MARLSC_CUDA(cudaMemcpyAsync(h.obs, io.obs, sizeof(float) * E * W * env->ds.obs_dim, cudaMemcpyDeviceToHost, cs));
+  }
+  MARLSC_CUDA(cudaStreamSynchronize(cs));
   return MARLSC_OK;
 }
 

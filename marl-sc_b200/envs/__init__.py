@@ -1,4 +1,4 @@
-from .batched_env import BatchedInventoryEnv, DeviceOrders
+from .batched_env import BatchedInventoryEnv, DeviceOrders, HostRollout
 from .multi_env import InventoryEnvironment
 
-__all__ = ["BatchedInventoryEnv", "DeviceOrders", "InventoryEnvironment"]
+__all__ = ["BatchedInventoryEnv", "DeviceOrders", "HostRollout", "InventoryEnvironment"]

@@ -311,3 +311,47 @@ class BatchedInventoryEnv:
         self._keep = (actions, orders, lead_t)   # keep inputs alive until the stream has consumed them
         self.timestep += 1
         return out, rew, self.timestep >= self.episode_length
+
+
+class HostRollout:
+    """Rollout segments driven from HOST buffers through ``marlsc_env_rollout_host``: the reference-facing
+    way to call the path (NumPy/pinned tensors in, rewards out) with the copies of step i+1 overlapped with
+    the kernel of step i. Holds the two device staging sets the C call needs."""
+
+    def __init__(self, env: BatchedInventoryEnv, max_orders_per_step: int, qty_bytes: int = 1):
+        self.env = env
+        E, W, S, dev = env.num_envs, env.n_warehouses, env.n_skus, env.device
+        self.qty_bytes = qty_bytes
+        self.max_orders = int(max_orders_per_step)
+        self.sets = []
+        for _ in range(2):
+            self.sets.append(dict(
+                actions=torch.empty((E, W, S), device=dev), offsets=torch.empty(E + 1, dtype=torch.int32, device=dev),
+                region=torch.empty(max(1, self.max_orders), dtype=torch.int16, device=dev),
+                qty=torch.empty(max(16, self.max_orders * S * qty_bytes + 16), dtype=torch.uint8, device=dev),
+                lead=torch.empty((E, W, S), dtype=torch.uint8, device=dev) if env.stochastic_lead else None,
+                obs=torch.empty_like(env.obs)))
+        self._staging = (_capi.StepIOC * 2)()
+        for i, st in enumerate(self.sets):
+            self._staging[i] = _capi.StepIOC(st["actions"].data_ptr(), st["offsets"].data_ptr(), st["region"].data_ptr(),
+                                             st["qty"].data_ptr(), qty_bytes, _ptr(st["lead"]), None, st["obs"].data_ptr(),
+                                             env.truncated.data_ptr(), None, None, None, None, None, None, None)
+
+    def run(self, actions, offsets, regions, qtys, n_orders, rewards_host, rewards_dev, leads=None) -> torch.Tensor:
+        """Each argument is a per-step list of (pinned) host tensors; ``rewards_host`` / ``rewards_dev`` are
+        [T,E,W] float32 (pinned host / device). Steps the env T times starting at its current timestep and
+        returns the observation buffer that holds the last step's observations."""
+        env, T = self.env, len(actions)
+        if max(n_orders) > self.max_orders:
+            raise ValueError("a step has more orders than the staging buffers hold")
+        if env.timestep + T > env.episode_length:
+            raise ValueError("segment crosses the end of the episode; reset first")
+        hs = (_capi.HostStepC * T)()
+        for i in range(T):
+            hs[i] = _capi.HostStepC(actions[i].data_ptr(), offsets[i].data_ptr(), regions[i].data_ptr(), qtys[i].data_ptr(),
+                                    int(n_orders[i]), None if leads is None else leads[i].data_ptr(),
+                                    rewards_host[i].data_ptr(), None)
+        _capi.check(_capi.lib().marlsc_env_rollout_host(env._h, C.byref(env._state), self._staging, hs, T, env.timestep,
+                                                        rewards_dev.data_ptr(), env._stream()))
+        env.timestep += T
+        return self.sets[(T - 1) & 1]["obs"]

@@ -255,3 +255,29 @@ def test_rollout_collector_matches_manual_loop():
     before = pol.log_std.detach().clone()
     stats = learner.minibatch_step(ro, slice(0, 10), slice(0, 16))
     assert np.isfinite(stats["total"]) and not torch.equal(before, pol.log_std.detach())
+
+
+def test_pipelined_host_rollout_equals_stepwise():
+    """marlsc_env_rollout_host (double-buffered host->device copies overlapping the step kernels) must
+    give exactly what step-by-step calls give."""
+    from marlsc_b200.envs import BatchedInventoryEnv, HostRollout
+    g = Golden("small_default")
+    cfg, _ = spec_for(g)
+    T = 24
+    env = BatchedInventoryEnv(cfg, g.N, device="cuda:0", host_samplers=False)
+    env.reset(init_inventory=torch.from_numpy(g["init_inventory"]))
+    batches = [step_orders(g, t) for t in range(T)]
+    hr = HostRollout(env, max(b.n_orders for b in batches))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+    acts = [pin(g["actions"][:, t]) for t in range(T)]
+    offs = [pin(b.offsets) for b in batches]
+    regs = [pin(b.region) for b in batches]
+    qtys = [pin(b.qty) for b in batches]
+    r_host = torch.empty((T, g.N, g.W)).pin_memory()
+    r_dev = torch.empty((T, g.N, g.W), device="cuda:0")
+    obs = hr.run(acts, offs, regs, qtys, [b.n_orders for b in batches], r_host, r_dev)
+    np.testing.assert_allclose(r_host.numpy(), np.moveaxis(g["rewards"][:, :T], 0, 1), rtol=1e-5, atol=1e-6)
+    assert torch.equal(r_host, r_dev.cpu())
+    assert np.array_equal(env.inventory.cpu().numpy(), g["inventory"][:, T - 1])
+    np.testing.assert_allclose(obs.cpu().numpy(), g["obs_local"][:, T - 1], rtol=1e-5, atol=1e-6)
+    assert env.timestep == T
