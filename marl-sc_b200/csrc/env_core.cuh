@@ -66,6 +66,7 @@ enum : uint32_t {
   C_BIGW = 1u << 14,     // more than 32 warehouses (no home bitmask)
   C_DHSMEM = 1u << 15,   // home demand needed without a history plane (kept in shared memory)
   C_LOSTCOST = 1u << 16, // softmax ("cost") lost-sales handler
+  C_FIXED = 1u << 17,    // non-zero outbound fixed costs (per-(warehouse, region) shipment counts)
 };
 constexpr uint32_t kCapsAll = 0xffffffffu;
 constexpr uint32_t kCapsLean = C_MEANSTD | C_IDHOT;
@@ -609,7 +610,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   // accumulator of this step's home-region demand per (warehouse, SKU)
   const int dh_mode = (CAPS & C_DHSMEM) ? sp.dh_mode : (sp.dh_mode == 1 ? 1 : 0);
   int32_t* const dh_acc = dh_mode == 1 ? pinned(p.hist + (t % kWindow) * WS) : s_dh;
-  const bool has_fixed = sp.has_fixed;
+  const bool has_fixed = (CAPS & C_FIXED) && sp.has_fixed;
 
   // ---- phase 1: orders in, arrivals in (multi_env.py:287-292) ------------------------------------
   for (int w = 0; w < W; ++w) {
@@ -739,7 +740,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       }
       const uint8_t* prio;
       if (!(CAPS & C_DYNPRIO) || tb.pstat[r]) {
-        prio = tb.prio + r * W;
+        prio = tb.prio + r * ((W + 3) & ~3);
       } else {
         // warehouse order depends on the order's weight: key = fixed + variable * weight in float64,
         // stable ascending (demand_allocator.py:168-173; ties to the lowest index)
@@ -767,11 +768,25 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         tm.sync();
         prio = s_prio;
       }
+      // the order's priority list, four warehouses per register (W <= 16 in the packed form)
+      uint32_t pk[4] = {0u, 0u, 0u, 0u};
+      const bool packed = W <= 16;
+      if (packed) {
+        MARLSC_UNROLL
+        for (int q4 = 0; q4 < 4; ++q4)
+          if (q4 * 4 < W) pk[q4] = reinterpret_cast<const uint32_t*>(prio)[q4];   // rows are 4-byte aligned, see spec_build.h
+      }
       int used = 0;
       bool left = true;
       for (int v = 0; v < W; ++v) {
         if (used >= sp.max_splits + 1) break;
-        const int w = prio[v];
+        int w;
+        if (packed) {
+          const uint32_t word = (v & 8) ? ((v & 4) ? pk[3] : pk[2]) : ((v & 4) ? pk[1] : pk[0]);
+          w = (int)((word >> ((v & 3) * 8)) & 0xffu);
+        } else {
+          w = prio[v];
+        }
         int32_t* inv_w = s_inv + w * S;
         const bool is_home = need_ship && (sp.home[w] == r);
         int fsum = 0, rsum = 0;

@@ -22,7 +22,7 @@ __device__ __forceinline__ Tables stage_tables(const DevSpec& sp, unsigned char*
   // cooperative copy of the per-CTA lookup tables (a few KB, L2 resident) into shared memory
   const void* src[7] = {sp.skw, sp.pen_rate, sp.hold_rate, sp.prio, sp.prio_static, sp.home_mask, sp.lead_u8};
   const int at[7] = {sp.t_skw, sp.t_pen, sp.t_hold, sp.t_prio, sp.t_pstat, sp.t_hmask, sp.t_lead};
-  const int bytes[7] = {sp.S * 8, sp.S * 8, sp.S * 8, sp.R * sp.W, sp.R, sp.home_mask ? sp.R * 4 : 0, sp.W * sp.S};
+  const int bytes[7] = {sp.S * 8, sp.S * 8, sp.S * 8, sp.R * ((sp.W + 3) & ~3), sp.R, sp.home_mask ? sp.R * 4 : 0, sp.W * sp.S};
 #pragma unroll 1
   for (int k = 0; k < 7; ++k) {
     // every table starts 16-byte aligned in the device blob and in shared memory and is padded to 16

@@ -98,7 +98,8 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
   for (int v : tb.region_map) if (v < 0 || v >= R) return "region_map entry out of range";
 
   // static priority: when the fixed cost column is constant the order never depends on the weight
-  tb.prio.assign((size_t)R * W, 0);
+  const int Wp = (W + 3) & ~3;                                   // priority rows are padded to whole 32-bit words
+  tb.prio.assign((size_t)R * Wp, 0);
   tb.prio_static.assign(R, 0);
   for (int r = 0; r < R; ++r) {
     bool constant = true;
@@ -107,7 +108,7 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     std::vector<int> idx(W);
     for (int w = 0; w < W; ++w) idx[w] = w;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return tb.out_var[a * R + r] < tb.out_var[b * R + r]; });
-    for (int w = 0; w < W; ++w) tb.prio[(size_t)r * W + w] = (uint8_t)idx[w];
+    for (int w = 0; w < W; ++w) tb.prio[(size_t)r * Wp + w] = (uint8_t)idx[w];
   }
 
   tb.home_mask.clear();
@@ -172,7 +173,7 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     ds.t_skw = blk(S * 8);
     ds.t_pen = blk(S * 8);
     ds.t_hold = blk(S * 8);
-    ds.t_prio = blk(R * W);
+    ds.t_prio = blk(R * ((W + 3) & ~3));
     ds.t_pstat = blk(R);
     ds.t_hmask = blk(W <= 32 ? R * 4 : 0);
     ds.t_lead = blk(W * S);
