@@ -69,6 +69,15 @@ int emu_env_reset(void* h, const marlsc_env_state_t* st, const int32_t* init, in
   return MARLSC_OK;
 }
 
+int emu_env_step_lean(void* h, const marlsc_env_state_t* st, const marlsc_step_io_t* io, int t) {
+  EmuEnv* e = static_cast<EmuEnv*>(h);
+  Team<1> tm;
+  tm.init();
+  Scratch sc{e->sd.data(), e->sw.data()};
+  for (int64_t i = 0; i < st->num_envs; ++i) step_env<1, kEmuSpl, kCapsLean>(e->ds, e->tabs, tm, sc, *st, *io, i, t);
+  return MARLSC_OK;
+}
+
 int emu_env_step(void* h, const marlsc_env_state_t* st, const marlsc_step_io_t* io, int t) {
   EmuEnv* e = static_cast<EmuEnv*>(h);
   Team<1> tm;

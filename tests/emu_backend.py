@@ -34,6 +34,7 @@ def emu_lib():
     L.emu_env_create.argtypes = [C.POINTER(_capi.EnvSpecC), C.POINTER(C.c_void_p)]
     L.emu_env_reset.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.c_void_p, C.c_int, C.c_void_p]
     L.emu_env_step.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.POINTER(_capi.StepIOC), C.c_int]
+    L.emu_env_step_lean.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.POINTER(_capi.StepIOC), C.c_int]
     L.emu_env_destroy.argtypes = [C.c_void_p]
     L.emu_env_destroy.restype = None
     for fn in ("emu_env_obs_dim", "emu_env_needs_history", "emu_env_needs_forecast"):
@@ -74,6 +75,17 @@ class EmuBatch:
         per_env = int(init.ndim == 3)
         assert emu_lib().emu_env_reset(self.h, C.byref(self.state), _p(init), per_env, _p(obs)) == 0
         return obs
+
+    def step_lean(self, t: int, actions: np.ndarray, orders: OrderBatch) -> Dict[str, np.ndarray]:
+        """The lean kernel instantiation (no diagnostics): inventory, rewards, observations, truncation only."""
+        E, W = self.E, self.W
+        act = np.ascontiguousarray(actions, dtype=np.float32)
+        o = dict(rewards=np.zeros((E, W), np.float32), obs=np.zeros((E, W, self.obs_dim), np.float32), trunc=np.zeros(E, np.uint8))
+        io = _capi.StepIOC(_p(act), _p(orders.offsets), _p(orders.region), _p(orders.qty), orders.qty_bytes, None,
+                           _p(o["rewards"]), _p(o["obs"]), _p(o["trunc"]), None, None, None, None, None, None, None)
+        assert emu_lib().emu_env_step_lean(self.h, C.byref(self.state), C.byref(io), t) == 0
+        o["inventory"] = self.inv.copy()
+        return o
 
     def step(self, t: int, actions: np.ndarray, orders: OrderBatch, leads: Optional[np.ndarray]) -> Dict[str, np.ndarray]:
         E, W, S, R = self.E, self.W, self.S, self.R

@@ -36,3 +36,16 @@ def test_emu_region_map_equals_premapped_demand():
         shifted = step_orders(g, t, region_shift=lambda i, tt, j: R * ((i + tt + j) % 2))
         compare_step(g, t, b.step(t, g["actions"][:, t], shifted, None), what="emu remap ")
     b.close()
+
+
+@pytest.mark.parametrize("name", ["small_default", "regions_ne_warehouses", "large_network"])
+def test_emu_lean_instantiation_matches_reference(name):
+    """Configurations the lean kernel instantiation covers (independent per-SKU allocation chains, no
+    diagnostics) replayed through it on the CPU."""
+    g = Golden(name)
+    _, spec = spec_for(g)
+    b = EmuBatch(spec, g.N)
+    b.reset(g["init_inventory"])
+    for t in range(g.T):
+        compare_step(g, t, b.step_lean(t, g["actions"][:, t], step_orders(g, t)), what="emu lean ")
+    b.close()
