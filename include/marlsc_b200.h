@@ -152,6 +152,10 @@ typedef struct marlsc_step_io {
   int32_t* d_unfulfilled;        /* [E,R,S] */
   int32_t* d_lost_orders;        /* [E,R] */
   float* d_lost_sales;           /* [E,W,S] needs d_unfulfilled */
+  /* padded order layout (what marlsc_demand_sample writes): when order_counts != NULL, env e owns rows
+   * [e*order_stride, e*order_stride + order_counts[e]) of order_region / order_qty and order_offsets is ignored */
+  const int32_t* order_counts;   /* [E] or NULL */
+  int32_t order_stride;
 } marlsc_step_io_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -212,6 +216,27 @@ int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, con
 int marlsc_env_rollout_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t staging[2],
                             const marlsc_host_step_t* host, int32_t n_steps, int32_t t0, float* rewards_dev,
                             void* stream);
+
+/* ---- on-device samplers and heuristic policies -------------------------------- */
+
+/* Device Poisson demand sampler: same distribution as the reference's PoissonDemandSampler
+ * (src/environment/components/demand_sampler.py:105-163; parameters broadcast to [R], [R], [R,S]), Philox
+ * counter-based stream keyed by (seed, env, step) - reproducible, but not the reference's PCG64 stream. */
+typedef struct marlsc_demand marlsc_demand_t;
+int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda_orders, const double* probability_skus,
+                         const double* lambda_quantity, int device, marlsc_demand_t** out);
+void marlsc_demand_destroy(marlsc_demand_t* d);
+/* Draw one step of orders for num_envs environments into the padded layout: order_counts [E],
+ * order_region [E*max_orders_per_env], order_qty uint8 [E*max_orders_per_env, S]. Orders beyond
+ * max_orders_per_env are dropped and *overflow_flag (device int32, caller-zeroed) is set to 1. */
+int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t max_orders_per_env,
+                         int32_t* order_counts, int16_t* order_region, uint8_t* order_qty, int32_t* overflow_flag, void* stream);
+
+/* Batched base-stock heuristic (reference: make_bs_newsvendor_action_fn, src/experiments/run_baselines.py:133-207):
+ * actions[e,w,s] = 2*clip(level[w,s] - on_hand - in_transit, 0, max_qty[s])/max_qty[s] - 1 evaluated before step t.
+ * level: device float32 [W,S]; actions: device float32 [E,W,S]. Direct action space only. */
+int marlsc_policy_base_stock(marlsc_env_t* env, const marlsc_env_state_t* state, const float* level, int32_t t,
+                             float* actions, void* stream);
 
 /* Reverse-time GAE(lambda) / value-target scan over a rollout segment, one column per
  * (environment, agent). Replaces RLlib's GeneralAdvantageEstimation connector that the reference

@@ -56,7 +56,7 @@ class StepIOC(C.Structure):
                 ("rewards", C.c_void_p), ("obs", C.c_void_p), ("truncated", C.c_void_p),
                 ("cost_breakdown", C.c_void_p), ("d_ordered", C.c_void_p), ("d_ship", C.c_void_p),
                 ("d_ship_count", C.c_void_p), ("d_unfulfilled", C.c_void_p), ("d_lost_orders", C.c_void_p),
-                ("d_lost_sales", C.c_void_p)]
+                ("d_lost_sales", C.c_void_p), ("order_counts", C.c_void_p), ("order_stride", C.c_int32)]
 
 
 class HostStepC(C.Structure):
@@ -103,6 +103,14 @@ def lib() -> C.CDLL:
     L.marlsc_env_step_host.restype = C.c_int
     L.marlsc_env_rollout_host.argtypes = [vp, C.POINTER(EnvStateC), C.POINTER(StepIOC), C.POINTER(HostStepC), i32, i32, vp, vp]
     L.marlsc_env_rollout_host.restype = C.c_int
+    L.marlsc_demand_create.argtypes = [i32, i32, _pd, _pd, _pd, C.c_int, C.POINTER(vp)]
+    L.marlsc_demand_create.restype = C.c_int
+    L.marlsc_demand_destroy.argtypes = [vp]
+    L.marlsc_demand_destroy.restype = None
+    L.marlsc_demand_sample.argtypes = [vp, i64, C.c_uint64, i64, i32, vp, vp, vp, vp, vp]
+    L.marlsc_demand_sample.restype = C.c_int
+    L.marlsc_policy_base_stock.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
+    L.marlsc_policy_base_stock.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.marlsc_gae.restype = C.c_int
     L.marlsc_standardize_workspace_bytes.argtypes = []

@@ -671,8 +671,9 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   tm.sync();
 
   // ---- phase 2: sequential greedy allocation of this step's orders (demand_allocator.py:150-208)
-  const int o_begin = io.order_offsets[e];
-  const int n_orders = io.order_offsets[e + 1] - o_begin;
+  // CSR (offsets) or padded layout (row e * stride, count[e]); the latter is what the device sampler writes
+  const long long o_begin = io.order_counts ? e * (long long)io.order_stride : (long long)io.order_offsets[e];
+  const int n_orders = io.order_counts ? io.order_counts[e] : io.order_offsets[e + 1] - (int)o_begin;
   const int qb = (CAPS & C_QTY16) ? io.order_qty_bytes : 1;
   const int row_bytes = S * qb;
   const int och = qb == 1 ? sp.och : sp.och / 2;   // the staging area is sized for och one-byte rows

@@ -130,6 +130,10 @@ int launch_reset_t(const LaunchArgs& a, const int32_t* init, int per_env, float*
   return launch_reset_caps<G, SPL, kCapsAll>(a, init, per_env, obs, s);   // reset is not a hot kernel
 }
 
+// K5 launcher (samplers.cu)
+int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int t, float* actions,
+                      cudaStream_t s);
+
 // One pair of entry points per team width, defined in env_inst_g*.cu; spl selects the instantiation.
 #define MARLSC_DECLARE_G(G)                                                                                   \
   int launch_step_g##G(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s);      \

@@ -230,8 +230,9 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   int rc = check_state(env, state);
   if (rc) return rc;
   if (!io) return set_error(MARLSC_EINVAL, "null io");
-  if (!io->actions || !io->order_offsets || !io->rewards || !io->obs)
-    return set_error(MARLSC_EINVAL, "io.actions, io.order_offsets, io.rewards and io.obs must not be NULL");
+  if (!io->actions || !io->rewards || !io->obs || (!io->order_offsets && !io->order_counts))
+    return set_error(MARLSC_EINVAL, "io.actions, io.rewards, io.obs and one of io.order_offsets / io.order_counts must not be NULL");
+  if (io->order_counts && io->order_stride < 1) return set_error(MARLSC_EINVAL, "order_stride must be positive with order_counts");
   if (io->order_qty_bytes != 1 && io->order_qty_bytes != 2) return set_error(MARLSC_EINVAL, "order_qty_bytes must be 1 or 2");
   if (env->ds.lead_mode == MARLSC_LEAD_STOCHASTIC && !io->actual_lead)
     return set_error(MARLSC_EINVAL, "io.actual_lead is required with a stochastic lead-time sampler");
@@ -321,6 +322,17 @@ int marlsc_env_rollout_host(marlsc_env_t* env, const marlsc_env_state_t* state, 
   }
   MARLSC_CUDA(cudaStreamSynchronize(cs));
   return MARLSC_OK;
+}
+
+int marlsc_policy_base_stock(marlsc_env_t* env, const marlsc_env_state_t* state, const float* level, int32_t t,
+                             float* actions, void* stream) {
+  int rc = check_state(env, state);
+  if (rc) return rc;
+  if (!level || !actions) return set_error(MARLSC_EINVAL, "level and actions must not be NULL");
+  if (env->ds.action_type != MARLSC_ACTION_DIRECT) return set_error(MARLSC_EINVAL, "the base-stock heuristic assumes the direct action space");
+  if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
+  MARLSC_CUDA(cudaSetDevice(env->device));
+  return launch_base_stock(env->ds, *state, level, t, actions, static_cast<cudaStream_t>(stream));
 }
 
 const char* marlsc_last_error(void) { return g_last_error.c_str(); }

@@ -1,0 +1,223 @@
+// samplers.cu - K4: on-device Poisson demand sampler, K5: batched base-stock heuristic policy.
+//
+// K4 draws, per environment and step, what the reference's PoissonDemandSampler draws
+// (src/environment/components/demand_sampler.py:105-163): per region r an order count ~ Poisson(lambda_orders[r]);
+// per order a Bernoulli(probability_skus[r]) mask over SKUs and quantities max(1, Poisson(lambda_quantity[r,s])).
+// Orders are emitted region-major like the reference. The random stream is Philox4x32-10 keyed by
+// (seed; env, step, row, lane block), so it is reproducible and independent of the launch geometry, but it is
+// NOT the reference's PCG64 stream: equality is distributional (tests compare moments and the quantity
+// histogram against the reference sampler), replay/host sampling stays the bit-exact path.
+// Output is the padded order layout marlsc_step_io accepts: env e owns rows [e*max_orders, e*max_orders + count[e]).
+//
+// K5 evaluates the reference's base-stock heuristic (src/experiments/run_baselines.py:133-207) for every
+// environment: qty = clip(S[w,k] - on_hand - in_transit, 0, max_qty), action = 2 qty / max_qty - 1 (float32).
+#include "env_kernels.cuh"
+
+namespace marlsc {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], const uint32_t (&k)[2]) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  c[0] = hi1 ^ c[1] ^ k[0];
+  c[1] = lo1;
+  c[2] = hi0 ^ c[3] ^ k[1];
+  c[3] = lo0;
+}
+
+__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint64_t seed) {
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k);
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }   // [0,1)
+
+// Poisson(lambda) from uniforms: inversion by sequential search below 30, rounded normal above.
+__device__ __forceinline__ int poisson_from(float lambda, float u, float u2) {
+  if (lambda <= 0.f) return 0;
+  if (lambda < 30.f) {
+    float p = __expf(-lambda), F = p;
+    int k = 0;
+    while (u > F && k < 200) {
+      ++k;
+      p *= lambda / (float)k;
+      F += p;
+    }
+    return k;
+  }
+  const float z = sqrtf(-2.f * __logf(fmaxf(u, 1e-7f))) * __cosf(6.2831853f * u2);
+  const float v = floorf(lambda + sqrtf(lambda) * z + 0.5f);
+  return v < 0.f ? 0 : (int)v;
+}
+
+struct DemandParams {
+  const float* lam_orders;   // [R]
+  const float* prob;         // [R]
+  const float* lam_qty;      // [R,S]
+};
+
+// one warp per environment
+__global__ void __launch_bounds__(128)
+sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, long long step, int omax,
+                     int32_t* __restrict__ counts, int16_t* __restrict__ region, uint8_t* __restrict__ qty,
+                     int32_t* __restrict__ overflow) {
+  const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  int16_t* reg_e = region + e * omax;
+  uint8_t* qty_e = qty + e * (long long)omax * S;
+  int row = 0;                                       // rows emitted so far (warp-uniform)
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    const int r = r0 + lane;
+    int n = 0;
+    if (r < R) {
+      uint32_t c[4] = {(uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)step, (uint32_t)r};
+      philox4x32(c, seed);
+      n = poisson_from(dp.lam_orders[r], u01(c[0]), u01(c[1]));
+    }
+    for (int l = 0; l < 32 && r0 + l < R; ++l) {      // regions in ascending order, like the reference
+      const int nr = __shfl_sync(0xffffffffu, n, l);
+      const int rr = r0 + l;
+      const float p = dp.prob[rr];
+      for (int i = 0; i < nr; ++i) {
+        if (row >= omax) {                             // staging is full: drop the order and flag it
+          if (lane == 0) atomicExch(overflow, 1);
+          continue;
+        }
+        if (lane == 0) reg_e[row] = (int16_t)rr;
+        for (int s0 = 0; s0 < S; s0 += 128) {          // four SKUs per lane per Philox call
+          uint32_t c[4] = {(uint32_t)e, (uint32_t)row | 0x80000000u, (uint32_t)step, (uint32_t)(s0 + lane)};
+          philox4x32(c, seed);
+          uint32_t d[4] = {(uint32_t)e ^ 0x9e3779b9u, (uint32_t)row | 0x40000000u, (uint32_t)step, (uint32_t)(s0 + lane)};
+          philox4x32(d, seed);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int s = s0 + lane + 32 * j;
+            if (s < S) {
+              int q = 0;
+              if (u01(c[j]) < p) {
+                q = poisson_from(dp.lam_qty[rr * S + s], u01(d[j]), u01(d[(j + 1) & 3] ^ 0x85ebca6bu));
+                q = q < 1 ? 1 : (q > 255 ? 255 : q);
+              }
+              qty_e[(long long)row * S + s] = (uint8_t)q;
+            }
+          }
+        }
+        ++row;
+      }
+    }
+  }
+  if (lane == 0) counts[e] = row;
+}
+
+// K5: one thread per (env, warehouse, SKU) cell
+__global__ void __launch_bounds__(256)
+base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
+                         const float* __restrict__ level, int t, float* __restrict__ actions) {
+  const long long WS = (long long)sp.W * sp.S;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= st.num_envs * WS) return;
+  const long long e = idx / WS;
+  const int i = (int)(idx - e * WS);
+  const int32_t* ring = st.ring_qty + e * WS * sp.D;
+  const int le = sp.lead_exp[i];
+  int pending = 0;                                     // units ordered and not yet arrived before step t
+  if (sp.lead_mode == MARLSC_LEAD_FIXED) {
+    for (int a = 1; a <= le && t - a >= 0; ++a) pending += ring[(long long)((t - a) % sp.D) * WS + i];
+  } else {
+    const uint8_t* rl = st.ring_lead + e * WS * sp.D;
+    for (int d = 0; d < sp.D; ++d) {
+      const int tau = (t - 1) - (((t - 1 - d) % sp.D + sp.D) % sp.D);
+      if (tau < 0) continue;
+      const int q = ring[(long long)d * WS + i];
+      if (q > 0 && tau + (int)rl[(long long)d * WS + i] >= t) pending += q;
+    }
+  }
+  const double mx = sp.action_max[i % sp.S];
+  double q = (double)level[i] - (double)st.inventory[idx] - (double)pending;
+  q = q < 0.0 ? 0.0 : (q > mx ? mx : q);
+  actions[idx] = (float)(2.0 * q / mx - 1.0);
+}
+
+int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int t, float* actions,
+                      cudaStream_t s) {
+  const long long n = st.num_envs * (long long)ds.W * ds.S;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  base_stock_policy_kernel<<<grid, 256, 0, s>>>(ds, st, level, t, actions);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+}  // namespace marlsc
+
+using namespace marlsc;
+
+struct marlsc_demand {
+  float* blob = nullptr;
+  DemandParams dp{};
+  int R = 0, S = 0, device = 0;
+};
+
+extern "C" {
+
+int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda_orders, const double* probability_skus,
+                         const double* lambda_quantity, int device, marlsc_demand_t** out) {
+  if (!out || !lambda_orders || !probability_skus || !lambda_quantity) return set_error(MARLSC_EINVAL, "null argument");
+  if (n_regions < 1 || n_skus < 1) return set_error(MARLSC_EINVAL, "n_regions and n_skus must be positive");
+  std::vector<float> host((size_t)2 * n_regions + (size_t)n_regions * n_skus);
+  for (int r = 0; r < n_regions; ++r) {
+    if (!(lambda_orders[r] >= 0.0) || !(probability_skus[r] >= 0.0 && probability_skus[r] <= 1.0))
+      return set_error(MARLSC_EINVAL, "lambda_orders must be >= 0 and probability_skus in [0,1]");
+    host[r] = (float)lambda_orders[r];
+    host[n_regions + r] = (float)probability_skus[r];
+  }
+  for (size_t i = 0; i < (size_t)n_regions * n_skus; ++i) {
+    if (!(lambda_quantity[i] >= 0.0)) return set_error(MARLSC_EINVAL, "lambda_quantity must be >= 0");
+    host[2 * n_regions + i] = (float)lambda_quantity[i];
+  }
+  marlsc_demand* d = new (std::nothrow) marlsc_demand();
+  if (!d) return set_error(MARLSC_ENOMEM, "out of host memory");
+  d->R = n_regions;
+  d->S = n_skus;
+  d->device = device;
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce == cudaSuccess) ce = cudaMalloc(&d->blob, host.size() * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMemcpy(d->blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    if (d->blob) cudaFree(d->blob);
+    delete d;
+    return set_error(MARLSC_ECUDA, std::string("uploading demand parameters: ") + cudaGetErrorString(ce));
+  }
+  d->dp.lam_orders = d->blob;
+  d->dp.prob = d->blob + n_regions;
+  d->dp.lam_qty = d->blob + 2 * n_regions;
+  *out = d;
+  return MARLSC_OK;
+}
+
+void marlsc_demand_destroy(marlsc_demand_t* d) {
+  if (!d) return;
+  if (d->blob) cudaFree(d->blob);
+  delete d;
+}
+
+int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t max_orders_per_env,
+                         int32_t* order_counts, int16_t* order_region, uint8_t* order_qty, int32_t* overflow_flag, void* stream) {
+  if (!d || !order_counts || !order_region || !order_qty || !overflow_flag) return set_error(MARLSC_EINVAL, "null argument");
+  if (num_envs < 1 || max_orders_per_env < 1) return set_error(MARLSC_EINVAL, "num_envs and max_orders_per_env must be positive");
+  MARLSC_CUDA(cudaSetDevice(d->device));
+  const int wpb = 4;
+  const unsigned grid = (unsigned)((num_envs + wpb - 1) / wpb);
+  sample_demand_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      d->dp, d->R, d->S, num_envs, seed, step_index, max_orders_per_env, order_counts, order_region, order_qty, overflow_flag);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+}  // extern "C"

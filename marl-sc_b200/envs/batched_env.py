@@ -57,7 +57,8 @@ class BatchedInventoryEnv:
                  seed: Optional[int] = None, env_meta: Optional[Dict[str, Any]] = None,
                  region_map: Optional[Sequence[int]] = None, env_seeds: Optional[Sequence[int]] = None,
                  host_samplers: bool = True, diagnostics: bool = False, team_size: int = 0,
-                 generic_kernel: bool = False):
+                 generic_kernel: bool = False, device_demand: bool = False, demand_seed: int = 0,
+                 max_orders_per_env: Optional[int] = None):
         if num_envs < 1:
             raise ValueError("num_envs must be positive")
         if not torch.cuda.is_available():
@@ -131,6 +132,10 @@ class BatchedInventoryEnv:
                 lost_orders=torch.zeros((E, R), dtype=torch.int32, device=dev),
                 lost_sales=torch.zeros((E, W, S), dtype=torch.float32, device=dev))
         self.timestep = 0
+        self._dd = None                      # device demand sampler state (enable_device_demand)
+        self._demand_step = 0
+        if device_demand:
+            self.enable_device_demand(demand_seed, max_orders_per_env)
 
         # host-side seeding / sampling that replays the reference's NumPy streams (optional)
         self.seed_managers: List[SeedManager] = []
@@ -149,11 +154,66 @@ class BatchedInventoryEnv:
                 self.demand_samplers.append(get_demand_sampler(env_config, context=self.spec.context))
                 self.lead_time_samplers.append(get_lead_time_sampler(env_config, context=self.spec.context))
 
+    # ------------------------------------------------------------------ on-device demand (K4)
+    def enable_device_demand(self, seed: int = 0, max_orders_per_env: Optional[int] = None) -> None:
+        """Draw demand on the device with the distribution of the reference's PoissonDemandSampler
+        (components/demand_sampler.py:105-163). The stream is Philox keyed by (seed, env, step): reproducible,
+        but not the reference's NumPy stream - use host samplers or replay when trajectories must match."""
+        smp = self.spec.components["demand_sampler"]
+        if not hasattr(smp, "dense_params"):
+            raise ValueError("device demand needs the 'poisson' demand sampler")
+        lam_o, prob, lam_q = smp.dense_params()
+        total = float(lam_o.sum())
+        omax = max_orders_per_env or int(np.ceil(total + 6.0 * np.sqrt(max(total, 1.0)) + 8.0))
+        omax = (omax + 3) & ~3
+        L = _capi.lib()
+        h = C.c_void_p()
+        dbl = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))   # noqa: E731
+        keep = (np.ascontiguousarray(lam_o, np.float64), np.ascontiguousarray(prob, np.float64), np.ascontiguousarray(lam_q, np.float64))
+        with torch.cuda.device(self.device):
+            _capi.check(L.marlsc_demand_create(self.n_regions, self.n_skus, dbl(keep[0]), dbl(keep[1]), dbl(keep[2]),
+                                               self.device.index, C.byref(h)))
+        E, S, dev = self.num_envs, self.n_skus, self.device
+        self._dd = dict(handle=h, seed=int(seed), omax=omax,
+                        counts=torch.zeros(E, dtype=torch.int32, device=dev),
+                        region=torch.zeros(E * omax, dtype=torch.int16, device=dev),
+                        qty=torch.zeros(E * omax * S + 16, dtype=torch.uint8, device=dev),
+                        overflow=torch.zeros(1, dtype=torch.int32, device=dev))
+
+    def sample_device_demand(self) -> None:
+        """Fill the device order buffers for the next step (called by step() when no orders are passed)."""
+        d = self._dd
+        _capi.check(_capi.lib().marlsc_demand_sample(d["handle"], self.num_envs, d["seed"], self._demand_step, d["omax"],
+                                                     d["counts"].data_ptr(), d["region"].data_ptr(), d["qty"].data_ptr(),
+                                                     d["overflow"].data_ptr(), self._stream()))
+        self._demand_step += 1
+
+    def demand_overflowed(self) -> bool:
+        """True when some environment drew more orders than max_orders_per_env (the surplus was dropped)."""
+        return bool(self._dd is not None and int(self._dd["overflow"].item()) != 0)
+
+    # ------------------------------------------------------------------ heuristic policies (K5)
+    def base_stock_actions(self, level: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Actions of the reference's base-stock heuristic (run_baselines.py:133-207) for every environment:
+        order up to ``level[w,s]`` given on-hand stock and units in transit, clipped to the order maximum."""
+        E, W, S = self.num_envs, self.n_warehouses, self.n_skus
+        lvl = level.to(device=self.device, dtype=torch.float32).contiguous()
+        if lvl.shape != (W, S):
+            raise ValueError(f"level must have shape {(W, S)}")
+        act = torch.empty((E, W, S), device=self.device) if out is None else out
+        _capi.check(_capi.lib().marlsc_policy_base_stock(self._h, C.byref(self._state), lvl.data_ptr(), self.timestep,
+                                                         act.data_ptr(), self._stream()))
+        self._keep_level = lvl
+        return act
+
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def close(self):
+        if getattr(self, "_dd", None):
+            _capi.lib().marlsc_demand_destroy(self._dd["handle"])
+            self._dd = None
         if getattr(self, "_h", None):
             _capi.lib().marlsc_env_destroy(self._h)
             self._h = None
@@ -277,6 +337,10 @@ class BatchedInventoryEnv:
         if actions.shape != (E, W, S) or actions.dtype != torch.float32 or actions.device != self.device:
             raise ValueError(f"actions must be a float32 tensor of shape {(E, W, S)} on {self.device}")
         actions = actions.contiguous()
+        use_dd = orders is None and self._dd is not None
+        if use_dd:
+            self.sample_device_demand()
+            orders = self._empty_orders
         if orders is None:
             host_orders, host_leads = self.sample_host_demand()
             orders = host_orders
@@ -307,6 +371,10 @@ class BatchedInventoryEnv:
             orders.qty_bytes, _ptr(lead_t), rew.data_ptr(), out.data_ptr(), self.truncated.data_ptr(),
             _ptr(d.get("cost_breakdown")), _ptr(d.get("ordered")), _ptr(d.get("ship_by_sku")), _ptr(d.get("ship_counts")),
             _ptr(d.get("unfulfilled")), _ptr(d.get("lost_orders")), _ptr(d.get("lost_sales")))
+        if use_dd:
+            dd = self._dd
+            io.order_offsets, io.order_region, io.order_qty, io.order_qty_bytes = None, dd["region"].data_ptr(), dd["qty"].data_ptr(), 1
+            io.order_counts, io.order_stride = dd["counts"].data_ptr(), dd["omax"]
         _capi.check(_capi.lib().marlsc_env_step(self._h, C.byref(self._state), C.byref(io), self.timestep, self._stream()))
         self._keep = (actions, orders, lead_t)   # keep inputs alive until the stream has consumed them
         self.timestep += 1

@@ -1,6 +1,7 @@
+from .baselines import base_stock_levels, baseline_rollout
 from .collector import Rollout, RolloutCollector, shard_envs
 from .gae import compute_gae, standardize_
 from .policy import ActorCritic, mlp
 from .ppo import PPOLearner
 
-__all__ = ["Rollout", "RolloutCollector", "shard_envs", "compute_gae", "standardize_", "ActorCritic", "mlp", "PPOLearner"]
+__all__ = ["base_stock_levels", "baseline_rollout", "Rollout", "RolloutCollector", "shard_envs", "compute_gae", "standardize_", "ActorCritic", "mlp", "PPOLearner"]

@@ -281,3 +281,141 @@ def test_pipelined_host_rollout_equals_stepwise():
     assert np.array_equal(env.inventory.cpu().numpy(), g["inventory"][:, T - 1])
     np.testing.assert_allclose(obs.cpu().numpy(), g["obs_local"][:, T - 1], rtol=1e-5, atol=1e-6)
     assert env.timestep == T
+
+
+# ---------------------------------------------------------------------------- K4 / K5
+def _small_env(E, **kw):
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    cfg = environment_config_from_dict(small_default())
+    return cfg, BatchedInventoryEnv(cfg, E, device="cuda:0", **kw)
+
+
+def test_device_demand_matches_reference_distribution():
+    """Philox stream != PCG64 stream, so the device sampler is checked distributionally against the reference
+    sampler's law: order counts ~ Poisson(lambda_orders), SKU inclusion ~ Bernoulli(p), quantities ~
+    max(1, Poisson(lambda_quantity)); 5-sigma bands on the moments and a chi-square on the quantity histogram."""
+    from scipy import stats
+    E = 8192
+    cfg, env = _small_env(E, host_samplers=False, device_demand=True, demand_seed=7)
+    env.sample_device_demand()
+    d = env._dd
+    counts = d["counts"].cpu().numpy()
+    omax, S, R = d["omax"], 2, 3
+    region = d["region"].cpu().numpy().reshape(E, omax)
+    qty = d["qty"].cpu().numpy()[:E * omax * S].reshape(E, omax, S)
+    assert not env.demand_overflowed()
+    valid = np.arange(omax)[None, :] < counts[:, None]
+    lam_o, p, lam_q = 4.0, 0.667, 5.0
+    n = E * R
+    per_region = np.stack([((region == r) & valid).sum(1) for r in range(R)], 1)
+    assert abs(per_region.mean() - lam_o) < 5 * np.sqrt(lam_o / n)
+    assert abs(per_region.var() - lam_o) < 0.15                                     # Poisson: variance = mean
+    assert all((np.diff(region[e][:counts[e]]) >= 0).all() for e in range(0, E, 97))   # region-major like the reference
+    q = qty[valid]                                                                   # [n_orders, S]
+    inc = (q > 0).mean()
+    assert abs(inc - p) < 5 * np.sqrt(p * (1 - p) / q.size)
+    nz = q[q > 0].astype(int)
+    ks = np.arange(1, 16)
+    pmf = stats.poisson.pmf(ks, lam_q)
+    pmf[0] += stats.poisson.pmf(0, lam_q)                                            # max(1, .)
+    pmf = np.append(pmf, 1 - pmf.sum())                                              # tail bucket >= 16
+    obs = np.array([(nz == k).sum() for k in ks] + [(nz >= 16).sum()])
+    chi2 = ((obs - nz.size * pmf) ** 2 / (nz.size * pmf)).sum()
+    assert chi2 < stats.chi2.ppf(1 - 1e-6, len(pmf) - 1), chi2
+    # reproducible: same seed and step index -> same draw; next step differs
+    a = d["qty"].clone()
+    env._demand_step = 0
+    env.sample_device_demand()
+    assert torch.equal(a, d["qty"])
+    env.sample_device_demand()
+    assert not torch.equal(a, d["qty"])
+    env.close()
+
+
+def test_step_with_device_demand_equals_same_orders_fed_as_csr():
+    """The padded order layout the sampler writes and the CSR layout must drive K1 to the same result."""
+    from marlsc_b200.demand import OrderBatch
+    E = 64
+    cfg, a = _small_env(E, host_samplers=False, device_demand=True, demand_seed=3)
+    _, b = _small_env(E, host_samplers=False)
+    a.reset()
+    b.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    for t in range(15):
+        act = torch.rand((E, 3, 2), device="cuda:0", generator=g) * 2 - 1
+        oa, ra, _ = a.step(act)
+        d = a._dd
+        counts = d["counts"].cpu().numpy()
+        omax = d["omax"]
+        region = d["region"].cpu().numpy().reshape(E, omax)
+        qty = d["qty"].cpu().numpy()[:E * omax * 2].reshape(E, omax, 2)
+        per_env = [[(int(region[e, j]), qty[e, j]) for j in range(counts[e])] for e in range(E)]
+        from marlsc_b200.demand import pack_orders
+        ob, rb, _ = b.step(act, orders=pack_orders(per_env, 2))
+        assert torch.equal(a.inventory, b.inventory) and torch.equal(ra, rb) and torch.equal(oa, ob)
+    a.close()
+    b.close()
+
+
+def test_base_stock_policy_kernel_matches_reference_formula():
+    from marlsc_b200.rollout import base_stock_levels
+    E = 32
+    cfg, env = _small_env(E, seed=5)
+    level = base_stock_levels(env, 2.0)
+    # reference: S = L*E[D] + z*sqrt(L*E[D]), E[D] = 4 * 0.667 * 5 for every (w,k), L = 3
+    ed = 4 * 0.667 * 5
+    assert np.allclose(level, 3 * ed + 2.0 * np.sqrt(3 * ed))
+    env.reset()
+    lvl = torch.from_numpy(level).float()
+    rng = np.random.default_rng(0)
+    for t in range(12):
+        act = env.base_stock_actions(lvl)
+        inv = env.inventory.cpu().numpy().astype(np.float64)
+        pend = env.pending_matrix().cpu().numpy().astype(np.float64)
+        qty = np.clip(level[None] - inv - pend, 0.0, 40.0)                       # run_baselines.py:196-203
+        exp = (2.0 * qty / 40.0 - 1.0).astype(np.float32)
+        np.testing.assert_allclose(act.cpu().numpy(), exp, rtol=1e-6, atol=1e-6)
+        env.step(act)
+    env.close()
+
+
+def test_config1_base_stock_returns_match_reference_numbers():
+    """BASELINE config #1: default small env, single env, heuristic base-stock policy z=2, eval seed 123.
+    The reference's first three episode returns (measured from the reference itself) are
+    -158.8005, -165.7435, -170.5540; the drop-in adapter seeded the same way must reproduce them."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import InventoryEnvironment
+    from marlsc_b200.rollout import base_stock_levels
+    cfg = environment_config_from_dict(small_default())
+    env = InventoryEnvironment(cfg, seed=123, env_meta={"data_mode": "train"})
+    level = base_stock_levels(env._batch, 2.0)
+    got = []
+    for ep in range(3):
+        obs, _ = env.reset()
+        total, done = 0.0, False
+        while not done:
+            inv, pipe = env.inventory, env._compute_pending_matrix().astype(float)
+            actions = {}
+            for w, agent in enumerate(env.agents):
+                qty = np.clip(level[w] - inv[w] - pipe[w], 0.0, 40.0)
+                actions[agent] = (2.0 * qty / 40.0 - 1.0).astype(np.float32)
+            obs, rew, term, trunc, _ = env.step(actions)
+            total += sum(rew.values())
+            done = all(trunc.values())
+        got.append(total)
+    np.testing.assert_allclose(got, [-158.8005, -165.7435, -170.5540], atol=2e-3)
+
+
+def test_device_baseline_rollout_statistics():
+    """Whole base-stock episodes on the device (K5 -> K4 -> K1 per step, no host round trip): the mean
+    episode return over many envs must sit where the reference's 20-episode estimate does (-165.40 +- 10.89)."""
+    from marlsc_b200.rollout import base_stock_levels, baseline_rollout
+    cfg, env = _small_env(2048, host_samplers=False, device_demand=True, demand_seed=11)
+    ret = baseline_rollout(env, base_stock_levels(env, 2.0), num_episodes=1)      # [1, E, W]
+    per_env = ret.sum(-1).reshape(-1).cpu().numpy()
+    assert abs(per_env.mean() - (-165.4)) < 3.0, per_env.mean()
+    assert 5.0 < per_env.std() < 20.0
+    env.close()
