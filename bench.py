@@ -446,13 +446,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_rollout(args):
+    """BASELINE configs[3]/[4]: full on-device rollout on the small env - PyTorch MLP policy/critic forward,
+    fused env step, rollout buffer, GAE scan (+ one PPO minibatch step with the NCCL gradient all-reduce for
+    MAPPO). Demand is drawn on the device (K4). A bench step = one rollout of T = episode length."""
+    import torch
+    import torch.distributed as dist
+
+    import marlsc_b200  # noqa: F401
+    from golden.scenarios import small_default
+    from marlsc_b200 import _capi
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from marlsc_b200.rollout import ActorCritic, PPOLearner, RolloutCollector
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mappo = args.workload == "mappo"
+    total = 1048576 if mappo else 262144
+    E = args.envs or (total // world if mappo else total)          # MAPPO: 1M envs sharded; IPPO: 262k per GPU
+    cfg = environment_config_from_dict(small_default())
+    env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False, device_demand=True, demand_seed=1 + rank,
+                              env_meta=dict(include_warehouse_id=True))
+    torch.manual_seed(0)
+    pol = ActorCritic(env.obs_dim, 3, 2, actor_hidden=(256, 256) if mappo else (256,), critic_hidden=(64, 64) if mappo else (256,),
+                      critic_obs_type="global" if mappo else "local", logstd_init=-1.2, logstd_floor=-3.5).to(dev)
+    T = cfg.episode_length
+    col = RolloutCollector(env, pol, T, gamma=GAMMA, lam=LAM, seed=rank)
+    learner = PPOLearner(pol, lr=5e-4, grad_clip=5.0)
+    L = _capi.lib()
+
+    def step():
+        ro = col.collect()
+        if mappo:
+            learner.minibatch_step(ro, slice(0, 1), slice(0, min(E, 65536)))   # one minibatch, grads all-reduced
+        return ro
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    barrier()
+    l0 = L.marlsc_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        ro = step()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        tm = torch.tensor([ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    if rank == 0:
+        value = E * 3 * T * args.steps * world / (ms * 1e-3)
+        r_host = ro.rewards.mean().item()                       # device->host read of the rollout's result
+        print(json.dumps(dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+            higher_is_better=True, scaling="strong" if mappo else "weak", vs_baseline=None, dtype="int32 state / fp32 obs, MLPs, GAE",
+            data="synthetic", gpu_launches=int(L.marlsc_launch_count() - l0),
+            config=dict(workload=("MAPPO centralised critic, 1,048,576 envs sharded (BASELINE configs[4])" if mappo else
+                                  "IPPO rollout, 262,144 envs per GPU (BASELINE configs[3])"),
+                        envs_per_gpu=E, horizon=T, env="env_symmetric_3WH2SKU + warehouse id", demand="device Poisson sampler (K4)",
+                        policy="PyTorch MLP actor/critic forward every step", learner="one PPO minibatch, NCCL grad all-reduce" if mappo else None,
+                        mean_reward=r_host))), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="large", choices=["large", "small"])
+    ap.add_argument("--workload", default="large", choices=["large", "small", "ippo", "mappo"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--team", type=int, default=0, help="threads per env (0 = auto)")
     ap.add_argument("--distinct-steps", type=int, default=8, help="uniform policy: distinct pre-sampled input steps cycled through")
@@ -464,7 +542,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload in ("ippo", "mappo"):
+        if args.impl == "reference":
+            args.workload = "small"
+            run_reference(args)
+        else:
+            run_rollout(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
