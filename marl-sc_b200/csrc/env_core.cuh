@@ -67,6 +67,7 @@ enum : uint32_t {
   C_DHSMEM = 1u << 15,   // home demand needed without a history plane (kept in shared memory)
   C_LOSTCOST = 1u << 16, // softmax ("cost") lost-sales handler
   C_FIXED = 1u << 17,    // non-zero outbound fixed costs (per-(warehouse, region) shipment counts)
+  C_SPLITLIM = 1u << 18, // max_splits < W-1: the split limit can bind, shipping warehouses are counted per order
 };
 constexpr uint32_t kCapsAll = 0xffffffffu;
 constexpr uint32_t kCapsLean = C_MEANSTD | C_IDHOT;
@@ -779,8 +780,9 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       }
       int used = 0;
       bool left = true;
+      constexpr bool kCount = (CAPS & (C_SPLITLIM | C_FIXED | C_DIAG)) != 0;   // else: no per-order bookkeeping
       for (int v = 0; v < W; ++v) {
-        if (used >= sp.max_splits + 1) break;
+        if ((CAPS & C_SPLITLIM) && used >= sp.max_splits + 1) break;
         int w;
         if (packed) {
           const uint32_t word = (v & 8) ? ((v & 4) ? pk[3] : pk[2]) : ((v & 4) ? pk[1] : pk[0]);
@@ -812,17 +814,19 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         }
         // Only two votes sit on the order's critical path; the shipped totals go to shared memory
         // with (warp-aggregated) atomic adds that nobody waits for.
-        const unsigned shipped = tm.ballot(fsum > 0);
-        if (shipped == 0u) continue;                           // this warehouse had nothing the order needs
         if (fsum > 0) {
           smem_add(&s_shipq[w * R + r], fsum);
           if (!unit_w) smem_add(&s_shipw[w * R + r], wsum);
         }
-        if ((has_fixed || kDiag) && tm.gl == lowest_bit(shipped)) {
-          if (has_fixed) s_cnt[w * R + r] += 1;
-          if (kDiag && io.d_ship_count) io.d_ship_count[(e * W + w) * R + r] += 1;
+        if (kCount) {
+          const unsigned shipped = tm.ballot(fsum > 0);
+          if (shipped == 0u) continue;                         // this warehouse had nothing the order needs
+          if ((has_fixed || kDiag) && tm.gl == lowest_bit(shipped)) {
+            if (has_fixed) s_cnt[w * R + r] += 1;
+            if (kDiag && io.d_ship_count) io.d_ship_count[(e * W + w) * R + r] += 1;
+          }
+          ++used;
         }
-        ++used;
         left = tm.any(rsum > 0);
         if (!left) break;
       }

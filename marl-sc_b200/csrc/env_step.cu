@@ -72,6 +72,7 @@ uint32_t required_caps(const DevSpec& ds, const HostTables& tb, const marlsc_ste
   if (ds.dh_mode == 2) c |= C_DHSMEM;
   if (ds.lost_type == MARLSC_LOST_COST) c |= C_LOSTCOST;
   if (ds.has_fixed) c |= C_FIXED;
+  if (ds.max_splits < ds.W - 1) c |= C_SPLITLIM;
   if (io) {
     if (io->order_qty_bytes == 2) c |= C_QTY16;
     if (io->cost_breakdown || io->d_ordered || io->d_ship || io->d_ship_count || io->d_unfulfilled || io->d_lost_orders ||
