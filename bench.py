@@ -298,6 +298,7 @@ def run_ours(args):
     tgt = torch.empty_like(rewards)
     obs_buf = [torch.empty_like(env.obs), torch.empty_like(env.obs)]
     k1_events = []
+    k2_events = []
 
     def segment(time_k1: bool, counter: list):
         for i in range(SEG):
@@ -312,7 +313,13 @@ def run_ours(args):
                 b.record()
                 k1_events.append((a, b))
             counter[0] += 1
+        if time_k1:
+            ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ga.record()
         compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
+        if time_k1:
+            gb.record()
+            k2_events.append((ga, gb))
 
     def barrier():
         torch.cuda.synchronize()
@@ -338,6 +345,7 @@ def run_ours(args):
     launches = L.marlsc_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
     k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    k2_ms = [a.elapsed_time(b) for a, b in k2_events]
     if world > 1:
         tmax = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -394,6 +402,41 @@ def run_ours(args):
                        "step kernels, rewards out) + marlsc_gae (host values in, advantages/targets out)",
                    segments=e2e_steps, gpu_launches=int(L.marlsc_launch_count() - launches_e2e0))
 
+    # ---- everything on the device: base-stock policy kernel (K5) -> Poisson demand kernel (K4) -> K1 ------
+    on_device = None
+    if args.workload == "large" and not args.no_e2e:
+        from marlsc_b200.rollout import base_stock_levels
+        env.enable_device_demand(seed=5 + rank)
+        lvl = torch.from_numpy(base_stock_levels(env, args.z, serve="cheapest")).float().to(dev)
+        act_buf = torch.empty((E, W, S), device=dev)
+
+        def device_segment():
+            for i in range(SEG):
+                if env.timestep >= env.episode_length:
+                    env.reset(obs_out=obs_buf[0])
+                env.base_stock_actions(lvl, out=act_buf)
+                env.step(act_buf, obs_out=obs_buf[i & 1], rewards_out=rewards[i])
+            compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
+
+        env.reset(obs_out=obs_buf[0])
+        for _ in range(2):
+            device_segment()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            device_segment()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            tmx = torch.tensor([ms], device=dev)
+            dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+            ms = float(tmx.item())
+        on_device = dict(value=E * W * SEG * 3 * world / (ms * 1e-3), unit=UNIT, ms_per_step=ms / 3,
+                         pipeline="per env step: marlsc_policy_base_stock (K5) -> marlsc_demand_sample (K4) -> marlsc_env_step (K1); "
+                                  "no host input at all", demand_overflow=env.demand_overflowed())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -421,6 +464,14 @@ def run_ours(args):
                     traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_env_step=b_env, k1_ms_per_launch=k1_avg_ms,
                     k1_share_of_step=sum(k1_ms) / elapsed_ms)
 
+    # K2 (GAE scan): reads rewards [T,N] + values [T+1,N], writes advantages + targets [T,N]; small working set
+    # (L2 resident at this size), reported for completeness
+    gae_bytes = 4.0 * E * W * (4 * SEG + 1)
+    k2_avg = statistics.mean(k2_ms)
+    roofline_gae = dict(bound="hbm", kernel="gae_kernel (K2)", achieved=gae_bytes / (k2_avg * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                        frac=gae_bytes / (k2_avg * 1e-3) / 1e9 / peak, k2_ms_per_launch=k2_avg, bytes_per_launch=gae_bytes,
+                        note="%.0f MB per launch: fits the 126 MB L2 only partly" % (gae_bytes / 1e6))
+
     # ---- CPU baseline: the oracle port on a bounded sample, one core -------------------------------
     cpu = None
     if not args.no_cpu:
@@ -440,7 +491,7 @@ def run_ours(args):
                             l2="inputs larger than L2 (per-step state+obs far exceeds 126 MB)" if args.workload == "large"
                             else "small working set; L2 resident (launch-latency bound)",
                             distinct_input_steps=n_in),
-                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+                roofline=roofline, roofline_gae=roofline_gae, cpu_baseline=cpu, e2e=e2e, on_device_pipeline=on_device, gpu_launches=int(launches), clocks=clk)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

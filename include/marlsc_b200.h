@@ -137,7 +137,8 @@ typedef struct marlsc_step_io {
   const float* actions;          /* [E,W,S] in [-1,1] (multi_env.py:253) */
   const int32_t* order_offsets;  /* [E+1] */
   const int16_t* order_region;   /* [n_orders] raw region ids */
-  const void* order_qty;         /* [n_orders,S] uint8 or uint16, see order_qty_bytes */
+  const void* order_qty;         /* [n_orders,S] uint8 or uint16, see order_qty_bytes. The kernel stages rows as
+                                    aligned 32-bit words: the allocation must extend at least 4 bytes past the last row */
   int32_t order_qty_bytes;       /* 1 or 2 */
   const uint8_t* actual_lead;    /* [E,W,S] this step's sampled lead times (stochastic) or NULL */
   float* rewards;                /* [E,W] */

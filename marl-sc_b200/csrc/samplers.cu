@@ -90,17 +90,19 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
         }
         if (lane == 0) reg_e[row] = (int16_t)rr;
         for (int s0 = 0; s0 < S; s0 += 128) {          // four SKUs per lane per Philox call
+          if (s0 + lane >= S) continue;
           uint32_t c[4] = {(uint32_t)e, (uint32_t)row | 0x80000000u, (uint32_t)step, (uint32_t)(s0 + lane)};
           philox4x32(c, seed);
-          uint32_t d[4] = {(uint32_t)e ^ 0x9e3779b9u, (uint32_t)row | 0x40000000u, (uint32_t)step, (uint32_t)(s0 + lane)};
-          philox4x32(d, seed);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int s = s0 + lane + 32 * j;
             if (s < S) {
+              // one 32-bit word per SKU: 12 bits decide inclusion, the other 20 drive the Poisson inversion
+              const float ub = (float)(c[j] & 0xfffu) * (1.0f / 4096.0f);
+              const float uq = (float)(c[j] >> 12) * (1.0f / 1048576.0f);
               int q = 0;
-              if (u01(c[j]) < p) {
-                q = poisson_from(dp.lam_qty[rr * S + s], u01(d[j]), u01(d[(j + 1) & 3] ^ 0x85ebca6bu));
+              if (ub < p) {
+                q = poisson_from(dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
                 q = q < 1 ? 1 : (q > 255 ? 255 : q);
               }
               qty_e[(long long)row * S + s] = (uint8_t)q;
@@ -127,7 +129,12 @@ base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_consta
   const int le = sp.lead_exp[i];
   int pending = 0;                                     // units ordered and not yet arrived before step t
   if (sp.lead_mode == MARLSC_LEAD_FIXED) {
-    for (int a = 1; a <= le && t - a >= 0; ++a) pending += ring[(long long)((t - a) % sp.D) * WS + i];
+    int row = (t - 1) % sp.D;                          // plane of the order placed one step ago, then backwards
+    const int n = le < t ? le : t;
+    for (int a = 0; a < n; ++a) {
+      pending += ring[(long long)row * WS + i];
+      row = row == 0 ? sp.D - 1 : row - 1;
+    }
   } else {
     const uint8_t* rl = st.ring_lead + e * WS * sp.D;
     for (int d = 0; d < sp.D; ++d) {
