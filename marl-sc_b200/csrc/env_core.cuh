@@ -357,6 +357,90 @@ MDEV double lost_weight(const DevSpec& sp, const int32_t* s_shipq, const int32_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pipeline block of warehouse w's observation row (multi_env.py:603-633, 941-968). It depends only on the
+// in-transit ring (including the order just placed at step t), not on this step's demand, so it is
+// emitted in phase 1 right after the ring row was read for arrivals: every ring sector is then touched
+// once per step instead of twice with the allocation phase in between (L2 cannot hold the in-flight
+// working set of all resident environments, so the second touch used to go back to DRAM).
+// ------------------------------------------------------------------------------------------------
+template <int G, int SPL, uint32_t CAPS>
+MDEV void write_obs_pipeline(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const EnvPtrs& p,
+                             float* MARLSC_RESTRICT obs_w, int w, int t) {
+  const int S = sp.S, L = sp.L, D = sp.D, WS = sp.W * sp.S;
+  const int base = w * S;
+  const bool ratio = (CAPS & C_RATIO) && sp.norm == MARLSC_NORM_RATIO;
+  const uint32_t F = sp.feat & (MARLSC_F_PIPELINE | ((CAPS & C_AGGX) ? MARLSC_F_PIPELINE_AGG : 0u));
+  const bool fixed_lead = !(CAPS & C_STOCH) || sp.lead_mode == MARLSC_LEAD_FIXED;
+  float* MARLSC_RESTRICT const out = pinned(obs_w + ((CAPS & C_IDHOT) ? sp.id_off : 0));
+  // pipeline, slot-major (L,S) ravel. Fixed leads: the order placed at tau sits in slot
+  //    tau + le - t, so slot k reads ring plane (t + k + 1 - le) mod D for k < le and is 0 otherwise
+  //    (planes of placement steps < 0 have not been written since reset and read 0).
+  if (sp.off_pipe >= 0) {
+    const bool need_total = ratio || (F & MARLSC_F_PIPELINE_AGG);
+    const int tm1 = (t + 1) % D;
+    const int32_t* const ring = p.ring_q;      // pinned per-env base; cells are addressed by 32-bit offsets
+    const unsigned WSu = (unsigned)WS, Su = (unsigned)S;
+    float* MARLSC_RESTRICT const pout = pinned(out + sp.off_pipe);
+    const bool ms = (CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD;
+    float den = 1.0f;
+    int total = 0;
+    for (int pass = need_total ? 0 : 1; pass < 2; ++pass) {
+      // pass 0 only sums (ratio denominator / aggregate), pass 1 writes
+#ifndef MARLSC_HOST_EMU
+#pragma unroll 1
+#endif
+      for (int j = 0; j < SPL; ++j) {
+        const int s = tm.gl + G * j;
+        if (s >= S) break;
+        const unsigned cell = (unsigned)(base + s);
+        const int le = (int)tb.lead[cell];
+        int row0 = tm1 - le;                   // ring plane of slot 0
+        row0 += row0 < 0 ? D : 0;
+        for (int k0 = 0; k0 < L; k0 += kPipeBatch) {
+          int v[kPipeBatch];
+          MARLSC_UNROLL
+          for (int kk = 0; kk < kPipeBatch; ++kk) {       // loads of the batch first
+            const int k = k0 + kk;
+            int val = 0;
+            if (fixed_lead) {
+              if (k < le) {
+                int row = row0 + k;
+                row -= row >= D ? D : 0;
+                val = ring[(unsigned)row * WSu + cell];
+              }
+            } else if ((CAPS & C_STOCH) && k < L) {
+              val = pipeline_value_stoch(sp, p, t, (int)cell, le, k);
+            }
+            v[kk] = val;
+          }
+          MARLSC_UNROLL
+          for (int kk = 0; kk < kPipeBatch; ++kk) {
+            const int k = k0 + kk;
+            if (k < L) {
+              if (pass == 0) {
+                total += v[kk];
+              } else {
+                float x = (float)v[kk];
+                if (ratio) x = f_div(x, den);
+                const unsigned idx = (unsigned)k * Su + (unsigned)s;
+                if (ms) x = f_mul(f_sub(x, sp.obs_mean[sp.off_pipe + idx]), sp.obs_std[sp.off_pipe + idx]);
+                pout[idx] = x;
+              }
+            }
+          }
+        }
+      }
+      if (pass == 0) {
+        total = tm.sum(total);
+        den = (float)((double)total + 1e-8);
+      }
+    }
+    if ((F & MARLSC_F_PIPELINE_AGG) && tm.gl == 0) emit<CAPS>(sp, out, sp.off_pipe + L * S, (float)total);
+  }
+
+}
+
+// ------------------------------------------------------------------------------------------------
 // Observation row of warehouse w (multi_env.py:577-710) from per-lane register values.
 //   vI/vdh/vsh/vst: on-hand, home demand, shipped home, shipped total (ints); vrm/vfc: rolling mean,
 //   forecast. hist_n = valid history entries including the current step (0 right after reset).
@@ -428,71 +512,7 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
     if ((F & MARLSC_F_INVENTORY_AGG) && tm.gl == 0) emit<CAPS>(sp, out, sp.off_inv + S, (float)sumI);
   }
 
-  // 2. pipeline, slot-major (L,S) ravel. Fixed leads: the order placed at tau sits in slot
-  //    tau + le - t, so slot k reads ring plane (t + k + 1 - le) mod D for k < le and is 0 otherwise
-  //    (planes of placement steps < 0 have not been written since reset and read 0).
-  if (sp.off_pipe >= 0) {
-    const bool need_total = ratio || (F & MARLSC_F_PIPELINE_AGG);
-    const int tm1 = (t + 1) % D;
-    const int32_t* const ring = p.ring_q;      // pinned per-env base; cells are addressed by 32-bit offsets
-    const unsigned WSu = (unsigned)WS, Su = (unsigned)S;
-    float* MARLSC_RESTRICT const pout = pinned(out + sp.off_pipe);
-    const bool ms = (CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD;
-    float den = 1.0f;
-    int total = 0;
-    for (int pass = need_total ? 0 : 1; pass < 2; ++pass) {
-      // pass 0 only sums (ratio denominator / aggregate), pass 1 writes
-#ifndef MARLSC_HOST_EMU
-#pragma unroll 1
-#endif
-      for (int j = 0; j < SPL; ++j) {
-        const int s = tm.gl + G * j;
-        if (s >= S) break;
-        const unsigned cell = (unsigned)(base + s);
-        const int le = (int)tb.lead[cell];
-        int row0 = tm1 - le;                   // ring plane of slot 0
-        row0 += row0 < 0 ? D : 0;
-        for (int k0 = 0; k0 < L; k0 += kPipeBatch) {
-          int v[kPipeBatch];
-          MARLSC_UNROLL
-          for (int kk = 0; kk < kPipeBatch; ++kk) {       // loads of the batch first
-            const int k = k0 + kk;
-            int val = 0;
-            if (fixed_lead) {
-              if (k < le) {
-                int row = row0 + k;
-                row -= row >= D ? D : 0;
-                val = ring[(unsigned)row * WSu + cell];
-              }
-            } else if ((CAPS & C_STOCH) && k < L) {
-              val = pipeline_value_stoch(sp, p, t, (int)cell, le, k);
-            }
-            v[kk] = val;
-          }
-          MARLSC_UNROLL
-          for (int kk = 0; kk < kPipeBatch; ++kk) {
-            const int k = k0 + kk;
-            if (k < L) {
-              if (pass == 0) {
-                total += v[kk];
-              } else {
-                float x = (float)v[kk];
-                if (ratio) x = f_div(x, den);
-                const unsigned idx = (unsigned)k * Su + (unsigned)s;
-                if (ms) x = f_mul(f_sub(x, sp.obs_mean[sp.off_pipe + idx]), sp.obs_std[sp.off_pipe + idx]);
-                pout[idx] = x;
-              }
-            }
-          }
-        }
-      }
-      if (pass == 0) {
-        total = tm.sum(total);
-        den = (float)((double)total + 1e-8);
-      }
-    }
-    if ((F & MARLSC_F_PIPELINE_AGG) && tm.gl == 0) emit<CAPS>(sp, out, sp.off_pipe + L * S, (float)total);
-  }
+  // 2. pipeline block: written by write_obs_pipeline() where the ring row is first touched (phase 1)
 
   MARLSC_UNROLL
   for (int j = 0; j < SPL; ++j) {
@@ -658,6 +678,8 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
         if (kDiag && io.d_ordered) io.d_ordered[e * WS + i] = q;
       }
     }
+    tm.sync();   // stochastic lead times / small teams: cells of this row were written by other lanes
+    write_obs_pipeline<G, SPL, CAPS>(sp, tb, tm, p, io.obs + (e * W + w) * (int64_t)sp.obs_dim, w, t);
   }
   for (int i = tm.gl; i < W * R; i += G) {
     s_shipq[i] = 0;
@@ -1009,6 +1031,7 @@ MDEV void reset_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, cons
       vz[j] = 0;
       vf[j] = 0.f;
     }
+    write_obs_pipeline<G, SPL, CAPS>(sp, tb, tm, p, obs + (e * W + w) * (int64_t)sp.obs_dim, w, 0);
     write_obs_row<G, SPL, CAPS>(sp, tb, tm, p, obs + (e * W + w) * (int64_t)sp.obs_dim, w, 0, 0, vI, vz, vz, vz, vf, vf);
   }
 }
