@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Turn the artefacts a gpurun call left in gpurun_out/ into the tracked evidence under profiles/.
+
+    python tools/refresh_profiles.py <full.ncu-rep> [round tag, default r1]
+"""
+import collections
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+
+def main(rep, tag="r1"):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    open(os.path.join(P, f"{tag}_k1_lean_65536envs.summary.txt"), "w").write(out)
+    rows = list(csv.reader(open(os.path.join(G, f"{tag}_launches.csv"))))
+    hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+    hdr = rows[hi]
+    kn, mv, mn = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Name')
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[hi + 1:]:
+        if len(r) <= mv or r[mn] != 'gpu__time_duration.sum':
+            continue
+        name = r[kn].split('(')[0][:70]
+        agg[name][0] += 1
+        agg[name][1] += float(r[mv].replace(',', ''))
+    tot = sum(v[1] for v in agg.values())
+    lines = ["ncu --metrics gpu__time_duration.sum --clock-control none -k regex:env_step|env_reset|gae_kernel|moments|standardize -c 400",
+             "command: python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu   (every launch of this library's kernels: recording pass, warm-up, timed segment)",
+             "(cold-cache, serialised per-launch times under the profiler: compare shares, not absolutes)", ""]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:15]:
+        lines.append(f"{100 * v[1] / tot:6.2f}%  n={v[0]:4d}  avg={v[1] / v[0] / 1e6:9.3f} ms  {k}")
+    open(os.path.join(P, f"{tag}_launch_list_summary.txt"), "w").write("\n".join(lines) + "\n")
+    shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{tag}_launches.csv"))
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, r = rows[0], rows[1], rows[2]
+
+    def val(n):
+        i = hdr.index(n)
+        return float(r[i].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(units[i], 1)
+    rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')
+    json.dump(dict(workload="large", envs=65536, kernel="env_step_kernel<32,4,lean>", dram_bytes_per_launch=rd + wr, dram_read=rd,
+                   dram_write=wr, source=f"profiles/{tag}_k1_lean_65536envs.summary.txt (ncu --set full, one launch)"),
+              open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
+    for name in ("bench_default", "bench_small", "bench_ippo", "bench_reference"):
+        src = os.path.join(G, name + ".json")
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(P, f"{tag}_{name}.json"))
+    print("\n".join(lines))
+    print(f"DRAM traffic per env-step: {(rd + wr) / 65536:.0f} B (read {rd / 65536:.0f}, write {wr / 65536:.0f})")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], *(sys.argv[2:3]))
