@@ -419,3 +419,86 @@ def test_device_baseline_rollout_statistics():
     assert abs(per_env.mean() - (-165.4)) < 3.0, per_env.mean()
     assert 5.0 < per_env.std() < 20.0
     env.close()
+
+
+@pytest.mark.parametrize("team", [0, 2, 8])
+def test_cuda_edge_cases_vs_oracle(team):
+    """Odd shapes (W4 S7 R6), weight-dependent priority, softmax lost-sales handler, stochastic leads, base-stock
+    actions, environments with no orders, all-zero orders, quantities that need 16 bits, an env count that does
+    not fill the last CTA, more steps than the ring is deep, and a reset in the middle - CUDA vs the oracle."""
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.demand import pack_orders
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from oracle.inventory_oracle import OracleEnv
+    W, S, R = 4, 7, 6
+    rng = np.random.default_rng(42)
+    env_dict = dict(
+        action_space=dict(type="base_stock", params=dict(max_stock_level=[int(x) for x in rng.integers(200, 900, S)])),
+        n_warehouses=W, n_skus=S, n_regions=R, episode_length=14, max_wh_capacities=[1e7] * W,
+        initial_inventory=dict(type="custom", params=dict(values=150)),
+        cost_structure=dict(
+            holding_cost=0.5, penalty_cost=[float(x) for x in rng.integers(1, 9, S)],
+            shipment_cost=dict(
+                outbound_fixed=(rng.integers(0, 8, (W, R)) * 0.5).tolist(), outbound_variable=(rng.integers(1, 16, (W, R)) / 16).tolist(),
+                inbound_fixed=(rng.integers(0, 3, (W, S)) * 1.0).tolist(), inbound_variable=(rng.integers(1, 5, (W, S)) * 0.25).tolist()),
+            sku_weights=[0.5, 1.0, 2.0, 0.25, 1.5, 1.0, 4.0], distances=(rng.integers(10, 500, (W, R)) * 1.0).tolist()),
+        components=dict(
+            demand_sampler=dict(type="poisson", params=dict(lambda_orders=1.0, probability_skus=0.5, lambda_quantity=5.0)),
+            demand_allocator=dict(type="greedy", params=dict(max_splits=2)),
+            lead_time_sampler=dict(type="stochastic", params=dict(
+                expected_lead_times=rng.integers(1, 5, (W, S)).tolist(), deviation=dict(type="uniform", max_deviation=2))),
+            lost_sales_handler=dict(type="cost", params=dict(alpha=3.0)),
+            reward_calculator=dict(type="cost", params=dict(scope="team", scale_factor=0.1, cost_weights=[0.25] * 4))),
+        data_source=dict(type="custom"),
+        features=dict(inventory=True, pipeline=True, incoming_demand_home=True, units_shipped_home=True, units_shipped_away=True,
+                      stockout=True, rolling_demand_mean=True, demand_forecast=True, days_of_supply=True,
+                      net_inventory_position=True, demand_variability=True, demand_history=True, inventory_aggregate=False,
+                      pipeline_aggregate=True, incoming_demand_home_aggregate=False, units_shipped_away_aggregate=True,
+                      rolling_demand_mean_aggregate=True, demand_forecast_aggregate=False))
+    cfg = environment_config_from_dict(dict(env_dict, allow_region_mismatch=True))
+    E, T = 5, 26
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, diagnostics=True, team_size=team,
+                              env_meta=dict(include_warehouse_id=True))
+    oracles = [OracleEnv(env_dict, include_warehouse_id=True) for _ in range(E)]
+    lead_exp = np.asarray(env_dict["components"]["lead_time_sampler"]["params"]["expected_lead_times"])
+
+    def reset_all():
+        obs = env.reset().cpu().numpy()
+        for i, o in enumerate(oracles):
+            np.testing.assert_allclose(obs[i], o.reset(np.full((W, S), 150)), rtol=1e-5, atol=1e-6)
+    reset_all()
+    for t in range(T):
+        if t == 14:                                   # episode over (truncated at t = 13): start the next one
+            reset_all()
+        per_env = []
+        for i in range(E):
+            if i == 1 or (i == 3 and t % 2):          # envs without any order this step
+                per_env.append([])
+                continue
+            orders = []
+            for _ in range(int(rng.integers(1, 9))):
+                q = np.where(rng.random(S) < 0.5, rng.integers(1, 700 if i == 4 else 40, S), 0)
+                if rng.random() < 0.15:
+                    q[:] = 0                          # all-zero order: legal no-op
+                orders.append((int(rng.integers(0, R)), q.astype(float)))
+            per_env.append(orders)
+        batch = pack_orders(per_env, S)
+        assert batch.qty_bytes == 2
+        act = rng.uniform(-1, 1, (E, W, S)).astype(np.float32)
+        leads = np.maximum(1, lead_exp[None] + rng.integers(-2, 3, (E, W, S))).astype(np.uint8)
+        obs, rew, trunc = env.step(torch.from_numpy(act).cuda(), orders=batch, actual_lead=leads)
+        d = {k: v.cpu().numpy() for k, v in env.diag.items()}
+        inv, r, ob = env.inventory.cpu().numpy(), rew.cpu().numpy(), obs.cpu().numpy()
+        for i, o in enumerate(oracles):
+            out = o.step(act[i], per_env[i], leads[i])
+            assert np.array_equal(inv[i], out["inventory"]), (t, i)
+            assert np.array_equal(d["ordered"][i], out["ordered"])
+            assert np.array_equal(d["ship_by_sku"][i], out["ship_by_sku"])
+            assert np.array_equal(d["ship_counts"][i], out["ship_counts"])
+            assert np.array_equal(d["unfulfilled"][i], out["unfulfilled"])
+            assert np.array_equal(d["lost_orders"][i], out["lost_orders"])
+            np.testing.assert_allclose(d["lost_sales"][i], out["lost_sales"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(r[i], out["rewards"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(ob[i], out["obs_local"], rtol=1e-5, atol=2e-5, err_msg=f"obs t={t} env={i}")
+            assert bool(trunc) == bool(out["trunc"])
+    env.close()
