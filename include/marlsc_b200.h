@@ -42,8 +42,6 @@ enum { MARLSC_LOST_CLOSEST = 0, MARLSC_LOST_SHIPMENT = 1, MARLSC_LOST_COST = 2 }
 enum { MARLSC_SCOPE_AGENT = 0, MARLSC_SCOPE_TEAM = 1 };
 /* observation normalisation done inside the env (reference: multi_env.py:591,607-610,700-702) */
 enum { MARLSC_NORM_OFF = 0, MARLSC_NORM_RATIO = 1, MARLSC_NORM_MEANSTD = 2 };
-/* demand source used by marlsc_env_step (reference: components/demand_sampler.py:105-163) */
-enum { MARLSC_DEMAND_REPLAY = 0, MARLSC_DEMAND_POISSON_DEVICE = 1 };
 
 /* feature toggles, same names as the reference FeatureConfig (src/config/schema.py:598-617);
  * block order in the observation follows multi_env.py:619-695 */

@@ -153,7 +153,6 @@ struct Team {
     return G == 32 ? b : (b >> ((threadIdx.x & 31) & ~(G - 1)));
   }
   __device__ __forceinline__ int sum(int v) const {
-    if (G == 1) return v;
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
     return v;
@@ -186,7 +185,6 @@ MDEV float f_sub(float a, float b) { return __fsub_rn(a, b); }
 MDEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
 MDEV float f_div(float a, float b) { return __fdiv_rn(a, b); }
 MDEV float f_sqrt(float a) { return __fsqrt_rn(a); }
-MDEV float f_fastdiv(float a, float b) { return __fdividef(a, b); }
 MDEV double d_add(double a, double b) { return __dadd_rn(a, b); }
 MDEV double d_mul(double a, double b) { return __dmul_rn(a, b); }
 MDEV double d_rint(double a) { return rint(a); }
@@ -199,7 +197,6 @@ MDEV float f_sub(float a, float b) { volatile float r = a - b; return r; }
 MDEV float f_mul(float a, float b) { volatile float r = a * b; return r; }
 MDEV float f_div(float a, float b) { volatile float r = a / b; return r; }
 MDEV float f_sqrt(float a) { return std::sqrt(a); }
-MDEV float f_fastdiv(float a, float b) { return a / b; }
 MDEV double d_add(double a, double b) { volatile double r = a + b; return r; }
 MDEV double d_mul(double a, double b) { volatile double r = a * b; return r; }
 MDEV double d_rint(double a) { return std::nearbyint(a); }

@@ -22,7 +22,7 @@ from .. import _capi
 from ..config.schema import (EnvironmentConfig, InitialInventoryCustom, InitialInventoryUniform,
                              InitialInventoryZero)
 from ..demand import OrderBatch, pack_orders
-from ..seeds import ENVIRONMENT_SEEDS, STOCHASTIC_SEEDS, SeedManager
+from ..seeds import ENVIRONMENT_SEEDS, SeedManager
 from ..spec import EnvSpec, build_env_spec
 
 
