@@ -42,6 +42,9 @@ namespace marlsc {
 
 constexpr int kWindow = MARLSC_ROLLING_WINDOW;
 constexpr int kPipeBatch = 5;   // pipeline slots loaded together per cell
+#ifndef MARLSC_FORCE_LANE_ALLOC
+#define MARLSC_FORCE_LANE_ALLOC 0   // the host emulation sets this to run the wide-team allocation with G == 1
+#endif
 
 // Capabilities compiled into a kernel instantiation. The lean instantiation (kCapsLean) covers the
 // common configurations - fixed lead times, direct actions, unit SKU weights, static warehouse
@@ -71,6 +74,14 @@ enum : uint32_t {
 };
 constexpr uint32_t kCapsAll = 0xffffffffu;
 constexpr uint32_t kCapsLean = C_MEANSTD | C_IDHOT;
+// Wide teams whose configuration couples the SKUs of an order through nothing but the inventory
+// (no binding split limit, no per-shipment fixed cost, static warehouse priority, no diagnostics) run
+// the allocation as independent per-lane chains, see step_env phase 2.
+template <int G, uint32_t CAPS>
+struct LaneAlloc {
+  static constexpr bool value = (G >= 8 || MARLSC_FORCE_LANE_ALLOC) &&
+                                !(CAPS & (C_SPLITLIM | C_FIXED | C_DIAG | C_DYNPRIO | C_QTY16 | C_BIGW));
+};
 
 // Device-side view of a marlsc_env_spec_t: device table pointers, observation block offsets and
 // the shared-memory layouts. Passed by value to the kernels.
@@ -190,6 +201,9 @@ MDEV double d_mul(double a, double b) { return __dmul_rn(a, b); }
 MDEV double d_rint(double a) { return rint(a); }
 MDEV int lowest_bit(uint32_t m) { return __ffs((int)m) - 1; }
 MDEV void smem_add(int32_t* addr, int v) { atomicAdd(addr, v); }
+// fire-and-forget add to a global cell (RED); read the cell back with load_cg() after a team sync
+MDEV void global_add(int32_t* addr, int v) { asm volatile("red.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
+MDEV int load_cg(const int32_t* addr) { return __ldcg(addr); }
 MDEV void smem_add(double* addr, double v) { atomicAdd(addr, v); }
 #else
 MDEV float f_add(float a, float b) { volatile float r = a + b; return r; }
@@ -202,6 +216,8 @@ MDEV double d_mul(double a, double b) { volatile double r = a * b; return r; }
 MDEV double d_rint(double a) { return std::nearbyint(a); }
 MDEV int lowest_bit(uint32_t m) { return __builtin_ctz(m); }
 MDEV void smem_add(int32_t* addr, int v) { *addr += v; }
+MDEV void global_add(int32_t* addr, int v) { *addr += v; }
+MDEV int load_cg(const int32_t* addr) { return *addr; }
 MDEV void smem_add(double* addr, double v) { *addr += v; }
 #endif
 // Keep a derived pointer in registers: without this the compiler re-derives per-environment bases
@@ -381,6 +397,53 @@ MDEV void write_obs_pipeline(const DevSpec& sp, const Tables& tb, const Team<G>&
     const bool ms = (CAPS & C_MEANSTD) && sp.norm == MARLSC_NORM_MEANSTD;
     float den = 1.0f;
     int total = 0;
+    if (fixed_lead && !need_total) {
+      // common case: every cell of the row in flight at once, kPipeBatch slots per round
+      int le[SPL], row0[SPL];
+      MARLSC_UNROLL
+      for (int j = 0; j < SPL; ++j) {
+        const int s = tm.gl + G * j;
+        le[j] = s < S ? (int)tb.lead[base + s] : 0;
+        row0[j] = tm1 - le[j];                 // ring plane of slot 0
+        row0[j] += row0[j] < 0 ? D : 0;
+      }
+#ifndef MARLSC_HOST_EMU
+#pragma unroll 1
+#endif
+      for (int k0 = 0; k0 < L; k0 += kPipeBatch) {
+        int v[SPL][kPipeBatch];
+        MARLSC_UNROLL
+        for (int j = 0; j < SPL; ++j) {
+          const unsigned cell = (unsigned)(base + tm.gl + G * j);
+          MARLSC_UNROLL
+          for (int kk = 0; kk < kPipeBatch; ++kk) {
+            const int k = k0 + kk;
+            v[j][kk] = 0;
+            if (k < le[j]) {
+              int row = row0[j] + k;
+              row -= row >= D ? D : 0;
+              v[j][kk] = ring[(unsigned)row * WSu + cell];
+            }
+          }
+        }
+        MARLSC_UNROLL
+        for (int j = 0; j < SPL; ++j) {
+          const int s = tm.gl + G * j;
+          if (s < S) {
+            MARLSC_UNROLL
+            for (int kk = 0; kk < kPipeBatch; ++kk) {
+              const int k = k0 + kk;
+              if (k < L) {
+                float x = (float)v[j][kk];
+                const unsigned idx = (unsigned)k * Su + (unsigned)s;
+                if (ms) x = f_mul(f_sub(x, sp.obs_mean[sp.off_pipe + idx]), sp.obs_std[sp.off_pipe + idx]);
+                pout[idx] = x;
+              }
+            }
+          }
+        }
+      }
+    } else
     for (int pass = need_total ? 0 : 1; pass < 2; ++pass) {
       // pass 0 only sums (ratio denominator / aggregate), pass 1 writes
 #ifndef MARLSC_HOST_EMU
@@ -676,7 +739,9 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       }
     }
     tm.sync();   // stochastic lead times / small teams: cells of this row were written by other lanes
+#ifndef MARLSC_EXP_NOPIPE
     write_obs_pipeline<G, SPL, CAPS>(sp, tb, tm, p, io.obs + (e * W + w) * (int64_t)sp.obs_dim, w, t);
+#endif
   }
   for (int i = tm.gl; i < W * R; i += G) {
     s_shipq[i] = 0;
@@ -722,152 +787,252 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       for (; k < nw; k += G) dst_w[k] = src_w[k];
     }
     tm.sync();
-    for (int j = 0; j < cn; ++j) {
-      const int r = s_sreg[j];
-      const uint8_t* row = s_sqty + shift + j * row_bytes;
-      int rem[SPL];
-      int dsum = 0;
-      MARLSC_UNROLL
-      for (int jj = 0; jj < SPL; ++jj) {
-        const int s = tm.gl + G * jj;
-        int d = 0;
-        if (s < S) d = qb == 1 ? (int)row[s] : (int)reinterpret_cast<const uint16_t*>(row)[s];
-        rem[jj] = d;
-        dsum += d;
-      }
-      if (!tm.any(dsum > 0)) continue;                         // all-zero order: nothing can ship or be lost
-      // home-region demand of this step (multi_env.py:763-768)
-      if (!dh_mode) {
-      } else if (!(CAPS & C_BIGW) || tb.hmask) {
-        uint32_t hm = tb.hmask[r];
-        while (hm) {
-          const int w = lowest_bit(hm);
-          hm &= hm - 1;
+    if constexpr (LaneAlloc<G, CAPS>::value) {
+      // Wide teams, SKUs coupled only through the inventory: the greedy allocation of one SKU never looks
+      // at another SKU, so every lane runs the chains of the SKUs it owns (four consecutive SKUs per
+      // 32-bit word of a row) on its own. A pass covers up to kPassOrders staged orders: the lane first
+      // notes which of its cells are non-zero (4 bits per row word, 64 bits in all), then works through
+      // those lines in order - take the next line, walk it down the region's warehouse priority list until
+      // it is filled or lost - one list step per loop trip, every lane on its own line. Orders stay in
+      // sequence per SKU, which is all the sequential semantics of demand_allocator.py:150-208 asks for
+      // when no split limit binds; the lanes only meet again at the end of the pass.
+      constexpr int NWL = SPL >= 4 ? SPL / 4 : 1;                     // row words per lane
+      constexpr int KG = NWL < 16 ? NWL : 16;                        // row words per lane and pass
+      constexpr int kPassOrders = 16 / KG;
+      const bool aligned = shift == 0 && (S & 3) == 0;
+      const uint8_t* rows = s_sqty + shift;
+      const int Wp = (W + 3) & ~3;
+      for (int j0 = 0; j0 < cn; j0 += kPassOrders)
+      for (int k0 = 0; k0 < NWL; k0 += KG) {
+        const int pn = imin(kPassOrders, cn - j0);
+        uint32_t mlo = 0, mhi = 0;                                    // orders 0-7 / 8-15 of the pass (KG = 1)
+        for (int jj = 0; jj < pn; ++jj) {
+          const uint8_t* row = rows + (j0 + jj) * row_bytes;
           MARLSC_UNROLL
-          for (int jj = 0; jj < SPL; ++jj) {
-            const int s = tm.gl + G * jj;
-            if (s < S && rem[jj] > 0) dh_acc[w * S + s] += rem[jj];
+          for (int k = 0; k < KG; ++k) {
+            const int c0s = 4 * (tm.gl + G * (k0 + k));               // first SKU of this word
+            uint32_t word = 0;
+            if (aligned) {
+              if (c0s < S) word = *reinterpret_cast<const uint32_t*>(row + c0s);
+            } else {
+              MARLSC_UNROLL
+              for (int b = 0; b < 4; ++b)
+                if (c0s + b < S) word |= (uint32_t)row[c0s + b] << (8 * b);
+            }
+            // bit 7 of every non-zero byte, gathered into the low four bits
+            uint32_t nz = (((word & 0x7f7f7f7fu) + 0x7f7f7f7fu) | word) & 0x80808080u;
+            nz = (((nz >> 7) * 0x204081u) >> 21) & 0xfu;
+            const int at = 4 * (jj * KG + k);
+            if (at < 32) mlo |= nz << at; else mhi |= nz << (at - 32);
           }
         }
-      } else {
-        for (int w = 0; w < W; ++w)
-          if (sp.home[w] == r) {
+        int rem = 0, v = 0, r = 0, sku = 0, oj = 0;
+        while (true) {
+          if (rem == 0 && (mlo | mhi) != 0) {                         // next line of this lane
+            int bit;
+            if (mlo) {
+              bit = lowest_bit(mlo);
+              mlo &= mlo - 1;
+            } else {
+              bit = 32 + lowest_bit(mhi);
+              mhi &= mhi - 1;
+            }
+            const int slot = bit >> 2;
+            oj = j0 + slot / KG;
+            sku = 4 * (tm.gl + G * (k0 + slot % KG)) + (bit & 3);
+            rem = rows[oj * row_bytes + sku];
+            r = s_sreg[oj] & 0x7fff;
+            v = 0;
+            // home-region demand of this step (multi_env.py:763-768); the cell belongs to this lane
+            if (dh_mode) {
+              uint32_t hm = tb.hmask[r];
+              while (hm) {
+                const int w = lowest_bit(hm);
+                hm &= hm - 1;
+                if (dh_mode == 1) global_add(&dh_acc[w * S + sku], rem);   // nobody waits for the sum
+                else dh_acc[w * S + sku] += rem;
+              }
+            }
+          }
+          if (rem > 0) {                                              // one step down the priority list
+            const int w = tb.prio[r * Wp + v];
+            ++v;
+            int32_t* cell = s_inv + w * S + sku;
+            const int a = *cell;
+            const int f = imin(rem, a);
+            if (f > 0) {
+              *cell = a - f;
+              smem_add(&s_shipq[w * R + r], f);
+              if (!unit_w) smem_add(&s_shipw[w * R + r], (double)f * tb.skw[sku]);
+              if (need_ship) {
+                s_st[w * S + sku] += f;
+                if (sp.home[w] == r) s_sh[w * S + sku] += f;
+              }
+            }
+            rem -= f;
+            if (rem > 0 && v >= W) {
+              // no warehouse can supply the rest: lost (demand_allocator.py:205-208)
+              smem_add(&s_lostW[r], (double)rem * tb.skw[sku]);
+              smem_add(&s_lostP[r], (double)rem * tb.pen[sku]);
+              s_sreg[oj] = (int16_t)(r | 0x8000);                    // the order counts as lost once, below
+              rem = 0;
+            }
+          }
+          if (!tm.any(rem > 0 || (mlo | mhi) != 0)) break;
+        }
+      }
+      tm.sync();
+#pragma unroll 1
+      for (int j = tm.gl; j < cn; j += G)
+        if (s_sreg[j] & 0x8000) smem_add(&s_lostN[s_sreg[j] & 0x7fff], 1);
+    } else {
+      for (int j = 0; j < cn; ++j) {
+        const int r = s_sreg[j];
+        const uint8_t* row = s_sqty + shift + j * row_bytes;
+        int rem[SPL];
+        int dsum = 0;
+        MARLSC_UNROLL
+        for (int jj = 0; jj < SPL; ++jj) {
+          const int s = tm.gl + G * jj;
+          int d = 0;
+          if (s < S) d = qb == 1 ? (int)row[s] : (int)reinterpret_cast<const uint16_t*>(row)[s];
+          rem[jj] = d;
+          dsum += d;
+        }
+        if (!tm.any(dsum > 0)) continue;                         // all-zero order: nothing can ship or be lost
+        // home-region demand of this step (multi_env.py:763-768)
+        if (!dh_mode) {
+        } else if (!(CAPS & C_BIGW) || tb.hmask) {
+          uint32_t hm = tb.hmask[r];
+          while (hm) {
+            const int w = lowest_bit(hm);
+            hm &= hm - 1;
             MARLSC_UNROLL
             for (int jj = 0; jj < SPL; ++jj) {
               const int s = tm.gl + G * jj;
               if (s < S && rem[jj] > 0) dh_acc[w * S + s] += rem[jj];
             }
           }
-      }
-      const uint8_t* prio;
-      if (!(CAPS & C_DYNPRIO) || tb.pstat[r]) {
-        prio = tb.prio + r * ((W + 3) & ~3);
-      } else {
-        // warehouse order depends on the order's weight: key = fixed + variable * weight in float64,
-        // stable ascending (demand_allocator.py:168-173; ties to the lowest index)
-        double wt = 0.0;
-        MARLSC_UNROLL
-        for (int jj = 0; jj < SPL; ++jj) {
-          const int s = tm.gl + G * jj;
-          if (s < S) wt += (double)rem[jj] * tb.skw[s];
-        }
-        const double wtot = tm.sum(wt);
-        if (tm.gl == 0) {
-          for (int w = 0; w < W; ++w) {
-            const double key = d_add(sp.out_fixed[w * R + r], d_mul(sp.out_var[w * R + r], wtot));
-            int pos = w;
-            while (pos > 0) {
-              const int pw = s_prio[pos - 1];
-              const double pk = d_add(sp.out_fixed[pw * R + r], d_mul(sp.out_var[pw * R + r], wtot));
-              if (pk <= key) break;
-              s_prio[pos] = (uint8_t)pw;
-              --pos;
-            }
-            s_prio[pos] = (uint8_t)w;
-          }
-        }
-        tm.sync();
-        prio = s_prio;
-      }
-      // the order's priority list, four warehouses per register (W <= 16 in the packed form)
-      uint32_t pk[4] = {0u, 0u, 0u, 0u};
-      const bool packed = W <= 16;
-      if (packed) {
-        MARLSC_UNROLL
-        for (int q4 = 0; q4 < 4; ++q4)
-          if (q4 * 4 < W) pk[q4] = reinterpret_cast<const uint32_t*>(prio)[q4];   // rows are 4-byte aligned, see spec_build.h
-      }
-      int used = 0;
-      bool left = true;
-      constexpr bool kCount = (CAPS & (C_SPLITLIM | C_FIXED | C_DIAG)) != 0;   // else: no per-order bookkeeping
-      for (int v = 0; v < W; ++v) {
-        if ((CAPS & C_SPLITLIM) && used >= sp.max_splits + 1) break;
-        int w;
-        if (packed) {
-          const uint32_t word = (v & 8) ? ((v & 4) ? pk[3] : pk[2]) : ((v & 4) ? pk[1] : pk[0]);
-          w = (int)((word >> ((v & 3) * 8)) & 0xffu);
         } else {
-          w = prio[v];
-        }
-        int32_t* inv_w = s_inv + w * S;
-        const bool is_home = need_ship && (sp.home[w] == r);
-        int fsum = 0, rsum = 0;
-        double wsum = 0.0;
-        MARLSC_UNROLL
-        for (int jj = 0; jj < SPL; ++jj) {
-          const int s = tm.gl + G * jj;            // rem[jj] > 0 implies s < S (rows beyond S were loaded as 0)
-          const int a = rem[jj] > 0 ? inv_w[s] : 0;
-          const int f = imin(rem[jj], a);
-          if (f > 0) inv_w[s] = a - f;
-          rem[jj] -= f;
-          fsum += f;
-          rsum += rem[jj];
-          if ((CAPS & (C_WEIGHT | C_SHIP | C_DIAG)) && f > 0) {
-            if (!unit_w) wsum += (double)f * tb.skw[s];
-            if (need_ship) {
-              s_st[w * S + s] += f;
-              if (is_home) s_sh[w * S + s] += f;
+          for (int w = 0; w < W; ++w)
+            if (sp.home[w] == r) {
+              MARLSC_UNROLL
+              for (int jj = 0; jj < SPL; ++jj) {
+                const int s = tm.gl + G * jj;
+                if (s < S && rem[jj] > 0) dh_acc[w * S + s] += rem[jj];
+              }
             }
-            if (kDiag && io.d_ship) io.d_ship[((e * W + w) * R + r) * S + s] += f;
+        }
+        const uint8_t* prio;
+        if (!(CAPS & C_DYNPRIO) || tb.pstat[r]) {
+          prio = tb.prio + r * ((W + 3) & ~3);
+        } else {
+          // warehouse order depends on the order's weight: key = fixed + variable * weight in float64,
+          // stable ascending (demand_allocator.py:168-173; ties to the lowest index)
+          double wt = 0.0;
+          MARLSC_UNROLL
+          for (int jj = 0; jj < SPL; ++jj) {
+            const int s = tm.gl + G * jj;
+            if (s < S) wt += (double)rem[jj] * tb.skw[s];
           }
-        }
-        // Only two votes sit on the order's critical path; the shipped totals go to shared memory
-        // with (warp-aggregated) atomic adds that nobody waits for.
-        if (fsum > 0) {
-          smem_add(&s_shipq[w * R + r], fsum);
-          if (!unit_w) smem_add(&s_shipw[w * R + r], wsum);
-        }
-        if (kCount) {
-          const unsigned shipped = tm.ballot(fsum > 0);
-          if (shipped == 0u) continue;                         // this warehouse had nothing the order needs
-          if ((has_fixed || kDiag) && tm.gl == lowest_bit(shipped)) {
-            if (has_fixed) s_cnt[w * R + r] += 1;
-            if (kDiag && io.d_ship_count) io.d_ship_count[(e * W + w) * R + r] += 1;
+          const double wtot = tm.sum(wt);
+          if (tm.gl == 0) {
+            for (int w = 0; w < W; ++w) {
+              const double key = d_add(sp.out_fixed[w * R + r], d_mul(sp.out_var[w * R + r], wtot));
+              int pos = w;
+              while (pos > 0) {
+                const int pw = s_prio[pos - 1];
+                const double pk = d_add(sp.out_fixed[pw * R + r], d_mul(sp.out_var[pw * R + r], wtot));
+                if (pk <= key) break;
+                s_prio[pos] = (uint8_t)pw;
+                --pos;
+              }
+              s_prio[pos] = (uint8_t)w;
+            }
           }
-          ++used;
+          tm.sync();
+          prio = s_prio;
         }
-        left = tm.any(rsum > 0);
-        if (!left) break;
-      }
-      // whatever is left is lost (demand_allocator.py:205-208)
-      if (left) {
-        double lw = 0.0, lp = 0.0;
-        MARLSC_UNROLL
-        for (int jj = 0; jj < SPL; ++jj) {
-          const int s = tm.gl + G * jj;
-          if (s < S && rem[jj] > 0) {
-            lw += (double)rem[jj] * tb.skw[s];
-            lp += (double)rem[jj] * tb.pen[s];
-            if (kDiag && io.d_unfulfilled) io.d_unfulfilled[(e * R + r) * S + s] += rem[jj];
+        // the order's priority list, four warehouses per register (W <= 16 in the packed form)
+        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+        const bool packed = W <= 16;
+        if (packed) {
+          MARLSC_UNROLL
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (q4 * 4 < W) pk[q4] = reinterpret_cast<const uint32_t*>(prio)[q4];   // rows are 4-byte aligned, see spec_build.h
+        }
+        int used = 0;
+        bool left = true;
+        constexpr bool kCount = (CAPS & (C_SPLITLIM | C_FIXED | C_DIAG)) != 0;   // else: no per-order bookkeeping
+        for (int v = 0; v < W; ++v) {
+          if ((CAPS & C_SPLITLIM) && used >= sp.max_splits + 1) break;
+          int w;
+          if (packed) {
+            const uint32_t word = (v & 8) ? ((v & 4) ? pk[3] : pk[2]) : ((v & 4) ? pk[1] : pk[0]);
+            w = (int)((word >> ((v & 3) * 8)) & 0xffu);
+          } else {
+            w = prio[v];
           }
+          int32_t* inv_w = s_inv + w * S;
+          const bool is_home = need_ship && (sp.home[w] == r);
+          int fsum = 0, rsum = 0;
+          double wsum = 0.0;
+          MARLSC_UNROLL
+          for (int jj = 0; jj < SPL; ++jj) {
+            const int s = tm.gl + G * jj;            // rem[jj] > 0 implies s < S (rows beyond S were loaded as 0)
+            const int a = rem[jj] > 0 ? inv_w[s] : 0;
+            const int f = imin(rem[jj], a);
+            if (f > 0) inv_w[s] = a - f;
+            rem[jj] -= f;
+            fsum += f;
+            rsum += rem[jj];
+            if ((CAPS & (C_WEIGHT | C_SHIP | C_DIAG)) && f > 0) {
+              if (!unit_w) wsum += (double)f * tb.skw[s];
+              if (need_ship) {
+                s_st[w * S + s] += f;
+                if (is_home) s_sh[w * S + s] += f;
+              }
+              if (kDiag && io.d_ship) io.d_ship[((e * W + w) * R + r) * S + s] += f;
+            }
+          }
+          // Only two votes sit on the order's critical path; the shipped totals go to shared memory
+          // with (warp-aggregated) atomic adds that nobody waits for.
+          if (fsum > 0) {
+            smem_add(&s_shipq[w * R + r], fsum);
+            if (!unit_w) smem_add(&s_shipw[w * R + r], wsum);
+          }
+          if (kCount) {
+            const unsigned shipped = tm.ballot(fsum > 0);
+            if (shipped == 0u) continue;                         // this warehouse had nothing the order needs
+            if ((has_fixed || kDiag) && tm.gl == lowest_bit(shipped)) {
+              if (has_fixed) s_cnt[w * R + r] += 1;
+              if (kDiag && io.d_ship_count) io.d_ship_count[(e * W + w) * R + r] += 1;
+            }
+            ++used;
+          }
+          left = tm.any(rsum > 0);
+          if (!left) break;
         }
-        lw = tm.sum(lw);
-        lp = tm.sum(lp);
-        if (tm.gl == 0) {
-          s_lostN[r] += 1;
-          s_lostW[r] += lw;
-          s_lostP[r] += lp;
-          if (kDiag && io.d_lost_orders) io.d_lost_orders[e * R + r] += 1;
+        // whatever is left is lost (demand_allocator.py:205-208)
+        if (left) {
+          double lw = 0.0, lp = 0.0;
+          MARLSC_UNROLL
+          for (int jj = 0; jj < SPL; ++jj) {
+            const int s = tm.gl + G * jj;
+            if (s < S && rem[jj] > 0) {
+              lw += (double)rem[jj] * tb.skw[s];
+              lp += (double)rem[jj] * tb.pen[s];
+              if (kDiag && io.d_unfulfilled) io.d_unfulfilled[(e * R + r) * S + s] += rem[jj];
+            }
+          }
+          lw = tm.sum(lw);
+          lp = tm.sum(lp);
+          if (tm.gl == 0) {
+            s_lostN[r] += 1;
+            s_lostW[r] += lw;
+            s_lostP[r] += lp;
+            if (kDiag && io.d_lost_orders) io.d_lost_orders[e * R + r] += 1;
+          }
         }
       }
     }
@@ -893,7 +1058,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       if (s < S) {
         const int i = base + s;
         vI[j] = s_inv[i];
-        if (dh_mode) vdh[j] = dh_acc[i];
+        if (dh_mode) vdh[j] = (LaneAlloc<G, CAPS>::value && dh_mode == 1) ? load_cg(&dh_acc[i]) : dh_acc[i];
         vq[j] = ring_new[i];
         if (need_ship) {
           vsh[j] = s_sh[i];

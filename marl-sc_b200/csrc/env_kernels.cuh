@@ -4,6 +4,7 @@
 // CTA layout: kBlock threads = kBlock/G teams, one environment each. Dynamic shared memory:
 //   [ lookup tables shared by the CTA | per-team double scratch ... | per-team word scratch ... ]
 #pragma once
+#include <cstdlib>
 #include "lib_common.h"
 #include "spec_build.h"
 
@@ -91,7 +92,8 @@ inline size_t step_smem_bytes(const DevSpec& ds, int G) {
 template <int G, int SPL, uint32_t CAPS>
 int launch_step_caps(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s) {
   const int teams = kBlock / G;
-  const size_t smem = step_smem_bytes(a.ds, G);
+  size_t smem = step_smem_bytes(a.ds, G);
+  if (const char* pad = getenv("MARLSC_EXP_SMEM_PAD")) smem += (size_t)atoi(pad);   // occupancy experiment
   if ((int)smem > a.max_smem_optin)
     return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
   static thread_local size_t configured = 0;

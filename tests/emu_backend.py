@@ -18,19 +18,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "emu.cpp")
 OUT = os.path.join(HERE, "emu", "_build", "libmarlsc_emu.so")
+OUT_LANES = os.path.join(HERE, "emu", "_build", "libmarlsc_emu_lanes.so")   # wide-team (per-lane chains) allocation
 _DEPS = [SRC, os.path.join(ROOT, "marl-sc_b200", "csrc", "env_core.cuh"),
          os.path.join(ROOT, "marl-sc_b200", "csrc", "spec_build.h"), os.path.join(ROOT, "include", "marlsc_b200.h")]
-_lib = None
+_libs = {}
 
 
-def emu_lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in _DEPS):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", OUT, SRC])
-    L = C.CDLL(OUT)
+def emu_lib(lanes: bool = False):
+    if lanes in _libs:
+        return _libs[lanes]
+    out = OUT_LANES if lanes else OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in _DEPS):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               f"-DMARLSC_FORCE_LANE_ALLOC={int(lanes)}", "-o", out, SRC])
+    L = C.CDLL(out)
     L.emu_env_create.argtypes = [C.POINTER(_capi.EnvSpecC), C.POINTER(C.c_void_p)]
     L.emu_env_reset.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.c_void_p, C.c_int, C.c_void_p]
     L.emu_env_step.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.POINTER(_capi.StepIOC), C.c_int]
@@ -40,7 +42,7 @@ def emu_lib():
     for fn in ("emu_env_obs_dim", "emu_env_needs_history", "emu_env_needs_forecast"):
         getattr(L, fn).argtypes = [C.c_void_p]
     L.emu_last_error.restype = C.c_char_p
-    _lib = L
+    _libs[lanes] = L
     return L
 
 
@@ -49,8 +51,8 @@ def _p(a: Optional[np.ndarray]):
 
 
 class EmuBatch:
-    def __init__(self, spec: EnvSpec, num_envs: int):
-        L = emu_lib()
+    def __init__(self, spec: EnvSpec, num_envs: int, lanes: bool = False):
+        L = self.L = emu_lib(lanes)
         self.spec, self.E = spec, num_envs
         self._c = spec.to_c()
         h = C.c_void_p()
@@ -73,7 +75,7 @@ class EmuBatch:
         init = np.ascontiguousarray(init_inventory, dtype=np.int32)
         obs = np.zeros((self.E, self.W, self.obs_dim), np.float32)
         per_env = int(init.ndim == 3)
-        assert emu_lib().emu_env_reset(self.h, C.byref(self.state), _p(init), per_env, _p(obs)) == 0
+        assert self.L.emu_env_reset(self.h, C.byref(self.state), _p(init), per_env, _p(obs)) == 0
         return obs
 
     def step_lean(self, t: int, actions: np.ndarray, orders: OrderBatch) -> Dict[str, np.ndarray]:
@@ -83,7 +85,7 @@ class EmuBatch:
         o = dict(rewards=np.zeros((E, W), np.float32), obs=np.zeros((E, W, self.obs_dim), np.float32), trunc=np.zeros(E, np.uint8))
         io = _capi.StepIOC(_p(act), _p(orders.offsets), _p(orders.region), _p(orders.qty), orders.qty_bytes, None,
                            _p(o["rewards"]), _p(o["obs"]), _p(o["trunc"]), None, None, None, None, None, None, None)
-        assert emu_lib().emu_env_step_lean(self.h, C.byref(self.state), C.byref(io), t) == 0
+        assert self.L.emu_env_step_lean(self.h, C.byref(self.state), C.byref(io), t) == 0
         o["inventory"] = self.inv.copy()
         return o
 
@@ -100,9 +102,9 @@ class EmuBatch:
                            _p(o["rewards"]), _p(o["obs"]), _p(o["trunc"]), _p(o["cost_breakdown"]), _p(o["ordered"]),
                            _p(o["ship_by_sku"]), _p(o["ship_counts"]), _p(o["unfulfilled"]), _p(o["lost_orders"]),
                            _p(o["lost_sales"]))
-        assert emu_lib().emu_env_step(self.h, C.byref(self.state), C.byref(io), t) == 0
+        assert self.L.emu_env_step(self.h, C.byref(self.state), C.byref(io), t) == 0
         o["inventory"] = self.inv.copy()
         return o
 
     def close(self):
-        emu_lib().emu_env_destroy(self.h)
+        self.L.emu_env_destroy(self.h)

@@ -38,13 +38,15 @@ def test_emu_region_map_equals_premapped_demand():
     b.close()
 
 
+# lanes=True: the wide-team allocation (independent per-lane chains) forced onto the one-lane emulation
+@pytest.mark.parametrize("lanes", [False, True], ids=["dense", "lanes"])
 @pytest.mark.parametrize("name", ["small_default", "regions_ne_warehouses", "large_network"])
-def test_emu_lean_instantiation_matches_reference(name):
+def test_emu_lean_instantiation_matches_reference(name, lanes):
     """Configurations the lean kernel instantiation covers (independent per-SKU allocation chains, no
     diagnostics) replayed through it on the CPU."""
     g = Golden(name)
     _, spec = spec_for(g)
-    b = EmuBatch(spec, g.N)
+    b = EmuBatch(spec, g.N, lanes=lanes)
     b.reset(g["init_inventory"])
     for t in range(g.T):
         compare_step(g, t, b.step_lean(t, g["actions"][:, t], step_orders(g, t)), what="emu lean ")
