@@ -276,7 +276,7 @@ def run_ours(args):
     cfg = environment_config_from_dict(d)
     E = args.envs or cfg_desc["envs_per_gpu"]
     W, S = cfg.n_warehouses, cfg.n_skus
-    env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False, team_size=args.team)
+    env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False, team_size=args.team, fused_kernel=args.fused)
     L = _capi.lib()
 
     gen = torch.Generator(device=dev)
@@ -584,6 +584,7 @@ def main():
     ap.add_argument("--workload", default="large", choices=["large", "small", "ippo", "mappo"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--team", type=int, default=0, help="threads per env (0 = auto)")
+    ap.add_argument("--fused", action="store_true", help="keep the step in the single fused kernel (comparison)")
     ap.add_argument("--distinct-steps", type=int, default=8, help="uniform policy: distinct pre-sampled input steps cycled through")
     ap.add_argument("--policy", default="base_stock", choices=["base_stock", "uniform"],
                     help="pre-sampled actions: recorded base-stock heuristic (default) or uniform noise")

@@ -168,12 +168,16 @@ void marlsc_env_destroy(marlsc_env_t* env);
 int32_t marlsc_env_obs_dim(const marlsc_env_t* env);
 int32_t marlsc_env_needs_history(const marlsc_env_t* env);
 int32_t marlsc_env_needs_forecast(const marlsc_env_t* env);
-/* Threads cooperating on one environment (1..256, power of two). 0 restores the automatic choice. */
+/* Threads cooperating on one environment (1..64, power of two; 64 = two warps, lean launches only, generic
+ * launches then use 32). 0 restores the automatic choice. */
 int marlsc_env_set_team_size(marlsc_env_t* env, int32_t threads_per_env);
 int32_t marlsc_env_team_size(const marlsc_env_t* env);
 /* The library holds a lean and a generic instantiation of the step kernel and picks the lean one when
  * the configuration allows it; on != 0 forces the generic one (used by the parity tests). */
 int marlsc_env_set_generic(marlsc_env_t* env, int32_t on);
+/* Lean launches of teams of 8+ lanes run the step as four kernels (place / allocate / features / rewards, see
+ * csrc/env_split.cuh); on != 0 keeps them in the single fused kernel (used for comparisons and by the tests). */
+int marlsc_env_set_fused(marlsc_env_t* env, int32_t on);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

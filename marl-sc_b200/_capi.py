@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
     L.marlsc_env_set_team_size.restype = C.c_int
     L.marlsc_env_set_generic.argtypes = [vp, i32]
     L.marlsc_env_set_generic.restype = C.c_int
+    L.marlsc_env_set_fused.argtypes = [vp, i32]
+    L.marlsc_env_set_fused.restype = C.c_int
     L.marlsc_env_reset.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
     L.marlsc_env_reset.restype = C.c_int
     L.marlsc_env_step.argtypes = [vp, C.POINTER(EnvStateC), C.POINTER(StepIOC), i32, vp]

@@ -138,50 +138,74 @@ struct Scratch {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Team: G lanes (aligned slice of a warp) working on one environment.
+// Team: G lanes (an aligned slice of a warp, or G/32 whole warps) working on one environment.
 // ------------------------------------------------------------------------------------------------
 template <int G>
 struct Team {
   int gl;    // lane inside the team
 #ifndef MARLSC_HOST_EMU
+  // G <= 32: an aligned slice of one warp, synchronised with warp-level primitives.
+  // G  > 32: G/32 whole warps; team-wide steps go through a named barrier (id 1 + team index in the CTA)
+  //          and a few doubles of static shared memory (xs) for the cross-warp sums.
   unsigned gmask;
-  __device__ __forceinline__ void init() {
+  int bar;
+  double* xs;
+  __device__ __forceinline__ void init(double* xchg = nullptr) {
     gl = threadIdx.x % G;
     const int wl = threadIdx.x & 31;
-    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1)));
+    gmask = (G >= 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (wl & ~(G - 1)));
+    bar = 1 + threadIdx.x / G;
+    xs = G > 32 ? xchg + (threadIdx.x / G) * (G / 32) : nullptr;
   }
   __device__ __forceinline__ void sync() const {
-    if (G > 1) __syncwarp(gmask);
+    if (G > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(G) : "memory");
+    else if (G > 1) __syncwarp(gmask);
   }
   __device__ __forceinline__ bool any(bool p) const {
     if (G == 1) return p;
+    if (G > 32) {
+      int r;
+      asm volatile("{ .reg .pred q, o; setp.ne.s32 q, %1, 0; bar.red.or.pred o, %2, %3, q; selp.s32 %0, 1, 0, o; }"
+                   : "=r"(r) : "r"((int)p), "r"(bar), "n"(G) : "memory");
+      return r != 0;
+    }
     return __ballot_sync(gmask, p) != 0u;
   }
-  // lanes of the team for which p holds, as a bit mask relative to the team's first lane
+  // vote among the lanes of this team that share a warp (all of them for G <= 32)
+  __device__ __forceinline__ bool warp_any(bool p) const {
+    if (G == 1) return p;
+    return __ballot_sync(gmask, p) != 0u;
+  }
+  // lanes of the team for which p holds, as a bit mask relative to the team's first lane (G <= 32 only)
   __device__ __forceinline__ unsigned ballot(bool p) const {
+    static_assert(G <= 32, "ballot needs a team inside one warp");
     if (G == 1) return p ? 1u : 0u;
     const unsigned b = __ballot_sync(gmask, p) & gmask;
     return G == 32 ? b : (b >> ((threadIdx.x & 31) & ~(G - 1)));
   }
-  __device__ __forceinline__ int sum(int v) const {
+  template <typename T>
+  __device__ __forceinline__ T sum_t(T v) const {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    for (int o = (G > 32 ? 32 : G) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    if (G > 32) {
+      if ((threadIdx.x & 31) == 0) xs[gl >> 5] = (double)v;      // int / float / double all fit a double exactly
+      sync();
+      double r = 0.0;
+#pragma unroll
+      for (int i = 0; i < G / 32; ++i) r += xs[i];
+      sync();
+      v = (T)r;
+    }
     return v;
   }
-  __device__ __forceinline__ float sum(float v) const {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-    return v;
-  }
-  __device__ __forceinline__ double sum(double v) const {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-    return v;
-  }
+  __device__ __forceinline__ int sum(int v) const { return sum_t(v); }
+  __device__ __forceinline__ float sum(float v) const { return sum_t(v); }
+  __device__ __forceinline__ double sum(double v) const { return sum_t(v); }
 #else
-  void init() { gl = 0; }
+  void init(double* = nullptr) { gl = 0; }
   void sync() const {}
   bool any(bool p) const { return p; }
+  bool warp_any(bool p) const { return p; }
   unsigned ballot(bool p) const { return p ? 1u : 0u; }
   int sum(int v) const { return v; }
   float sum(float v) const { return v; }
@@ -655,16 +679,16 @@ MDEV void write_obs_row(const DevSpec& sp, const Tables& tb, const Team<G>& tm, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// One environment, one step.
+// Phase 2 of a step: sequential greedy allocation of environment e's orders against the stock in the
+// team's shared-memory scratch (demand_allocator.py:150-208). Shared by the fused step kernel and the
+// allocation kernel of the split step (env_split.cuh). Expects s_inv filled, the shipped / lost
+// accumulators zeroed and the team synchronised; leaves the team unsynchronised.
 // ------------------------------------------------------------------------------------------------
 template <int G, int SPL, uint32_t CAPS>
-MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const Scratch& sc,
-                   const marlsc_env_state_t& st, const marlsc_step_io_t& io, int64_t e, int t) {
-  const int W = sp.W, S = sp.S, R = sp.R, D = sp.D, WS = W * S;
-  const EnvPtrs p = env_ptrs(sp, st, e);
-
+MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const Scratch& sc, const EnvPtrs& p,
+                          const marlsc_step_io_t& io, int64_t e, int32_t* dh_acc, int dh_mode) {
+  const int W = sp.W, S = sp.S, R = sp.R;
   int32_t* s_inv = sc.w + sp.w_inv;
-  int32_t* s_dh = sc.w + sp.w_dh;
   int32_t* s_sh = sc.w + sp.w_sh;
   int32_t* s_st = sc.w + sp.w_st;
   int32_t* s_shipq = sc.w + sp.w_shipq;
@@ -675,87 +699,13 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
   uint8_t* s_sqty = reinterpret_cast<uint8_t*>(sc.w + sp.w_sqty);
   double* s_lostW = sc.d + sp.d_lostW;
   double* s_lostP = sc.d + sp.d_lostP;
-  double* s_ctot = sc.d + sp.d_ctot;
   double* s_shipw = sc.d + sp.d_shipw;
-
-  const float* act = pinned(io.actions + e * WS);
-  const bool fixed_lead = !(CAPS & C_STOCH) || sp.lead_mode == MARLSC_LEAD_FIXED;
   const bool need_ship = (CAPS & C_SHIP) && sp.need_ship;
-  const bool need_fcst = (CAPS & C_FCST) && sp.need_fcst;
   const bool unit_w = !(CAPS & C_WEIGHT) || sp.unit_weights;
-  const bool direct = !(CAPS & C_ACTX) || sp.action_type == MARLSC_ACTION_DIRECT;
-  constexpr bool kDiag = (CAPS & C_DIAG) != 0;
-  const uint8_t* lead_new = fixed_lead ? nullptr : io.actual_lead + e * WS;
-  const int slot_new = t % D;
-  int32_t* ring_new = pinned(p.ring_q + slot_new * WS);
-  // accumulator of this step's home-region demand per (warehouse, SKU)
-  const int dh_mode = (CAPS & C_DHSMEM) ? sp.dh_mode : (sp.dh_mode == 1 ? 1 : 0);
-  int32_t* const dh_acc = dh_mode == 1 ? pinned(p.hist + (t % kWindow) * WS) : s_dh;
   const bool has_fixed = (CAPS & C_FIXED) && sp.has_fixed;
+  constexpr bool kDiag = (CAPS & C_DIAG) != 0;
+  (void)p; (void)s_cnt; (void)s_prio; (void)s_sh; (void)s_st; (void)s_shipw; (void)has_fixed; (void)kDiag;
 
-  // ---- phase 1: orders in, arrivals in (multi_env.py:287-292) ------------------------------------
-  for (int w = 0; w < W; ++w) {
-    const int base = w * S;
-    float a_in[SPL];
-    int inv_in[SPL], arr_in[SPL], le[SPL];
-    MARLSC_UNROLL
-    for (int j = 0; j < SPL; ++j) {                 // issue every load of this row first
-      const int s = tm.gl + G * j;
-      a_in[j] = 0.f;
-      inv_in[j] = arr_in[j] = le[j] = 0;
-      if (s < S) {
-        const int i = base + s;
-        le[j] = tb.lead[i];
-        a_in[j] = act[i];
-        inv_in[j] = p.inv[i];
-        if (fixed_lead) {
-          int row = slot_new - le[j];               // plane of the order placed at t - le
-          if (row < 0) row += D;
-          arr_in[j] = p.ring_q[row * WS + i];        // t < le: plane not written since reset, reads 0
-        }
-      }
-    }
-    MARLSC_UNROLL
-    for (int j = 0; j < SPL; ++j) {
-      const int s = tm.gl + G * j;
-      if (s < S) {
-        const int i = base + s;
-        int prev_dem = 0, pend = 0;
-        if (!direct) {
-          if (t > 0) prev_dem = p.hist[pmod(t - 1, kWindow) * WS + i];
-          if (sp.action_type == MARLSC_ACTION_BASE_STOCK) pend = pending_before(sp, p, t, i, le[j]);
-        }
-        if ((CAPS & C_STOCH) && !fixed_lead) arr_in[j] = arrivals_stoch(sp, p, t, i);   // reads the ring before the slot is reused
-        const int q = rescale_action<CAPS>(sp, a_in[j], sp.action_max[s], prev_dem, pend);
-        s_inv[i] = inv_in[j] + arr_in[j];
-        ring_new[i] = q;
-        if (lead_new) p.ring_l[slot_new * WS + i] = lead_new[i];
-        if (dh_mode) dh_acc[i] = 0;
-        if (need_ship) {
-          s_sh[i] = 0;
-          s_st[i] = 0;
-        }
-        if (kDiag && io.d_ordered) io.d_ordered[e * WS + i] = q;
-      }
-    }
-    tm.sync();   // stochastic lead times / small teams: cells of this row were written by other lanes
-#ifndef MARLSC_EXP_NOPIPE
-    write_obs_pipeline<G, SPL, CAPS>(sp, tb, tm, p, io.obs + (e * W + w) * (int64_t)sp.obs_dim, w, t);
-#endif
-  }
-  for (int i = tm.gl; i < W * R; i += G) {
-    s_shipq[i] = 0;
-    if (has_fixed) s_cnt[i] = 0;
-    if (!unit_w) s_shipw[i] = 0.0;
-  }
-  for (int i = tm.gl; i < R; i += G) {
-    s_lostN[i] = 0;
-    s_lostW[i] = 0.0;
-    s_lostP[i] = 0.0;
-  }
-  tm.sync();
-
-  // ---- phase 2: sequential greedy allocation of this step's orders (demand_allocator.py:150-208)
   // CSR (offsets) or padded layout (row e * stride, count[e]); the latter is what the device sampler writes
   const long long o_begin = io.order_counts ? e * (long long)io.order_stride : (long long)io.order_offsets[e];
   const int n_orders = io.order_counts ? io.order_counts[e] : io.order_offsets[e + 1] - (int)o_begin;
@@ -796,33 +746,36 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       // it is filled or lost - one list step per loop trip, every lane on its own line. Orders stay in
       // sequence per SKU, which is all the sequential semantics of demand_allocator.py:150-208 asks for
       // when no split limit binds; the lanes only meet again at the end of the pass.
-      constexpr int NWL = SPL >= 4 ? SPL / 4 : 1;                     // row words per lane
-      constexpr int KG = NWL < 16 ? NWL : 16;                        // row words per lane and pass
-      constexpr int kPassOrders = 16 / KG;
+      constexpr int CW = SPL >= 4 ? 4 : SPL;                          // cells per lane and row group (1, 2 or 4 bytes)
+      constexpr int NWL = SPL / CW;                                   // row groups per lane
+      constexpr int KG = NWL < 16 ? NWL : 16;                        // row groups per lane and pass
+      constexpr int kPassOrders = 64 / (CW * KG);                     // CW * KG mask bits per order, 64 in all
       const bool aligned = shift == 0 && (S & 3) == 0;
       const uint8_t* rows = s_sqty + shift;
       const int Wp = (W + 3) & ~3;
       for (int j0 = 0; j0 < cn; j0 += kPassOrders)
       for (int k0 = 0; k0 < NWL; k0 += KG) {
         const int pn = imin(kPassOrders, cn - j0);
-        uint32_t mlo = 0, mhi = 0;                                    // orders 0-7 / 8-15 of the pass (KG = 1)
+        uint32_t mlo = 0, mhi = 0;                                    // non-zero cells of the pass, order-major
         for (int jj = 0; jj < pn; ++jj) {
           const uint8_t* row = rows + (j0 + jj) * row_bytes;
           MARLSC_UNROLL
           for (int k = 0; k < KG; ++k) {
-            const int c0s = 4 * (tm.gl + G * (k0 + k));               // first SKU of this word
+            const int c0s = CW * (tm.gl + G * (k0 + k));              // first SKU of this group
             uint32_t word = 0;
-            if (aligned) {
-              if (c0s < S) word = *reinterpret_cast<const uint32_t*>(row + c0s);
-            } else {
+            if (aligned && c0s < S) {
+              if (CW == 4) word = *reinterpret_cast<const uint32_t*>(row + c0s);
+              else if (CW == 2) word = *reinterpret_cast<const uint16_t*>(row + c0s);
+              else word = row[c0s];
+            } else if (!aligned) {
               MARLSC_UNROLL
-              for (int b = 0; b < 4; ++b)
+              for (int b = 0; b < CW; ++b)
                 if (c0s + b < S) word |= (uint32_t)row[c0s + b] << (8 * b);
             }
             // bit 7 of every non-zero byte, gathered into the low four bits
             uint32_t nz = (((word & 0x7f7f7f7fu) + 0x7f7f7f7fu) | word) & 0x80808080u;
             nz = (((nz >> 7) * 0x204081u) >> 21) & 0xfu;
-            const int at = 4 * (jj * KG + k);
+            const int at = CW * (jj * KG + k);
             if (at < 32) mlo |= nz << at; else mhi |= nz << (at - 32);
           }
         }
@@ -837,9 +790,9 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
               bit = 32 + lowest_bit(mhi);
               mhi &= mhi - 1;
             }
-            const int slot = bit >> 2;
+            const int slot = bit / CW;
             oj = j0 + slot / KG;
-            sku = 4 * (tm.gl + G * (k0 + slot % KG)) + (bit & 3);
+            sku = CW * (tm.gl + G * (k0 + slot % KG)) + bit % CW;
             rem = rows[oj * row_bytes + sku];
             r = s_sreg[oj] & 0x7fff;
             v = 0;
@@ -878,7 +831,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
               rem = 0;
             }
           }
-          if (!tm.any(rem > 0 || (mlo | mhi) != 0)) break;
+          if (!tm.warp_any(rem > 0 || (mlo | mhi) != 0)) break;   // the team's warps run their chains apart
         }
       }
       tm.sync();
@@ -1038,6 +991,106 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
     }
     tm.sync();
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One environment, one step.
+// ------------------------------------------------------------------------------------------------
+template <int G, int SPL, uint32_t CAPS>
+MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const Scratch& sc,
+                   const marlsc_env_state_t& st, const marlsc_step_io_t& io, int64_t e, int t) {
+  const int W = sp.W, S = sp.S, R = sp.R, D = sp.D, WS = W * S;
+  const EnvPtrs p = env_ptrs(sp, st, e);
+
+  int32_t* s_inv = sc.w + sp.w_inv;
+  int32_t* s_dh = sc.w + sp.w_dh;
+  int32_t* s_sh = sc.w + sp.w_sh;
+  int32_t* s_st = sc.w + sp.w_st;
+  int32_t* s_shipq = sc.w + sp.w_shipq;
+  int32_t* s_cnt = sc.w + sp.w_cnt;
+  int32_t* s_lostN = sc.w + sp.w_lostN;
+  double* s_lostW = sc.d + sp.d_lostW;
+  double* s_lostP = sc.d + sp.d_lostP;
+  double* s_ctot = sc.d + sp.d_ctot;
+  double* s_shipw = sc.d + sp.d_shipw;
+
+  const float* act = pinned(io.actions + e * WS);
+  const bool fixed_lead = !(CAPS & C_STOCH) || sp.lead_mode == MARLSC_LEAD_FIXED;
+  const bool need_ship = (CAPS & C_SHIP) && sp.need_ship;
+  const bool need_fcst = (CAPS & C_FCST) && sp.need_fcst;
+  const bool unit_w = !(CAPS & C_WEIGHT) || sp.unit_weights;
+  const bool direct = !(CAPS & C_ACTX) || sp.action_type == MARLSC_ACTION_DIRECT;
+  constexpr bool kDiag = (CAPS & C_DIAG) != 0;
+  const uint8_t* lead_new = fixed_lead ? nullptr : io.actual_lead + e * WS;
+  const int slot_new = t % D;
+  int32_t* ring_new = pinned(p.ring_q + slot_new * WS);
+  // accumulator of this step's home-region demand per (warehouse, SKU)
+  const int dh_mode = (CAPS & C_DHSMEM) ? sp.dh_mode : (sp.dh_mode == 1 ? 1 : 0);
+  int32_t* const dh_acc = dh_mode == 1 ? pinned(p.hist + (t % kWindow) * WS) : s_dh;
+  const bool has_fixed = (CAPS & C_FIXED) && sp.has_fixed;
+
+  // ---- phase 1: orders in, arrivals in (multi_env.py:287-292) ------------------------------------
+  for (int w = 0; w < W; ++w) {
+    const int base = w * S;
+    float a_in[SPL];
+    int inv_in[SPL], arr_in[SPL], le[SPL];
+    MARLSC_UNROLL
+    for (int j = 0; j < SPL; ++j) {                 // issue every load of this row first
+      const int s = tm.gl + G * j;
+      a_in[j] = 0.f;
+      inv_in[j] = arr_in[j] = le[j] = 0;
+      if (s < S) {
+        const int i = base + s;
+        le[j] = tb.lead[i];
+        a_in[j] = act[i];
+        inv_in[j] = p.inv[i];
+        if (fixed_lead) {
+          int row = slot_new - le[j];               // plane of the order placed at t - le
+          if (row < 0) row += D;
+          arr_in[j] = p.ring_q[row * WS + i];        // t < le: plane not written since reset, reads 0
+        }
+      }
+    }
+    MARLSC_UNROLL
+    for (int j = 0; j < SPL; ++j) {
+      const int s = tm.gl + G * j;
+      if (s < S) {
+        const int i = base + s;
+        int prev_dem = 0, pend = 0;
+        if (!direct) {
+          if (t > 0) prev_dem = p.hist[pmod(t - 1, kWindow) * WS + i];
+          if (sp.action_type == MARLSC_ACTION_BASE_STOCK) pend = pending_before(sp, p, t, i, le[j]);
+        }
+        if ((CAPS & C_STOCH) && !fixed_lead) arr_in[j] = arrivals_stoch(sp, p, t, i);   // reads the ring before the slot is reused
+        const int q = rescale_action<CAPS>(sp, a_in[j], sp.action_max[s], prev_dem, pend);
+        s_inv[i] = inv_in[j] + arr_in[j];
+        ring_new[i] = q;
+        if (lead_new) p.ring_l[slot_new * WS + i] = lead_new[i];
+        if (dh_mode) dh_acc[i] = 0;
+        if (need_ship) {
+          s_sh[i] = 0;
+          s_st[i] = 0;
+        }
+        if (kDiag && io.d_ordered) io.d_ordered[e * WS + i] = q;
+      }
+    }
+    tm.sync();   // stochastic lead times / small teams: cells of this row were written by other lanes
+    write_obs_pipeline<G, SPL, CAPS>(sp, tb, tm, p, io.obs + (e * W + w) * (int64_t)sp.obs_dim, w, t);
+  }
+  for (int i = tm.gl; i < W * R; i += G) {
+    s_shipq[i] = 0;
+    if (has_fixed) s_cnt[i] = 0;
+    if (!unit_w) s_shipw[i] = 0.0;
+  }
+  for (int i = tm.gl; i < R; i += G) {
+    s_lostN[i] = 0;
+    s_lostW[i] = 0.0;
+    s_lostP[i] = 0.0;
+  }
+  tm.sync();
+
+  // ---- phase 2: sequential greedy allocation of this step's orders (demand_allocator.py:150-208)
+  allocate_orders<G, SPL, CAPS>(sp, tb, tm, sc, p, io, e, dh_acc, dh_mode);
   tm.sync();
 
   // ---- phase 3: per warehouse - state write-back, feature buffers, costs, observation row ----------

@@ -1,5 +1,5 @@
 // env_inst_g8.cu - K1 instantiations for teams of 8 lanes (SKUs per lane: 1 4).
-#include "env_kernels.cuh"
+#include "env_split.cuh"
 #define STEP_CASES \
   MARLSC_SPL_CASE(8, 1, launch_step_t, a, io, t, s) \
   MARLSC_SPL_CASE(8, 4, launch_step_t, a, io, t, s) \
@@ -9,3 +9,4 @@
   MARLSC_SPL_CASE(8, 4, launch_reset_t, a, init, per_env, obs, s) \
 
 MARLSC_DEFINE_G(8, STEP_CASES, RESET_CASES)
+MARLSC_DEFINE_SPLIT(8, MARLSC_SPLIT_CASE(8, 1) MARLSC_SPLIT_CASE(8, 4))

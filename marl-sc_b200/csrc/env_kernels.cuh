@@ -1,16 +1,21 @@
 // env_kernels.cuh - K1 kernels (step / reset) and their templated launchers. Included by one
 // translation unit per team width G (env_inst_g*.cu) so the instantiations compile in parallel.
 //
-// CTA layout: kBlock threads = kBlock/G teams, one environment each. Dynamic shared memory:
+// CTA layout: block_threads(G) threads = four teams (more for narrow teams), one environment each. Dynamic shared memory:
 //   [ lookup tables shared by the CTA | per-team double scratch ... | per-team word scratch ... ]
 #pragma once
-#include <cstdlib>
 #include "lib_common.h"
 #include "spec_build.h"
 
 namespace marlsc {
 
-constexpr int kBlock = 128;
+// Threads per CTA: 128 for teams inside a warp, four teams for multi-warp teams.
+template <int G>
+struct Block {
+  static constexpr int threads = G <= 32 ? 128 : 4 * G;
+  static constexpr int teams = threads / G;
+};
+inline int block_teams(int G) { return G <= 32 ? 128 / G : 4; }
 
 struct LaunchArgs {
   DevSpec ds;
@@ -45,22 +50,29 @@ __device__ __forceinline__ Tables stage_tables(const DevSpec& sp, unsigned char*
 // Geometries for which the lean instantiation is built (the automatic choices of auto_team_size()).
 constexpr bool has_lean(int G, int SPL) {
   return (G == 1 && (SPL == 2 || SPL == 4 || SPL == 8)) || (G == 4 && SPL == 4) || (G == 8 && SPL == 4) ||
-         (G == 16 && SPL == 4) || (G == 32 && (SPL == 4 || SPL == 8 || SPL == 16));
+         (G == 16 && SPL == 4) || (G == 32 && (SPL == 4 || SPL == 8 || SPL == 16)) || G > 32;
+}
+// Multi-warp teams exist for the lean instantiation only (the generic allocation votes across the team per
+// warehouse visit, which does not pay across warps); the host falls back to 32 lanes for generic launches.
+constexpr bool has_generic(int G) { return G <= 32; }
+constexpr int min_blocks(int G, uint32_t CAPS) {
+  return CAPS != kCapsLean ? 1 : (G == 32 ? 6 : (G > 32 ? 4 : 1));   // two-warp teams: 64 registers beat a fifth CTA
 }
 
 template <int G, int SPL, uint32_t CAPS>
-__global__ void __launch_bounds__(kBlock, (CAPS == kCapsLean && G == 32) ? 6 : 1)
+__global__ void __launch_bounds__(Block<G>::threads, min_blocks(G, CAPS))
 env_step_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                 const __grid_constant__ marlsc_step_io_t io, int t) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int TEAMS = kBlock / G;
+  __shared__ double xchg[Block<G>::threads / 32];
+  constexpr int TEAMS = Block<G>::teams;
   const Tables tb = stage_tables(sp, smem);
   __syncthreads();
   const int team = threadIdx.x / G;
   const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
   if (e >= st.num_envs) return;   // whole teams leave together; everything below is team-local
   Team<G> tm;
-  tm.init();
+  tm.init(xchg);
   Scratch sc;
   unsigned char* base = smem + sp.t_bytes;
   sc.d = reinterpret_cast<double*>(base) + (size_t)team * sp.d_words;
@@ -69,40 +81,46 @@ env_step_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marl
 }
 
 template <int G, int SPL, uint32_t CAPS>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(Block<G>::threads)
 env_reset_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                  const int32_t* __restrict__ init_inventory, int per_env, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int TEAMS = kBlock / G;
+  __shared__ double xchg[Block<G>::threads / 32];
+  constexpr int TEAMS = Block<G>::teams;
   const Tables tb = stage_tables(sp, smem);
   __syncthreads();
   const int team = threadIdx.x / G;
   const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
   if (e >= st.num_envs) return;
   Team<G> tm;
-  tm.init();
+  tm.init(xchg);
   reset_env<G, SPL, CAPS>(sp, tb, tm, st, init_inventory, per_env, obs, e);
 }
 
 inline size_t step_smem_bytes(const DevSpec& ds, int G) {
-  const int teams = kBlock / G;
+  const int teams = block_teams(G);
   return (size_t)ds.t_bytes + (size_t)teams * ((size_t)ds.d_words * sizeof(double) + (size_t)ds.w_words * sizeof(int32_t));
 }
 
 template <int G, int SPL, uint32_t CAPS>
 int launch_step_caps(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s) {
-  const int teams = kBlock / G;
-  size_t smem = step_smem_bytes(a.ds, G);
-  if (const char* pad = getenv("MARLSC_EXP_SMEM_PAD")) smem += (size_t)atoi(pad);   // occupancy experiment
+  const int teams = Block<G>::teams;
+  const size_t smem = step_smem_bytes(a.ds, G);
   if ((int)smem > a.max_smem_optin)
     return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
   static thread_local size_t configured = 0;
+  static thread_local bool carveout = false;
+  if (!carveout) {   // the scratch is what bounds residency: ask for the largest shared-memory carveout
+    MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_kernel<G, SPL, CAPS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+    carveout = true;
+  }
   if (smem > 48 * 1024 && smem > configured) {
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_kernel<G, SPL, CAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const unsigned grid = (unsigned)((a.st.num_envs + teams - 1) / teams);
-  env_step_kernel<G, SPL, CAPS><<<grid, kBlock, smem, s>>>(a.ds, a.st, io, t);
+  env_step_kernel<G, SPL, CAPS><<<grid, Block<G>::threads, smem, s>>>(a.ds, a.st, io, t);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;
@@ -113,15 +131,16 @@ int launch_step_t(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaSt
   if constexpr (has_lean(G, SPL)) {
     if (a.lean) return launch_step_caps<G, SPL, kCapsLean>(a, io, t, s);
   }
-  return launch_step_caps<G, SPL, kCapsAll>(a, io, t, s);
+  if constexpr (has_generic(G)) return launch_step_caps<G, SPL, kCapsAll>(a, io, t, s);
+  return set_error(MARLSC_EUNSUPPORTED, "multi-warp teams run the lean instantiation only");
 }
 
 template <int G, int SPL, uint32_t CAPS>
 int launch_reset_caps(const LaunchArgs& a, const int32_t* init, int per_env, float* obs, cudaStream_t s) {
-  const int teams = kBlock / G;
+  const int teams = Block<G>::teams;
   const size_t smem = (size_t)a.ds.t_bytes;
   const unsigned grid = (unsigned)((a.st.num_envs + teams - 1) / teams);
-  env_reset_kernel<G, SPL, CAPS><<<grid, kBlock, smem, s>>>(a.ds, a.st, init, per_env, obs);
+  env_reset_kernel<G, SPL, CAPS><<<grid, Block<G>::threads, smem, s>>>(a.ds, a.st, init, per_env, obs);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;
@@ -146,6 +165,7 @@ MARLSC_DECLARE_G(4)
 MARLSC_DECLARE_G(8)
 MARLSC_DECLARE_G(16)
 MARLSC_DECLARE_G(32)
+MARLSC_DECLARE_G(64)
 
 #define MARLSC_SPL_CASE(G, SPL, FN, ...) case SPL: return FN<G, SPL>(__VA_ARGS__);
 #define MARLSC_DEFINE_G(G, CASES_STEP, CASES_RESET)                                                           \

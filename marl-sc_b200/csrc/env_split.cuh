@@ -1,0 +1,276 @@
+// env_split.cuh - the step of the common configurations as a sequence of four kernels (K1a..K1d).
+//
+// The fused kernel (env_kernels.cuh) keeps one environment's stock, shipped totals and order staging in
+// shared memory for the whole step, which caps it at 24 warps per SM although only the allocation needs
+// that scratch. For configurations the lean capability set covers (fixed lead times, direct actions, static
+// warehouse priority, unit SKU weights, inventory / pipeline / home-demand / rolling-mean blocks, no
+// diagnostics) the step is split along its data dependencies instead:
+//
+//   K1a place   - one team per (environment, warehouse) row, no shared memory: action -> order quantity
+//                 into the ring (multi_env.py:819-903), arrivals added to the inventory in place
+//                 (multi_env.py:905-919), this step's home-demand plane cleared, pipeline block of the
+//                 observation row written (multi_env.py:603-633, 941-968). Pure streaming.
+//   K1b allocate- one team per environment with the shared-memory scratch: inventory in, greedy allocation
+//                 (allocate_orders), inventory out, outbound + lost-sales cost of every warehouse.
+//   K1c features- one team per row, no shared memory: holding and inbound cost, rolling mean, the remaining
+//                 blocks of the observation row (multi_env.py:577-710, 747-793). Pure streaming.
+//   K1d rewards - one thread per environment: cost -> reward per agent or team (multi_env.py:316-327),
+//                 truncation flag.
+//
+// Results are the fused kernel's up to the order of float64 additions in the cost sums.
+#pragma once
+#include "env_kernels.cuh"
+
+namespace marlsc {
+
+struct SplitWork {
+  double* cost_alloc;   // [E,W] outbound + penalty cost (K1b)
+  double* cost_rows;    // [E,W] holding + inbound cost (K1c)
+};
+
+// Lookup tables straight from global memory (a few KB, read-only, L1 resident) for the kernels without scratch.
+MDEV Tables global_tables(const DevSpec& sp) {
+  Tables tb;
+  tb.skw = sp.skw;
+  tb.pen = sp.pen_rate;
+  tb.hold = sp.hold_rate;
+  tb.prio = sp.prio;
+  tb.pstat = sp.prio_static;
+  tb.hmask = sp.home_mask;
+  tb.lead = sp.lead_u8;
+  return tb;
+}
+
+// ---- K1a ------------------------------------------------------------------------------------------
+template <int G, int SPL>
+__global__ void __launch_bounds__(128)
+env_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
+                 const __grid_constant__ marlsc_step_io_t io, int t) {
+  constexpr uint32_t CAPS = kCapsLean;
+  const int W = sp.W, S = sp.S, D = sp.D, WS = W * S;
+  const int64_t row = (int64_t)blockIdx.x * (128 / G) + threadIdx.x / G;
+  if (row >= st.num_envs * W) return;
+  Team<G> tm;
+  tm.init();
+  const int64_t e = row / W;
+  const int w = (int)(row - e * W);
+  const Tables tb = global_tables(sp);
+  const EnvPtrs p = env_ptrs(sp, st, e);
+  const float* act = pinned(io.actions + e * WS);
+  const int slot_new = t % D;
+  int32_t* ring_new = pinned(p.ring_q + slot_new * WS);
+  int32_t* dh_plane = sp.dh_mode == 1 ? p.hist + (t % kWindow) * WS : nullptr;
+  const int base = w * S;
+  float a_in[SPL];
+  int inv_in[SPL], arr_in[SPL];
+  MARLSC_UNROLL
+  for (int j = 0; j < SPL; ++j) {                   // every load of the row first
+    const int s = tm.gl + G * j;
+    a_in[j] = 0.f;
+    inv_in[j] = arr_in[j] = 0;
+    if (s < S) {
+      const int i = base + s;
+      int src = slot_new - (int)tb.lead[i];         // plane of the order placed at t - lead
+      if (src < 0) src += D;
+      a_in[j] = act[i];
+      arr_in[j] = p.ring_q[src * WS + i];           // t < lead: plane not written since reset, reads 0
+      inv_in[j] = p.inv[i];
+    }
+  }
+  MARLSC_UNROLL
+  for (int j = 0; j < SPL; ++j) {
+    const int s = tm.gl + G * j;
+    if (s < S) {
+      const int i = base + s;
+      ring_new[i] = rescale_action<CAPS>(sp, a_in[j], sp.action_max[s], 0, 0);
+      if (arr_in[j] != 0) p.inv[i] = inv_in[j] + arr_in[j];
+      if (dh_plane) dh_plane[i] = 0;
+    }
+  }
+  // the cells of a lane's pipeline slots are its own: no team synchronisation needed before reading them back
+  write_obs_pipeline<G, SPL, CAPS>(sp, tb, tm, p, io.obs + row * (int64_t)sp.obs_dim, w, t);
+}
+
+// ---- K1b ------------------------------------------------------------------------------------------
+template <int G, int SPL>
+__global__ void __launch_bounds__(Block<G>::threads, G >= 32 ? (G > 32 ? 4 : 6) : 1)
+env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
+                 const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_alloc, int t) {
+  constexpr uint32_t CAPS = kCapsLean;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double xchg[Block<G>::threads / 32];
+  constexpr int TEAMS = Block<G>::teams;
+  const Tables tb = stage_tables(sp, smem);
+  __syncthreads();
+  const int team = threadIdx.x / G;
+  const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
+  if (e >= st.num_envs) return;
+  Team<G> tm;
+  tm.init(xchg);
+  Scratch sc;
+  unsigned char* sbase = smem + sp.t_bytes;
+  sc.d = reinterpret_cast<double*>(sbase) + (size_t)team * sp.d_words;
+  sc.w = reinterpret_cast<int32_t*>(sbase + (size_t)TEAMS * sp.d_words * sizeof(double)) + (size_t)team * sp.w_words;
+
+  const int W = sp.W, S = sp.S, R = sp.R, WS = W * S;
+  const EnvPtrs p = env_ptrs(sp, st, e);
+  int32_t* s_inv = sc.w + sp.w_inv;
+  int32_t* s_shipq = sc.w + sp.w_shipq;
+  int32_t* s_lostN = sc.w + sp.w_lostN;
+  double* s_lostW = sc.d + sp.d_lostW;
+  double* s_lostP = sc.d + sp.d_lostP;
+  for (int i0 = 0; i0 < WS; i0 += 4 * G) {           // inventory in, four cells per lane in flight
+    int v[4];
+    MARLSC_UNROLL
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + tm.gl + G * k;
+      v[k] = i < WS ? p.inv[i] : 0;
+    }
+    MARLSC_UNROLL
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + tm.gl + G * k;
+      if (i < WS) s_inv[i] = v[k];
+    }
+  }
+  for (int i = tm.gl; i < W * R; i += G) s_shipq[i] = 0;
+  for (int i = tm.gl; i < R; i += G) {
+    s_lostN[i] = 0;
+    s_lostW[i] = 0.0;
+    s_lostP[i] = 0.0;
+  }
+  tm.sync();
+
+  const int dh_mode = sp.dh_mode == 1 ? 1 : 0;
+  int32_t* const dh_acc = dh_mode ? pinned(p.hist + (t % kWindow) * WS) : nullptr;
+  allocate_orders<G, SPL, CAPS>(sp, tb, tm, sc, p, io, e, dh_acc, dh_mode);
+  tm.sync();
+
+  for (int i = tm.gl; i < WS; i += G) p.inv[i] = s_inv[i];      // multi_env.py:307 (never negative)
+  // outbound cost and lost-sales penalty of every warehouse: lanes over regions (reward_calculator.py:150-175)
+  for (int w = 0; w < W; ++w) {
+    double c = 0.0;
+    for (int r = tm.gl; r < R; r += G) {
+      const int sq = s_shipq[w * R + r];
+      if (sq > 0) c += (double)sq * sp.out_var[w * R + r];
+      if (s_lostN[r] > 0) c += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * s_lostP[r];
+    }
+    c = tm.sum(c);
+    if (tm.gl == 0) cost_alloc[e * W + w] = c;
+  }
+}
+
+// ---- K1c ------------------------------------------------------------------------------------------
+template <int G, int SPL>
+__global__ void __launch_bounds__(128)
+env_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
+                   const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_rows, int t) {
+  constexpr uint32_t CAPS = kCapsLean;
+  const int W = sp.W, S = sp.S, D = sp.D, WS = W * S;
+  const int64_t row = (int64_t)blockIdx.x * (128 / G) + threadIdx.x / G;
+  if (row >= st.num_envs * W) return;
+  Team<G> tm;
+  tm.init();
+  const int64_t e = row / W;
+  const int w = (int)(row - e * W);
+  const Tables tb = global_tables(sp);
+  const EnvPtrs p = env_ptrs(sp, st, e);
+  const int32_t* ring_new = pinned(p.ring_q + (t % D) * WS);
+  const int hist_n = imin(t + 1, kWindow);
+  const int base = w * S;
+  int vI[SPL], vdh[SPL], vz[SPL], vq[SPL], hsum[SPL];
+  float vrm[SPL], vf[SPL];
+  MARLSC_UNROLL
+  for (int j = 0; j < SPL; ++j) {                   // loads first
+    const int s = tm.gl + G * j;
+    vI[j] = vdh[j] = vz[j] = vq[j] = hsum[j] = 0;
+    vrm[j] = vf[j] = 0.f;
+    if (s < S) {
+      const int i = base + s;
+      vI[j] = p.inv[i];
+      vq[j] = ring_new[i];
+      if (sp.need_hist) {
+        vdh[j] = load_cg(&p.hist[(t % kWindow) * WS + i]);     // accumulated by K1b with fire-and-forget adds
+        MARLSC_UNROLL
+        for (int back = 1; back < kWindow; ++back)
+          if (back < hist_n) hsum[j] += p.hist[pmod(t - back, kWindow) * WS + i];
+      }
+    }
+  }
+  double cost = 0.0;
+  MARLSC_UNROLL
+  for (int j = 0; j < SPL; ++j) {
+    const int s = tm.gl + G * j;
+    if (s < S) {
+      const int i = base + s;
+      cost += (double)vI[j] * tb.hold[s];                                                     // holding
+      if (vq[j] > 0) cost += sp.in_fixed[i] + ((double)vq[j] * tb.skw[s]) * sp.in_var[i];    // inbound
+      // integer-valued float32 sum over the window is exact in any order (multi_env.py:785-787)
+      if (sp.need_hist) vrm[j] = f_div((float)(hsum[j] + vdh[j]), (float)hist_n);
+    }
+  }
+  cost = tm.sum(cost);
+  if (tm.gl == 0) cost_rows[row] = cost;
+  write_obs_row<G, SPL, CAPS>(sp, tb, tm, p, io.obs + row * (int64_t)sp.obs_dim, w, t, hist_n, vI, vdh, vz, vz, vrm, vf);
+}
+
+// ---- K1d ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+env_reward_kernel(const __grid_constant__ DevSpec sp, int64_t num_envs, const double* __restrict__ cost_alloc,
+                  const double* __restrict__ cost_rows, float* __restrict__ rewards, uint8_t* __restrict__ truncated, int t);
+
+// One launcher per (G, SPL); defined through MARLSC_DEFINE_SPLIT in the per-width translation units.
+template <int G, int SPL>
+int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitWork& wk, int t, cudaStream_t s) {
+  constexpr int GR = G > 32 ? 32 : G;               // the row kernels never need more than a warp per row
+  constexpr int SPLR = G > 32 ? SPL * (G / 32) : SPL;
+  const int64_t rows = a.st.num_envs * a.ds.W;
+  const unsigned grid_rows = (unsigned)((rows + 128 / GR - 1) / (128 / GR));
+  env_place_kernel<GR, SPLR><<<grid_rows, 128, 0, s>>>(a.ds, a.st, io, t);
+  MARLSC_CUDA(cudaGetLastError());
+
+  const size_t smem = step_smem_bytes(a.ds, G);
+  if ((int)smem > a.max_smem_optin)
+    return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
+  static thread_local size_t configured = 0;
+  static thread_local bool carveout = false;
+  if (!carveout) {
+    MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_alloc_kernel<G, SPL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+    carveout = true;
+  }
+  if (smem > 48 * 1024 && smem > configured) {
+    MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_alloc_kernel<G, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const unsigned grid_envs = (unsigned)((a.st.num_envs + Block<G>::teams - 1) / Block<G>::teams);
+  env_alloc_kernel<G, SPL><<<grid_envs, Block<G>::threads, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
+  MARLSC_CUDA(cudaGetLastError());
+
+  env_feature_kernel<GR, SPLR><<<grid_rows, 128, 0, s>>>(a.ds, a.st, io, wk.cost_rows, t);
+  MARLSC_CUDA(cudaGetLastError());
+
+  env_reward_kernel<<<(unsigned)((a.st.num_envs + 255) / 256), 256, 0, s>>>(a.ds, a.st.num_envs, wk.cost_alloc, wk.cost_rows,
+                                                                           io.rewards, io.truncated, t);
+  MARLSC_CUDA(cudaGetLastError());
+  g_launches.fetch_add(4, std::memory_order_relaxed);
+  return MARLSC_OK;
+}
+
+#define MARLSC_DECLARE_SPLIT(G) \
+  int launch_split_g##G(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, const SplitWork& wk, int t, cudaStream_t s);
+MARLSC_DECLARE_SPLIT(8)
+MARLSC_DECLARE_SPLIT(16)
+MARLSC_DECLARE_SPLIT(32)
+MARLSC_DECLARE_SPLIT(64)
+
+#define MARLSC_SPLIT_CASE(G, SPL) case SPL: return launch_split_t<G, SPL>(a, io, wk, t, s);
+#define MARLSC_DEFINE_SPLIT(G, CASES)                                                                          \
+  namespace marlsc {                                                                                           \
+  int launch_split_g##G(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, const SplitWork& wk, int t,  \
+                        cudaStream_t s) {                                                                      \
+    switch (spl) { CASES default: break; }                                                                     \
+    return set_error(MARLSC_EUNSUPPORTED, "no split-step kernels instantiated for this team size / SKU count"); \
+  }                                                                                                            \
+  }
+
+}  // namespace marlsc

@@ -7,9 +7,26 @@
 #include <new>
 #include <string>
 
-#include "env_kernels.cuh"
+#include "env_split.cuh"
 
 namespace marlsc {
+
+// K1d of the split step (env_split.cuh): cost -> reward per agent or team (multi_env.py:316-327), truncation flag.
+__global__ void __launch_bounds__(256)
+env_reward_kernel(const __grid_constant__ DevSpec sp, int64_t num_envs, const double* __restrict__ cost_alloc,
+                  const double* __restrict__ cost_rows, float* __restrict__ rewards, uint8_t* __restrict__ truncated, int t) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= num_envs) return;
+  const int W = sp.W;
+  if (sp.scope == MARLSC_SCOPE_TEAM) {
+    double rew = 0.0;
+    for (int w = 0; w < W; ++w) rew += -((cost_rows[e * W + w] + cost_alloc[e * W + w]) * sp.scale);
+    for (int w = 0; w < W; ++w) rewards[e * W + w] = (float)rew;
+  } else {
+    for (int w = 0; w < W; ++w) rewards[e * W + w] = (float)(-((cost_rows[e * W + w] + cost_alloc[e * W + w]) * sp.scale));
+  }
+  if (truncated) truncated[e] = (uint8_t)(t + 1 >= sp.episode_length);
+}
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
@@ -33,6 +50,9 @@ struct marlsc_env {
   void* d_blob = nullptr;  // one allocation holding every device table
   int max_smem_optin = 0;
   int force_generic = 0;   // tests: always run the generic instantiation
+  int force_fused = 0;     // tests / comparisons: lean launches stay in the fused kernel
+  double* d_work = nullptr;    // split step: [2, work_envs, W] cost partials
+  int64_t work_envs = 0;
   cudaStream_t copy_stream = nullptr;        // marlsc_env_rollout_host: H2D copies of the next step
   cudaEvent_t ready[2] = {nullptr, nullptr};  // staging set filled
   cudaEvent_t done[2] = {nullptr, nullptr};   // staging set consumed by its step kernel
@@ -43,8 +63,8 @@ namespace {
 // SKUs-per-lane values instantiated for each team width (env_inst_g*.cu)
 int pick_spl(int G, int S) {
   static const int k1[] = {1, 2, 4, 8, 0}, k2[] = {1, 2, 4, 0}, k4[] = {1, 2, 4, 0}, k8[] = {1, 4, 0},
-                   k16[] = {1, 4, 8, 0}, k32[] = {1, 4, 8, 16, 0};
-  const int* tbl = G == 1 ? k1 : G == 2 ? k2 : G == 4 ? k4 : G == 8 ? k8 : G == 16 ? k16 : G == 32 ? k32 : nullptr;
+                   k16[] = {1, 4, 8, 0}, k32[] = {1, 4, 8, 16, 0}, k64[] = {2, 4, 8, 0};
+  const int* tbl = G == 1 ? k1 : G == 2 ? k2 : G == 4 ? k4 : G == 8 ? k8 : G == 16 ? k16 : G == 32 ? k32 : G == 64 ? k64 : nullptr;
   if (!tbl) return 0;
   const int need = skus_per_lane(S, G);
   for (; *tbl; ++tbl)
@@ -86,6 +106,8 @@ int set_team(marlsc_env* env, int G) {
   if (!spl)
     return set_error(MARLSC_EUNSUPPORTED, "team size " + std::to_string(G) + " cannot hold " + std::to_string(env->ds.S) +
                                               " SKUs (at most 16 per lane, 512 SKUs in total); use a wider team");
+  if (G > 32 && !pick_spl(32, env->ds.S))
+    return set_error(MARLSC_EUNSUPPORTED, "a two-warp team needs the 32-lane instantiation as its generic fallback");
   env->team = G;
   env->spl = spl;
   return MARLSC_OK;
@@ -99,8 +121,32 @@ int set_team(marlsc_env* env, int G) {
     case 8: return FN##8(__VA_ARGS__);                                                     \
     case 16: return FN##16(__VA_ARGS__);                                                   \
     case 32: return FN##32(__VA_ARGS__);                                                   \
-    default: return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,32]"); \
+    case 64: return FN##64(__VA_ARGS__);                                                   \
+    default: return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,64]"); \
   }
+
+// Split-step workspace (cost partials between K1b/K1c and K1d), grown on demand. Growing synchronises the
+// device, so reset sizes it up front.
+int ensure_work(marlsc_env* env, int64_t num_envs) {
+  if (env->work_envs >= num_envs) return MARLSC_OK;
+  if (env->d_work) {
+    MARLSC_CUDA(cudaDeviceSynchronize());
+    MARLSC_CUDA(cudaFree(env->d_work));
+    env->d_work = nullptr;
+    env->work_envs = 0;
+  }
+  MARLSC_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->d_work), sizeof(double) * 2 * (size_t)num_envs * env->ds.W));
+  env->work_envs = num_envs;
+  return MARLSC_OK;
+}
+
+// The split step covers what the lean instantiation covers, for teams of at least 8 lanes (and the SKUs-per-lane
+// values the automatic team choice produces).
+bool split_ok(const marlsc_env* env) {
+  if (env->force_fused) return false;
+  const int g = env->team, k = env->spl;   // instantiated pairs, see MARLSC_DEFINE_SPLIT in env_inst_g*.cu
+  return ((g == 8 || g == 16) && (k == 1 || k == 4)) || (g == 32 && (k == 1 || k == 4 || k == 8 || k == 16)) || g == 64;
+}
 
 int check_state(const marlsc_env* env, const marlsc_env_state_t* st) {
   if (!env || !st) return set_error(MARLSC_EINVAL, "null handle or state");
@@ -195,6 +241,7 @@ void marlsc_env_destroy(marlsc_env_t* env) {
     if (env->done[i]) cudaEventDestroy(env->done[i]);
   }
   if (env->d_blob) cudaFree(env->d_blob);
+  if (env->d_work) cudaFree(env->d_work);
   delete env;
 }
 
@@ -206,13 +253,19 @@ int32_t marlsc_env_team_size(const marlsc_env_t* env) { return env ? env->team :
 int marlsc_env_set_team_size(marlsc_env_t* env, int32_t tpe) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
   if (tpe == 0) return set_team(env, env->team_auto);
-  if (tpe < 1 || tpe > 32 || (tpe & (tpe - 1))) return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,32]");
+  if (tpe < 1 || tpe > 64 || (tpe & (tpe - 1))) return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,64]");
   return set_team(env, tpe);
 }
 
 int marlsc_env_set_generic(marlsc_env_t* env, int32_t on) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
   env->force_generic = on ? 1 : 0;
+  return MARLSC_OK;
+}
+
+int marlsc_env_set_fused(marlsc_env_t* env, int32_t on) {
+  if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  env->force_fused = on ? 1 : 0;
   return MARLSC_OK;
 }
 
@@ -223,8 +276,15 @@ int marlsc_env_reset(marlsc_env_t* env, const marlsc_env_state_t* state, const i
   if (!init_inventory || !obs) return set_error(MARLSC_EINVAL, "init_inventory and obs must not be NULL");
   MARLSC_CUDA(cudaSetDevice(env->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (split_ok(env)) {
+    rc = ensure_work(env, state->num_envs);
+    if (rc) return rc;
+  }
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, false};
-  MARLSC_DISPATCH_G(env->team, launch_reset_g, env->spl, la, init_inventory, per_env, obs, s)
+  // the state layout does not depend on the team width: two-warp teams reset through the 32-lane kernel
+  const int team = env->team > 32 ? 32 : env->team;
+  const int spl = env->team > 32 ? pick_spl(32, env->ds.S) : env->spl;
+  MARLSC_DISPATCH_G(team, launch_reset_g, spl, la, init_inventory, per_env, obs, s)
 }
 
 int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* io, int32_t t, void* stream) {
@@ -243,7 +303,23 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool lean = !env->force_generic && (required_caps(env->ds, env->tb, io) & ~kCapsLean) == 0;
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
-  MARLSC_DISPATCH_G(env->team, launch_step_g, env->spl, la, *io, t, s)
+  if (lean && split_ok(env)) {
+    rc = ensure_work(env, state->num_envs);
+    if (rc) return rc;
+    const SplitWork wk{env->d_work, env->d_work + (size_t)env->work_envs * env->ds.W};
+    switch (env->team) {
+      case 8: return launch_split_g8(env->spl, la, *io, wk, t, s);
+      case 16: return launch_split_g16(env->spl, la, *io, wk, t, s);
+      case 32: return launch_split_g32(env->spl, la, *io, wk, t, s);
+      case 64: return launch_split_g64(env->spl, la, *io, wk, t, s);
+      default: break;
+    }
+  }
+  // two-warp teams exist for the lean instantiation only; generic launches fall back to 32 lanes
+  const bool narrow = env->team > 32 && !lean;
+  const int team = narrow ? 32 : env->team;
+  const int spl = narrow ? pick_spl(32, env->ds.S) : env->spl;
+  MARLSC_DISPATCH_G(team, launch_step_g, spl, la, *io, t, s)
 }
 
 int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* dev,

@@ -57,7 +57,7 @@ class BatchedInventoryEnv:
                  seed: Optional[int] = None, env_meta: Optional[Dict[str, Any]] = None,
                  region_map: Optional[Sequence[int]] = None, env_seeds: Optional[Sequence[int]] = None,
                  host_samplers: bool = True, diagnostics: bool = False, team_size: int = 0,
-                 generic_kernel: bool = False, device_demand: bool = False, demand_seed: int = 0,
+                 generic_kernel: bool = False, fused_kernel: bool = False, device_demand: bool = False, demand_seed: int = 0,
                  max_orders_per_env: Optional[int] = None):
         if num_envs < 1:
             raise ValueError("num_envs must be positive")
@@ -102,6 +102,8 @@ class BatchedInventoryEnv:
             _capi.check(L.marlsc_env_set_team_size(self._h, team_size))
         if generic_kernel:      # tests: bypass the lean instantiation of the step kernel
             _capi.check(L.marlsc_env_set_generic(self._h, 1))
+        if fused_kernel:        # comparisons: keep lean launches in the single fused kernel instead of the split step
+            _capi.check(L.marlsc_env_set_fused(self._h, 1))
         self.obs_dim = int(L.marlsc_env_obs_dim(self._h))            # local_obs_dim of the reference
         self.global_obs_dim = self.n_warehouses * self.obs_dim
 

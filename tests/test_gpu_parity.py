@@ -11,13 +11,13 @@ from parity_common import compare_step, spec_for, step_orders
 pytestmark = pytest.mark.gpu
 
 
-def _run(g, team_size=0, region_map=None, region_shift=None, steps=None, diagnostics=True, generic=False):
+def _run(g, team_size=0, region_map=None, region_shift=None, steps=None, diagnostics=True, generic=False, fused=False):
     from marlsc_b200.envs import BatchedInventoryEnv
     cfg, _ = spec_for(g)
     meta = dict(obs_normalization=g.meta["obs_normalization"], obs_stats=g.obs_stats,
                 include_warehouse_id=g.meta["include_warehouse_id"])
     env = BatchedInventoryEnv(cfg, g.N, device="cuda:0", env_meta=meta, host_samplers=False, diagnostics=diagnostics,
-                              team_size=team_size, region_map=region_map, generic_kernel=generic)
+                              team_size=team_size, region_map=region_map, generic_kernel=generic, fused_kernel=fused)
     # poison the state so reset has to clear it
     env.ring_qty.fill_(-5)
     env.inventory.fill_(123)
@@ -41,12 +41,14 @@ def test_cuda_matches_reference_auto_team(name):
     _run(Golden(name))
 
 
-@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("mode", ["auto", "fused", "generic"])
 @pytest.mark.parametrize("name", NAMES)
-def test_cuda_without_diagnostics(name, generic):
-    """No diagnostic outputs: configurations the lean step-kernel instantiation covers (small_default,
-    regions_ne_warehouses, large_network) run it; ``generic`` forces the generic instantiation instead."""
-    _run(Golden(name), diagnostics=False, generic=generic)
+def test_cuda_without_diagnostics(name, mode):
+    """No diagnostic outputs: configurations the lean capability set covers (small_default,
+    regions_ne_warehouses, large_network) run the lean path - the four-kernel split step for teams of 8+
+    lanes, else the lean fused kernel; ``fused`` keeps them in the fused kernel, ``generic`` forces the generic
+    instantiation."""
+    _run(Golden(name), diagnostics=False, generic=mode == "generic", fused=mode == "fused")
 
 
 @pytest.mark.parametrize("team", [1, 2, 4, 8, 16, 32])
@@ -60,11 +62,27 @@ def test_cuda_team_sizes_large(team):
     _run(Golden("large_network"), team_size=team, steps=6)
 
 
+@pytest.mark.parametrize("mode", ["split", "fused", "diagnostics"])
+def test_cuda_two_warp_team_large(mode):
+    """64 lanes per environment (two warps): the lean paths without diagnostics, the 32-lane generic fallback
+    with them."""
+    _run(Golden("large_network"), team_size=64, steps=8, diagnostics=mode == "diagnostics", fused=mode == "fused")
+
+
+@pytest.mark.parametrize("team", [8, 16, 32])
+@pytest.mark.parametrize("name", ["small_default", "regions_ne_warehouses"])
+def test_cuda_split_step_small_shapes(name, team):
+    """The split step on the small networks (teams wider than the automatic choice, one SKU per lane)."""
+    _run(Golden(name), team_size=team, diagnostics=False)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("team", [0, 64])
 @pytest.mark.parametrize("fixed_cost", [0.0, 2.0])
-def test_lean_equals_generic_under_stockouts(fixed_cost):
-    """The lean instantiation finishes leftover SKUs of an order with a warp prefix sum over the priority
-    list; the generic one walks warehouse by warehouse (and is itself pinned to the golden trajectories).
-    On a scarce-inventory large network (constant splitting, lost sales) both must agree exactly."""
+def test_lean_equals_generic_under_stockouts(fixed_cost, team, fused):
+    """The lean instantiation allocates through independent per-lane SKU chains (one or two warps per
+    environment); the generic one walks every order warehouse by warehouse (and is itself pinned to the golden
+    trajectories). On a scarce-inventory large network (constant splitting, lost sales) both must agree exactly."""
     from golden.scenarios import large_network
     from marlsc_b200.config import environment_config_from_dict
     from marlsc_b200.context import create_environment_context
@@ -84,7 +102,7 @@ def test_lean_equals_generic_under_stockouts(fixed_cost):
         smp = get_demand_sampler(cfg, context=create_environment_context(cfg))
         smp.reset(np.random.default_rng(100 + i))
         samplers.append(smp)
-    lean = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False)
+    lean = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, team_size=team, fused_kernel=fused)
     gen = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, generic_kernel=True)
     o1, o2 = lean.reset().clone(), gen.reset().clone()
     assert torch.equal(o1, o2)
