@@ -807,22 +807,32 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
               }
             }
           }
-          if (rem > 0) {                                              // one step down the priority list
-            const int w = tb.prio[r * Wp + v];
-            ++v;
-            int32_t* cell = s_inv + w * S + sku;
-            const int a = *cell;
-            const int f = imin(rem, a);
-            if (f > 0) {
-              *cell = a - f;
-              smem_add(&s_shipq[w * R + r], f);
-              if (!unit_w) smem_add(&s_shipw[w * R + r], (double)f * tb.skw[sku]);
-              if (need_ship) {
-                s_st[w * S + sku] += f;
-                if (sp.home[w] == r) s_sh[w * S + sku] += f;
-              }
+          if (rem > 0) {                                              // four warehouses down the priority list
+            // the stock cells of the line's SKU belong to this lane: the four reads go out together, the
+            // takes follow in priority order (rows of the priority table are padded to whole words)
+            const uint32_t pw = *reinterpret_cast<const uint32_t*>(tb.prio + r * Wp + v);
+            int a[4], wk[4];
+            MARLSC_UNROLL
+            for (int k = 0; k < 4; ++k) {
+              wk[k] = (int)((pw >> (8 * k)) & 0xffu);
+              a[k] = v + k < W ? s_inv[wk[k] * S + sku] : 0;
             }
-            rem -= f;
+            MARLSC_UNROLL
+            for (int k = 0; k < 4; ++k) {
+              const int f = imin(rem, a[k]);
+              if (f > 0) {
+                const int w = wk[k];
+                s_inv[w * S + sku] = a[k] - f;
+                smem_add(&s_shipq[w * R + r], f);
+                if (!unit_w) smem_add(&s_shipw[w * R + r], (double)f * tb.skw[sku]);
+                if (need_ship) {
+                  s_st[w * S + sku] += f;
+                  if (sp.home[w] == r) s_sh[w * S + sku] += f;
+                }
+              }
+              rem -= f;
+            }
+            v += 4;
             if (rem > 0 && v >= W) {
               // no warehouse can supply the rest: lost (demand_allocator.py:205-208)
               smem_add(&s_lostW[r], (double)rem * tb.skw[sku]);
