@@ -712,17 +712,50 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
   const int qb = (CAPS & C_QTY16) ? io.order_qty_bytes : 1;
   const int row_bytes = S * qb;
   const int och = qb == 1 ? sp.och : sp.och / 2;   // the staging area is sized for och one-byte rows
+  // Staging of a chunk: regions (mapped onto included regions) and quantity rows, as aligned words. When a
+  // lane's share of a chunk fits kPre registers the words of the NEXT chunk are requested before the current
+  // chunk is allocated and written to shared memory afterwards, so the allocation hides their latency.
+  constexpr int kPre = 12;
+  const bool prefetch = LaneAlloc<G, CAPS>::value && ((och * row_bytes + 6 + 3) >> 2) <= kPre * G && och <= G;
+  uint32_t pre[kPre];
+  int pre_r = 0, pre_shift = 0;
+  MARLSC_UNROLL
+  for (int k = 0; k < kPre; ++k) pre[k] = 0;
+  auto request = [&](int c0) {
+    const int cn = imin(och, n_orders - c0);
+    if (tm.gl < cn) pre_r = io.order_region[o_begin + c0 + tm.gl];
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(io.order_qty) + (int64_t)(o_begin + c0) * row_bytes;
+    pre_shift = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t* src_w = reinterpret_cast<const uint32_t*>(src - pre_shift);
+    const int nw = (pre_shift + cn * row_bytes + 3) >> 2;
+    MARLSC_UNROLL
+    for (int k = 0; k < kPre; ++k)
+      if (tm.gl + G * k < nw) pre[k] = src_w[tm.gl + G * k];
+  };
+  if (prefetch && n_orders > 0) request(0);
   for (int c0 = 0; c0 < n_orders; c0 += och) {
     const int cn = imin(och, n_orders - c0);
-    // stage the chunk: regions (mapped onto included regions) and quantity rows, as aligned words
-    for (int j = tm.gl; j < cn; j += G) {
-      int r = io.order_region[o_begin + c0 + j];
-      if ((CAPS & C_REGMAP) && sp.region_map) r = sp.region_map[r];
-      s_sreg[j] = (int16_t)r;
-    }
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(io.order_qty) + (int64_t)(o_begin + c0) * row_bytes;
-    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
-    {
+    int shift;
+    if (prefetch) {
+      if (tm.gl < cn) {
+        int r = pre_r;
+        if ((CAPS & C_REGMAP) && sp.region_map) r = sp.region_map[r];
+        s_sreg[tm.gl] = (int16_t)r;
+      }
+      shift = pre_shift;
+      uint32_t* dst_w = reinterpret_cast<uint32_t*>(s_sqty);
+      const int nw = (shift + cn * row_bytes + 3) >> 2;
+      MARLSC_UNROLL
+      for (int k = 0; k < kPre; ++k)
+        if (tm.gl + G * k < nw) dst_w[tm.gl + G * k] = pre[k];
+    } else {
+      for (int j = tm.gl; j < cn; j += G) {
+        int r = io.order_region[o_begin + c0 + j];
+        if ((CAPS & C_REGMAP) && sp.region_map) r = sp.region_map[r];
+        s_sreg[j] = (int16_t)r;
+      }
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(io.order_qty) + (int64_t)(o_begin + c0) * row_bytes;
+      shift = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
       const uint32_t* src_w = reinterpret_cast<const uint32_t*>(src - shift);
       uint32_t* dst_w = reinterpret_cast<uint32_t*>(s_sqty);
       const int nw = (shift + cn * row_bytes + 3) >> 2;
@@ -737,6 +770,7 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
       for (; k < nw; k += G) dst_w[k] = src_w[k];
     }
     tm.sync();
+    if (prefetch && c0 + och < n_orders) request(c0 + och);   // in flight while this chunk is allocated
     if constexpr (LaneAlloc<G, CAPS>::value) {
       // Wide teams, SKUs coupled only through the inventory: the greedy allocation of one SKU never looks
       // at another SKU, so every lane runs the chains of the SKUs it owns (four consecutive SKUs per

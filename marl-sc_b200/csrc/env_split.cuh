@@ -92,6 +92,42 @@ env_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
 }
 
 // ---- K1b ------------------------------------------------------------------------------------------
+// The allocation needs three of the lookup tables at shared-memory latency (warehouse priority per region,
+// static-priority flags, home-warehouse masks); the per-SKU rates are only touched when a line is lost and
+// stay in global memory. One round of loads per thread instead of one dependent round per table.
+__device__ __forceinline__ Tables stage_alloc_tables(const DevSpec& sp, unsigned char* smem) {
+  const int n_prio = (sp.R * ((sp.W + 3) & ~3)) >> 2, n_stat = (sp.R + 3) >> 2, n_mask = sp.home_mask ? sp.R : 0;
+  const int n = n_prio + n_stat + n_mask;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 2 * blockDim.x) {
+    uint32_t v[2];
+    uint32_t* dst[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = i0 + k * blockDim.x;
+      v[k] = 0;
+      dst[k] = nullptr;
+      if (i < n_prio) {
+        v[k] = reinterpret_cast<const uint32_t*>(sp.prio)[i];
+        dst[k] = reinterpret_cast<uint32_t*>(smem + sp.t_prio) + i;
+      } else if (i < n_prio + n_stat) {
+        v[k] = reinterpret_cast<const uint32_t*>(sp.prio_static)[i - n_prio];
+        dst[k] = reinterpret_cast<uint32_t*>(smem + sp.t_pstat) + (i - n_prio);
+      } else if (i < n) {
+        v[k] = sp.home_mask[i - n_prio - n_stat];
+        dst[k] = reinterpret_cast<uint32_t*>(smem + sp.t_hmask) + (i - n_prio - n_stat);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (dst[k]) *dst[k] = v[k];
+  }
+  Tables tb = global_tables(sp);
+  tb.prio = smem + sp.t_prio;
+  tb.pstat = smem + sp.t_pstat;
+  tb.hmask = sp.home_mask ? reinterpret_cast<const uint32_t*>(smem + sp.t_hmask) : nullptr;
+  return tb;
+}
+
 template <int G, int SPL>
 __global__ void __launch_bounds__(Block<G>::threads, G >= 32 ? (G > 32 ? 4 : 6) : 1)
 env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
@@ -100,7 +136,7 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double xchg[Block<G>::threads / 32];
   constexpr int TEAMS = Block<G>::teams;
-  const Tables tb = stage_tables(sp, smem);
+  const Tables tb = stage_alloc_tables(sp, smem);
   __syncthreads();
   const int team = threadIdx.x / G;
   const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
@@ -119,15 +155,15 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
   int32_t* s_lostN = sc.w + sp.w_lostN;
   double* s_lostW = sc.d + sp.d_lostW;
   double* s_lostP = sc.d + sp.d_lostP;
-  for (int i0 = 0; i0 < WS; i0 += 4 * G) {           // inventory in, four cells per lane in flight
-    int v[4];
+  for (int i0 = 0; i0 < WS; i0 += 8 * G) {           // inventory in, eight cells per lane in flight
+    int v[8];
     MARLSC_UNROLL
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const int i = i0 + tm.gl + G * k;
       v[k] = i < WS ? p.inv[i] : 0;
     }
     MARLSC_UNROLL
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const int i = i0 + tm.gl + G * k;
       if (i < WS) s_inv[i] = v[k];
     }
@@ -146,16 +182,42 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
   tm.sync();
 
   for (int i = tm.gl; i < WS; i += G) p.inv[i] = s_inv[i];      // multi_env.py:307 (never negative)
-  // outbound cost and lost-sales penalty of every warehouse: lanes over regions (reward_calculator.py:150-175)
-  for (int w = 0; w < W; ++w) {
-    double c = 0.0;
+  tm.sync();
+  // Outbound cost and lost-sales penalty of every warehouse (reward_calculator.py:150-175). Lanes take regions;
+  // a lane's partial sums per warehouse go to a [W][G + 1] tile laid over the stock scratch (written back above),
+  // then lane w adds up row w. Needs (W * (G + 1)) doubles <= W * S words, i.e. 2 * (G + 1) <= S.
+  const bool tiled = 2 * (G + 1) <= S && W <= G;
+  double* tile = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(s_inv + 1) & ~uintptr_t(7));
+  if (tiled) {
+    for (int w = 0; w < W; ++w) tile[w * (G + 1) + tm.gl] = 0.0;
     for (int r = tm.gl; r < R; r += G) {
-      const int sq = s_shipq[w * R + r];
-      if (sq > 0) c += (double)sq * sp.out_var[w * R + r];
-      if (s_lostN[r] > 0) c += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * s_lostP[r];
+      const bool lost = s_lostN[r] > 0;
+      const double lp = lost ? s_lostP[r] : 0.0;
+      for (int w = 0; w < W; ++w) {
+        const int sq = s_shipq[w * R + r];
+        double c = 0.0;
+        if (sq > 0) c = (double)sq * sp.out_var[w * R + r];
+        if (lost) c += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * lp;
+        if (sq > 0 || lost) tile[w * (G + 1) + tm.gl] += c;
+      }
     }
-    c = tm.sum(c);
-    if (tm.gl == 0) cost_alloc[e * W + w] = c;
+    tm.sync();
+    if (tm.gl < W) {
+      double c = 0.0;
+      for (int l = 0; l < G; ++l) c += tile[tm.gl * (G + 1) + l];
+      cost_alloc[e * W + tm.gl] = c;
+    }
+  } else {
+    for (int w = 0; w < W; ++w) {
+      double c = 0.0;
+      for (int r = tm.gl; r < R; r += G) {
+        const int sq = s_shipq[w * R + r];
+        if (sq > 0) c += (double)sq * sp.out_var[w * R + r];
+        if (s_lostN[r] > 0) c += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * s_lostP[r];
+      }
+      c = tm.sum(c);
+      if (tm.gl == 0) cost_alloc[e * W + w] = c;
+    }
   }
 }
 
