@@ -42,6 +42,9 @@ namespace marlsc {
 
 constexpr int kWindow = MARLSC_ROLLING_WINDOW;
 constexpr int kPipeBatch = 5;   // pipeline slots loaded together per cell
+#ifndef MARLSC_LANE_CHAINS
+#define MARLSC_LANE_CHAINS 1        // independent allocation chains a lane interleaves (1 or 2)
+#endif
 #ifndef MARLSC_FORCE_LANE_ALLOC
 #define MARLSC_FORCE_LANE_ALLOC 0   // the host emulation sets this to run the wide-team allocation with G == 1
 #endif
@@ -773,109 +776,104 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
     if (prefetch && c0 + och < n_orders) request(c0 + och);   // in flight while this chunk is allocated
     if constexpr (LaneAlloc<G, CAPS>::value) {
       // Wide teams, SKUs coupled only through the inventory: the greedy allocation of one SKU never looks
-      // at another SKU, so every lane runs the chains of the SKUs it owns (four consecutive SKUs per
-      // 32-bit word of a row) on its own. A pass covers up to kPassOrders staged orders: the lane first
-      // notes which of its cells are non-zero (4 bits per row word, 64 bits in all), then works through
-      // those lines in order - take the next line, walk it down the region's warehouse priority list until
-      // it is filled or lost - one list step per loop trip, every lane on its own line. Orders stay in
+      // at another SKU, so every lane runs the chains of the SKUs it owns (s = lane + G*j, as everywhere else)
+      // on its own. A pass covers up to kPassOrders staged orders: the lane first notes which of its cells
+      // are non-zero, then works through those lines in order - take the next line, walk it down the
+      // region's warehouse priority list (four warehouses per trip) until it is filled or lost. A lane runs
+      // TWO such chains side by side, over its even and its odd SKU slots, so that every trip carries two
+      // independent dependency chains and the longest lane finishes in about half the trips. Orders stay in
       // sequence per SKU, which is all the sequential semantics of demand_allocator.py:150-208 asks for
       // when no split limit binds; the lanes only meet again at the end of the pass.
-      constexpr int CW = SPL >= 4 ? 4 : SPL;                          // cells per lane and row group (1, 2 or 4 bytes)
-      constexpr int NWL = SPL / CW;                                   // row groups per lane
-      constexpr int KG = NWL < 16 ? NWL : 16;                        // row groups per lane and pass
-      constexpr int kPassOrders = 64 / (CW * KG);                     // CW * KG mask bits per order, 64 in all
-      const bool aligned = shift == 0 && (S & 3) == 0;
+      constexpr int NC = MARLSC_LANE_CHAINS < SPL ? MARLSC_LANE_CHAINS : SPL;   // chains per lane
+      constexpr int NS = (SPL + NC - 1) / NC;                         // SKU slots per chain
+      constexpr int NA = NS < 64 ? NS : 64;                           // ... per pass (mask bits per order)
+      constexpr int kPassOrders = 64 / NA;
       const uint8_t* rows = s_sqty + shift;
       const int Wp = (W + 3) & ~3;
       for (int j0 = 0; j0 < cn; j0 += kPassOrders)
-      for (int k0 = 0; k0 < NWL; k0 += KG) {
+      for (int q0 = 0; q0 < NS; q0 += NA) {                           // one trip unless a lane owns > 64 * NC SKUs
         const int pn = imin(kPassOrders, cn - j0);
-        uint32_t mlo = 0, mhi = 0;                                    // non-zero cells of the pass, order-major
+        uint32_t m[2][2] = {{0u, 0u}, {0u, 0u}};                      // [chain][low / high word], order-major bits
         for (int jj = 0; jj < pn; ++jj) {
           const uint8_t* row = rows + (j0 + jj) * row_bytes;
           MARLSC_UNROLL
-          for (int k = 0; k < KG; ++k) {
-            const int c0s = CW * (tm.gl + G * (k0 + k));              // first SKU of this group
-            uint32_t word = 0;
-            if (aligned && c0s < S) {
-              if (CW == 4) word = *reinterpret_cast<const uint32_t*>(row + c0s);
-              else if (CW == 2) word = *reinterpret_cast<const uint16_t*>(row + c0s);
-              else word = row[c0s];
-            } else if (!aligned) {
-              MARLSC_UNROLL
-              for (int b = 0; b < CW; ++b)
-                if (c0s + b < S) word |= (uint32_t)row[c0s + b] << (8 * b);
-            }
-            // bit 7 of every non-zero byte, gathered into the low four bits
-            uint32_t nz = (((word & 0x7f7f7f7fu) + 0x7f7f7f7fu) | word) & 0x80808080u;
-            nz = (((nz >> 7) * 0x204081u) >> 21) & 0xfu;
-            const int at = CW * (jj * KG + k);
-            if (at < 32) mlo |= nz << at; else mhi |= nz << (at - 32);
+          for (int jq = 0; jq < NA * NC; ++jq) {
+            const int j = q0 * NC + jq;
+            const int s = tm.gl + G * j;
+            const uint32_t nz = (j < SPL && s < S && row[s] != 0) ? 1u : 0u;
+            const int at = jj * NA + jq / NC;
+            if (at < 32) m[j % NC][0] |= nz << at; else m[j % NC][1] |= nz << (at - 32);
           }
         }
-        int rem = 0, v = 0, r = 0, sku = 0, oj = 0;
+        int rem[2] = {0, 0}, v[2] = {0, 0}, r[2] = {0, 0}, sku[2] = {0, 0}, oj[2] = {0, 0};
         while (true) {
-          if (rem == 0 && (mlo | mhi) != 0) {                         // next line of this lane
-            int bit;
-            if (mlo) {
-              bit = lowest_bit(mlo);
-              mlo &= mlo - 1;
-            } else {
-              bit = 32 + lowest_bit(mhi);
-              mhi &= mhi - 1;
-            }
-            const int slot = bit / CW;
-            oj = j0 + slot / KG;
-            sku = CW * (tm.gl + G * (k0 + slot % KG)) + bit % CW;
-            rem = rows[oj * row_bytes + sku];
-            r = s_sreg[oj] & 0x7fff;
-            v = 0;
-            // home-region demand of this step (multi_env.py:763-768); the cell belongs to this lane
-            if (dh_mode) {
-              uint32_t hm = tb.hmask[r];
-              while (hm) {
-                const int w = lowest_bit(hm);
-                hm &= hm - 1;
-                if (dh_mode == 1) global_add(&dh_acc[w * S + sku], rem);   // nobody waits for the sum
-                else dh_acc[w * S + sku] += rem;
+          MARLSC_UNROLL
+          for (int c = 0; c < NC; ++c) {
+            if (rem[c] == 0 && (m[c][0] | m[c][1]) != 0) {            // next line of this chain
+              int bit;
+              if (m[c][0]) {
+                bit = lowest_bit(m[c][0]);
+                m[c][0] &= m[c][0] - 1;
+              } else {
+                bit = 32 + lowest_bit(m[c][1]);
+                m[c][1] &= m[c][1] - 1;
               }
-            }
-          }
-          if (rem > 0) {                                              // four warehouses down the priority list
-            // the stock cells of the line's SKU belong to this lane: the four reads go out together, the
-            // takes follow in priority order (rows of the priority table are padded to whole words)
-            const uint32_t pw = *reinterpret_cast<const uint32_t*>(tb.prio + r * Wp + v);
-            int a[4], wk[4];
-            MARLSC_UNROLL
-            for (int k = 0; k < 4; ++k) {
-              wk[k] = (int)((pw >> (8 * k)) & 0xffu);
-              a[k] = v + k < W ? s_inv[wk[k] * S + sku] : 0;
-            }
-            MARLSC_UNROLL
-            for (int k = 0; k < 4; ++k) {
-              const int f = imin(rem, a[k]);
-              if (f > 0) {
-                const int w = wk[k];
-                s_inv[w * S + sku] = a[k] - f;
-                smem_add(&s_shipq[w * R + r], f);
-                if (!unit_w) smem_add(&s_shipw[w * R + r], (double)f * tb.skw[sku]);
-                if (need_ship) {
-                  s_st[w * S + sku] += f;
-                  if (sp.home[w] == r) s_sh[w * S + sku] += f;
+              oj[c] = j0 + bit / NA;
+              sku[c] = tm.gl + G * (NC * (q0 + bit % NA) + c);
+              rem[c] = rows[oj[c] * row_bytes + sku[c]];
+              r[c] = s_sreg[oj[c]] & 0x7fff;
+              v[c] = 0;
+              // home-region demand of this step (multi_env.py:763-768); the cell belongs to this lane
+              if (dh_mode) {
+                uint32_t hm = tb.hmask[r[c]];
+                while (hm) {
+                  const int w = lowest_bit(hm);
+                  hm &= hm - 1;
+                  if (dh_mode == 1) global_add(&dh_acc[w * S + sku[c]], rem[c]);   // nobody waits for the sum
+                  else dh_acc[w * S + sku[c]] += rem[c];
                 }
               }
-              rem -= f;
-            }
-            v += 4;
-            if (rem > 0 && v >= W) {
-              // no warehouse can supply the rest: lost (demand_allocator.py:205-208)
-              smem_add(&s_lostW[r], (double)rem * tb.skw[sku]);
-              smem_add(&s_lostP[r], (double)rem * tb.pen[sku]);
-              s_sreg[oj] = (int16_t)(r | 0x8000);                    // the order counts as lost once, below
-              rem = 0;
             }
           }
-          if (!tm.warp_any(rem > 0 || (mlo | mhi) != 0)) break;   // the team's warps run their chains apart
+          MARLSC_UNROLL
+          for (int c = 0; c < NC; ++c) {
+            if (rem[c] > 0) {                                         // four warehouses down the priority list
+              // the stock cells of the line's SKU belong to this lane: the four reads go out together, the
+              // takes follow in priority order (rows of the priority table are padded to whole words)
+              const uint32_t pw = *reinterpret_cast<const uint32_t*>(tb.prio + r[c] * Wp + v[c]);
+              int a[4], wk[4];
+              MARLSC_UNROLL
+              for (int k = 0; k < 4; ++k) {
+                wk[k] = (int)((pw >> (8 * k)) & 0xffu);
+                a[k] = v[c] + k < W ? s_inv[wk[k] * S + sku[c]] : 0;
+              }
+              MARLSC_UNROLL
+              for (int k = 0; k < 4; ++k) {
+                const int f = imin(rem[c], a[k]);
+                if (f > 0) {
+                  const int w = wk[k];
+                  s_inv[w * S + sku[c]] = a[k] - f;
+                  smem_add(&s_shipq[w * R + r[c]], f);
+                  if (!unit_w) smem_add(&s_shipw[w * R + r[c]], (double)f * tb.skw[sku[c]]);
+                  if (need_ship) {
+                    s_st[w * S + sku[c]] += f;
+                    if (sp.home[w] == r[c]) s_sh[w * S + sku[c]] += f;
+                  }
+                }
+                rem[c] -= f;
+              }
+              v[c] += 4;
+              if (rem[c] > 0 && v[c] >= W) {
+                // no warehouse can supply the rest: lost (demand_allocator.py:205-208)
+                smem_add(&s_lostW[r[c]], (double)rem[c] * tb.skw[sku[c]]);
+                smem_add(&s_lostP[r[c]], (double)rem[c] * tb.pen[sku[c]]);
+                s_sreg[oj[c]] = (int16_t)(r[c] | 0x8000);            // the order counts as lost once, below
+                rem[c] = 0;
+              }
+            }
+          }
+          // the team's warps run their chains apart
+          if (!tm.warp_any((rem[0] | rem[1]) > 0 || (m[0][0] | m[0][1] | m[1][0] | m[1][1]) != 0)) break;
         }
       }
       tm.sync();
