@@ -368,14 +368,18 @@ MDEV int rescale_action(const DevSpec& sp, float a, double mx, int prev_home_dem
 }
 
 // Share of region r's lost volume attributed to warehouse w (lost_sales_handler.py:71-210).
+// ``shipped_r`` >= 0: units shipped to region r from all warehouses, when the caller has it at hand.
 template <uint32_t CAPS>
 MDEV double lost_weight(const DevSpec& sp, const int32_t* s_shipq, const int32_t* s_lostN, const double* s_lostW,
-                        int w, int r) {
+                        int w, int r, int shipped_r = -1) {
   const int W = sp.W, R = sp.R;
   if (sp.lost_type == MARLSC_LOST_CLOSEST) return sp.closest[r] == w ? 1.0 : 0.0;
   if (sp.lost_type == MARLSC_LOST_SHIPMENT) {
-    int tot = 0;
-    for (int ww = 0; ww < W; ++ww) tot += s_shipq[ww * R + r];
+    int tot = shipped_r;
+    if (tot < 0) {
+      tot = 0;
+      for (int ww = 0; ww < W; ++ww) tot += s_shipq[ww * R + r];
+    }
     if (tot > 0) return (double)s_shipq[w * R + r] / (double)tot;
     return sp.closest[r] == w ? 1.0 : 0.0;
   }
@@ -786,23 +790,27 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
       // when no split limit binds; the lanes only meet again at the end of the pass.
       constexpr int NC = MARLSC_LANE_CHAINS < SPL ? MARLSC_LANE_CHAINS : SPL;   // chains per lane
       constexpr int NS = (SPL + NC - 1) / NC;                         // SKU slots per chain
-      constexpr int NA = NS < 64 ? NS : 64;                           // ... per pass (mask bits per order)
+      constexpr int NA = NS < 32 ? NS : 32;                           // ... per pass (mask bits per order, a power of two)
       constexpr int kPassOrders = 64 / NA;
       const uint8_t* rows = s_sqty + shift;
       const int Wp = (W + 3) & ~3;
       for (int j0 = 0; j0 < cn; j0 += kPassOrders)
-      for (int q0 = 0; q0 < NS; q0 += NA) {                           // one trip unless a lane owns > 64 * NC SKUs
+      for (int q0 = 0; q0 < NS; q0 += NA) {                           // one trip unless a lane owns > 32 * NC SKUs
         const int pn = imin(kPassOrders, cn - j0);
         uint32_t m[2][2] = {{0u, 0u}, {0u, 0u}};                      // [chain][low / high word], order-major bits
         for (int jj = 0; jj < pn; ++jj) {
           const uint8_t* row = rows + (j0 + jj) * row_bytes;
+          uint32_t nb[2] = {0u, 0u};                                  // this order's non-zero cells per chain
           MARLSC_UNROLL
           for (int jq = 0; jq < NA * NC; ++jq) {
             const int j = q0 * NC + jq;
             const int s = tm.gl + G * j;
-            const uint32_t nz = (j < SPL && s < S && row[s] != 0) ? 1u : 0u;
-            const int at = jj * NA + jq / NC;
-            if (at < 32) m[j % NC][0] |= nz << at; else m[j % NC][1] |= nz << (at - 32);
+            if (j < SPL && s < S && row[s] != 0) nb[jq % NC] |= 1u << (jq / NC);
+          }
+          const int at = jj * NA;                                     // NA divides 32: an order never straddles the words
+          MARLSC_UNROLL
+          for (int c = 0; c < NC; ++c) {
+            if (at < 32) m[c][0] |= nb[c] << at; else m[c][1] |= nb[c] << (at - 32);
           }
         }
         int rem[2] = {0, 0}, v[2] = {0, 0}, r[2] = {0, 0}, sku[2] = {0, 0}, oj[2] = {0, 0};

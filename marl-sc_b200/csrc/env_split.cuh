@@ -193,11 +193,14 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
     for (int r = tm.gl; r < R; r += G) {
       const bool lost = s_lostN[r] > 0;
       const double lp = lost ? s_lostP[r] : 0.0;
+      int shipped_r = 0;
+      if (lost)
+        for (int w = 0; w < W; ++w) shipped_r += s_shipq[w * R + r];
       for (int w = 0; w < W; ++w) {
         const int sq = s_shipq[w * R + r];
         double c = 0.0;
         if (sq > 0) c = (double)sq * sp.out_var[w * R + r];
-        if (lost) c += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r) * lp;
+        if (lost) c += lost_weight<CAPS>(sp, s_shipq, s_lostN, s_lostW, w, r, shipped_r) * lp;
         if (sq > 0 || lost) tile[w * (G + 1) + tm.gl] += c;
       }
     }
