@@ -1,17 +1,19 @@
 #!/usr/bin/env python
-"""bench.py - agent-steps/s of the hot path (fused env step K1 + GAE scan K2) on N B200s.
+"""bench.py - agent-steps/s of the hot path (env step K1 + GAE scan K2) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload large|small]
 
-One bench "step" is one rollout segment: SEG env steps of all E environments (one K1 launch each,
-plus a reset launch when an episode ends) followed by one K2 launch over the segment's
+One bench "step" is one rollout segment: SEG env steps of all E environments (one marlsc_env_step call each =
+four launches of the split step K1a-K1d, or one fused launch; plus a reset launch when an episode ends) followed
+by one K2 launch over the segment's
 [SEG, E, W] rewards/values. agent-steps per bench step = E * W * SEG. Workload (default): BASELINE.json
 configs[2], the large network (10 warehouses x 100 SKUs x 50 regions, lead times 1..10) with 65,536
 envs per GPU - the config the 1e9 agent-steps/s target is quoted on. Environments are independent,
 so N GPUs run N shards with no communication on the path (weak scaling).
 
 Printed JSON (rank 0): the driver's contract plus
-  roofline     - K1 achieved HBM GB/s (algorithmic bytes / CUDA-event launch time) against MEASURED_PEAKS.json
+  roofline     - K1 achieved HBM GB/s (algorithmic bytes / CUDA-event time of the step's launches) against
+                 MEASURED_PEAKS.json, plus every launch of the step on its own (kernels[])
   cpu_baseline - the CPU oracle port (oracle/inventory_oracle.py + gae_oracle.py) on a bounded sample
   e2e          - same metric through the host-buffer C-ABI call (marlsc_env_step_host): pinned host
                  actions/demand copied in, rewards (and the segment's advantages/targets) copied out
@@ -344,6 +346,19 @@ def run_ours(args):
     elapsed_ms = start.elapsed_time(stop)
     launches = L.marlsc_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
+    # per-launch durations of the step's kernels: a separate short pass with the library's own CUDA events
+    # around each launch (marlsc_env_set_timing); each step is read back before the next one starts
+    per_launch = []
+    if rank == 0:
+        env.set_timing(True)
+        for i in range(12):
+            if env.timestep >= env.episode_length:
+                env.reset(obs_out=obs_buf[0])
+            j = env.timestep % n_in if args.policy == "base_stock" else i % n_in
+            env.step(actions[j], orders=demand[j], obs_out=obs_buf[i & 1], rewards_out=rewards[i % SEG])
+            per_launch.append(env.last_step_timing())
+        env.set_timing(False)
+        per_launch = per_launch[2:]
     k1_ms = [a.elapsed_time(b) for a, b in k1_events]
     k2_ms = [a.elapsed_time(b) for a, b in k2_events]
     if world > 1:
@@ -460,9 +475,32 @@ def run_ours(args):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = dict(bound="hbm", kernel="env_step_kernel (K1)", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+    n_launch = len(per_launch[0]) if per_launch else 0
+    split = n_launch == 4
+    kernels = []
+    if per_launch:
+        ms = [statistics.mean(x[i] for x in per_launch) for i in range(n_launch)]
+        WS, Lmax, od = W * S, env.max_expected_lead_time, env.obs_dim
+        if split:
+            # algorithmic bytes per env step of each launch (int32 state, fp32 obs), including what the split itself adds
+            # (inventory and the home-demand plane pass through HBM between the kernels)
+            parts = [("env_place_kernel (K1a)", 4 * WS * (2 * Lmax + 6), "hbm"),
+                     ("env_alloc_kernel (K1b)", 8 * WS + mean_orders * (S + 2) + 8 * W, "issue"),
+                     ("env_feature_kernel (K1c)", 4 * WS * 7 + 4 * W * (od - Lmax * S) + 8 * W, "hbm"),
+                     ("env_reward_kernel (K1d)", 20 * W + 1, "latency")]
+        else:
+            parts = [("env_step_kernel (fused K1)", b_env, "hbm")]
+        for (name, b, bound), t_ms in zip(parts, ms):
+            kernels.append(dict(kernel=name, ms_per_launch=t_ms, bound=bound, algorithmic_bytes_per_env_step=b,
+                                achieved=b * E / (t_ms * 1e-3) / 1e9, frac=b * E / (t_ms * 1e-3) / 1e9 / peak))
+    roofline = dict(bound="hbm",
+                    kernel=("env step K1 = place + allocate + features + rewards launches (csrc/env_split.cuh)" if split
+                            else "env_step_kernel (K1)"),
+                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_env_step=b_env, k1_ms_per_launch=k1_avg_ms,
-                    k1_share_of_step=sum(k1_ms) / elapsed_ms)
+                    k1_share_of_step=sum(k1_ms) / elapsed_ms, launches_per_env_step=n_launch, kernels=kernels,
+                    note=("achieved = SURVEY 8d algorithmic bytes of one env step x envs / time of the step's launches; "
+                          "kernels[] gives every launch with its own bytes (K1b is issue-bound, not HBM-bound)") if split else None)
 
     # K2 (GAE scan): reads rewards [T,N] + values [T+1,N], writes advantages + targets [T,N]; small working set
     # (L2 resident at this size), reported for completeness

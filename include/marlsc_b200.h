@@ -178,6 +178,12 @@ int marlsc_env_set_generic(marlsc_env_t* env, int32_t on);
 /* Lean launches of teams of 8+ lanes run the step as four kernels (place / allocate / features / rewards, see
  * csrc/env_split.cuh); on != 0 keeps them in the single fused kernel (used for comparisons and by the tests). */
 int marlsc_env_set_fused(marlsc_env_t* env, int32_t on);
+/* Measurement aid: with on != 0 every marlsc_env_step records CUDA events on its stream around each kernel it
+ * launches. marlsc_env_last_timing waits for the last timed step and writes the per-launch durations in
+ * milliseconds (split step: place, allocate, features, rewards; fused step: one entry); returns how many, or a
+ * negative error code. */
+int marlsc_env_set_timing(marlsc_env_t* env, int32_t on);
+int marlsc_env_last_timing(marlsc_env_t* env, float* ms, int32_t capacity);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

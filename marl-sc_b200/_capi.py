@@ -97,6 +97,10 @@ def lib() -> C.CDLL:
     L.marlsc_env_set_generic.restype = C.c_int
     L.marlsc_env_set_fused.argtypes = [vp, i32]
     L.marlsc_env_set_fused.restype = C.c_int
+    L.marlsc_env_set_timing.argtypes = [vp, i32]
+    L.marlsc_env_set_timing.restype = C.c_int
+    L.marlsc_env_last_timing.argtypes = [vp, C.POINTER(C.c_float), i32]
+    L.marlsc_env_last_timing.restype = C.c_int
     L.marlsc_env_reset.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
     L.marlsc_env_reset.restype = C.c_int
     L.marlsc_env_step.argtypes = [vp, C.POINTER(EnvStateC), C.POINTER(StepIOC), i32, vp]

@@ -26,6 +26,7 @@ namespace marlsc {
 struct SplitWork {
   double* cost_alloc;   // [E,W] outbound + penalty cost (K1b)
   double* cost_rows;    // [E,W] holding + inbound cost (K1c)
+  cudaEvent_t* marks;   // five events around the four launches when timing is on (marlsc_env_set_timing), else null
 };
 
 // Lookup tables straight from global memory (a few KB, read-only, L1 resident) for the kernels without scratch.
@@ -290,8 +291,10 @@ int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitW
   constexpr int SPLR = G > 32 ? SPL * (G / 32) : SPL;
   const int64_t rows = a.st.num_envs * a.ds.W;
   const unsigned grid_rows = (unsigned)((rows + 128 / GR - 1) / (128 / GR));
+  if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[0], s));
   env_place_kernel<GR, SPLR><<<grid_rows, 128, 0, s>>>(a.ds, a.st, io, t);
   MARLSC_CUDA(cudaGetLastError());
+  if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[1], s));
 
   const size_t smem = step_smem_bytes(a.ds, G);
   if ((int)smem > a.max_smem_optin)
@@ -310,13 +313,16 @@ int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitW
   const unsigned grid_envs = (unsigned)((a.st.num_envs + Block<G>::teams - 1) / Block<G>::teams);
   env_alloc_kernel<G, SPL><<<grid_envs, Block<G>::threads, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
   MARLSC_CUDA(cudaGetLastError());
+  if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[2], s));
 
   env_feature_kernel<GR, SPLR><<<grid_rows, 128, 0, s>>>(a.ds, a.st, io, wk.cost_rows, t);
   MARLSC_CUDA(cudaGetLastError());
+  if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[3], s));
 
   env_reward_kernel<<<(unsigned)((a.st.num_envs + 255) / 256), 256, 0, s>>>(a.ds, a.st.num_envs, wk.cost_alloc, wk.cost_rows,
                                                                            io.rewards, io.truncated, t);
   MARLSC_CUDA(cudaGetLastError());
+  if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[4], s));
   g_launches.fetch_add(4, std::memory_order_relaxed);
   return MARLSC_OK;
 }

@@ -53,6 +53,9 @@ struct marlsc_env {
   int force_fused = 0;     // tests / comparisons: lean launches stay in the fused kernel
   double* d_work = nullptr;    // split step: [2, work_envs, W] cost partials
   int64_t work_envs = 0;
+  int timing = 0;              // marlsc_env_set_timing: events around the launches of a step
+  int timed_launches = 0;      // launches the last timed step made (4 split, 1 fused)
+  cudaEvent_t marks[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;        // marlsc_env_rollout_host: H2D copies of the next step
   cudaEvent_t ready[2] = {nullptr, nullptr};  // staging set filled
   cudaEvent_t done[2] = {nullptr, nullptr};   // staging set consumed by its step kernel
@@ -242,6 +245,8 @@ void marlsc_env_destroy(marlsc_env_t* env) {
   }
   if (env->d_blob) cudaFree(env->d_blob);
   if (env->d_work) cudaFree(env->d_work);
+  for (cudaEvent_t ev : env->marks)
+    if (ev) cudaEventDestroy(ev);
   delete env;
 }
 
@@ -267,6 +272,27 @@ int marlsc_env_set_fused(marlsc_env_t* env, int32_t on) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
   env->force_fused = on ? 1 : 0;
   return MARLSC_OK;
+}
+
+int marlsc_env_set_timing(marlsc_env_t* env, int32_t on) {
+  if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  MARLSC_CUDA(cudaSetDevice(env->device));
+  if (on)
+    for (cudaEvent_t& ev : env->marks)
+      if (!ev) MARLSC_CUDA(cudaEventCreate(&ev));
+  env->timing = on ? 1 : 0;
+  env->timed_launches = 0;
+  return MARLSC_OK;
+}
+
+int marlsc_env_last_timing(marlsc_env_t* env, float* ms, int32_t capacity) {
+  if (!env || !ms) return set_error(MARLSC_EINVAL, "null handle or output");
+  const int n = env->timed_launches;
+  if (!env->timing || n == 0) return set_error(MARLSC_EINVAL, "no timed step: call marlsc_env_set_timing(env, 1) and step first");
+  if (capacity < n) return set_error(MARLSC_EINVAL, "ms[] too small");
+  MARLSC_CUDA(cudaEventSynchronize(env->marks[n]));
+  for (int i = 0; i < n; ++i) MARLSC_CUDA(cudaEventElapsedTime(&ms[i], env->marks[i], env->marks[i + 1]));
+  return n;
 }
 
 int marlsc_env_reset(marlsc_env_t* env, const marlsc_env_state_t* state, const int32_t* init_inventory, int32_t per_env,
@@ -306,7 +332,8 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   if (lean && split_ok(env)) {
     rc = ensure_work(env, state->num_envs);
     if (rc) return rc;
-    const SplitWork wk{env->d_work, env->d_work + (size_t)env->work_envs * env->ds.W};
+    const SplitWork wk{env->d_work, env->d_work + (size_t)env->work_envs * env->ds.W, env->timing ? env->marks : nullptr};
+    env->timed_launches = env->timing ? 4 : 0;
     switch (env->team) {
       case 8: return launch_split_g8(env->spl, la, *io, wk, t, s);
       case 16: return launch_split_g16(env->spl, la, *io, wk, t, s);
@@ -319,6 +346,14 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   const bool narrow = env->team > 32 && !lean;
   const int team = narrow ? 32 : env->team;
   const int spl = narrow ? pick_spl(32, env->ds.S) : env->spl;
+  if (env->timing) {
+    MARLSC_CUDA(cudaEventRecord(env->marks[0], s));
+    rc = [&]() -> int { MARLSC_DISPATCH_G(team, launch_step_g, spl, la, *io, t, s) }();
+    if (rc) return rc;
+    MARLSC_CUDA(cudaEventRecord(env->marks[1], s));
+    env->timed_launches = 1;
+    return MARLSC_OK;
+  }
   MARLSC_DISPATCH_G(team, launch_step_g, spl, la, *io, t, s)
 }
 

@@ -230,6 +230,19 @@ class BatchedInventoryEnv:
     def team_size(self) -> int:
         return int(_capi.lib().marlsc_env_team_size(self._h))
 
+    def set_timing(self, on: bool) -> None:
+        """Measurement aid: record CUDA events around every kernel a step launches (marlsc_env_set_timing)."""
+        _capi.check(_capi.lib().marlsc_env_set_timing(self._h, int(on)))
+
+    def last_step_timing(self) -> list:
+        """Per-launch milliseconds of the last timed step: [place, allocate, features, rewards] for the split
+        step, one entry for the fused kernel. Waits for that step."""
+        buf = (C.c_float * 8)()
+        n = _capi.lib().marlsc_env_last_timing(self._h, buf, 8)
+        if n < 0:
+            _capi.check(n)
+        return [float(buf[i]) for i in range(n)]
+
     def _compute_local_obs_dim(self) -> int:
         return self.obs_dim
 

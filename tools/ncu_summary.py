@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Summarise an ncu report of the env-step kernel: headline metrics, stall reasons and executed
-instructions / stall samples per kernel phase (needs -lineinfo and --import-source on).
+"""Summarise an ncu report of the env-step kernels: per kernel the headline metrics and stall reasons, then the
+executed instructions / stall samples per source region and the hottest source lines (needs -lineinfo and
+--import-source on).
 
     python tools/ncu_summary.py gpurun_out/foo.ncu-rep [> profiles/foo.summary.txt]
 """
@@ -19,10 +20,34 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+# (label, text that opens the region in env_core.cuh); a line belongs to the last marker at or above it
+MARKS = [("helpers (arithmetic, team votes, tables)", None),
+         ("write_obs_pipeline", "MDEV void write_obs_pipeline"),
+         ("write_obs_row", "MDEV void write_obs_row"),
+         ("allocate_orders: setup + staging", "MDEV void allocate_orders"),
+         ("allocate_orders: lane masks", "if constexpr (LaneAlloc<G, CAPS>::value) {"),
+         ("allocate_orders: lane chains", "int rem[2] = {0, 0}"),
+         ("allocate_orders: lost-order flags", "if (s_sreg[j] & 0x8000) smem_add"),
+         ("allocate_orders: dense (narrow teams / generic)", "      for (int j = 0; j < cn; ++j) {"),
+         ("step_env (fused kernel phases 1, 3, 4)", "MDEV void step_env"),
+         ("reset_env", "MDEV void reset_env")]
 
 
 def ncu(args):
     return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
+
+
+def regions():
+    src = open(os.path.join(ROOT, "marl-sc_b200", "csrc", "env_core.cuh")).read().split("\n")
+    out = []
+    for label, pat in MARKS:
+        if pat is None:
+            out.append((label, 1))
+            continue
+        hits = [i + 1 for i, l in enumerate(src) if pat in l]
+        if hits:
+            out.append((label, hits[0]))
+    return out
 
 
 def main(rep):
@@ -40,10 +65,26 @@ def main(rep):
                         print(f"  {h:90s} {r[i]:>18s}")
                 except ValueError:
                     pass
+    marks = regions()
+
+    def region(f, n):
+        if f != "env_core.cuh":
+            return f
+        name = marks[0][0]
+        for label, at in marks:
+            if n >= at:
+                name = label
+        return name
+
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"]))))
-    cur, hdr, last = None, None, None
-    agg = collections.defaultdict(lambda: [0, 0, 0, ''])
+    kern, cur, hdr, last = None, None, None, None
+    per = collections.OrderedDict()        # kernel -> {(file, line): [inst, samples, sass, text]}
+    seen = set()
     for r in rows:
+        if len(r) >= 2 and r[0] == "Function Name":
+            kern = r[1].replace("marlsc::", "").split("(")[0].replace("(int)", "")
+            per.setdefault(kern, collections.defaultdict(lambda: [0, 0, 0, '']))
+            continue
         if len(r) >= 2 and r[0] == "File Path":
             cur = r[1].split('/')[-1]
             continue
@@ -51,52 +92,38 @@ def main(rep):
             hdr = r
             iex, ism = hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
             continue
-        if hdr and len(r) == len(hdr):
+        if hdr and len(r) == len(hdr) and kern:
+            if r[0]:
+                last = (cur, int(r[0]))
+                per[kern][last][3] = r[1]
+                continue
             try:
+                key = (kern, int(r[2], 16))
                 ex, sm = int(r[iex] or 0), int(r[ism] or 0)
             except ValueError:
                 continue
-            k = (cur, r[0])
-            if r[0]:
-                last = k
-                agg[k][3] = r[1].strip()[:80]
-            else:
-                k = last
-            agg[k][0] += ex
-            agg[k][1] += sm
-            agg[k][2] += 1
-    tot = sum(v[0] for v in agg.values()) or 1
-    ts = sum(v[1] for v in agg.values()) or 1
-    src = open(os.path.join(ROOT, "marl-sc_b200", "csrc", "env_core.cuh")).read().splitlines()
-
-    def find(pat):
-        return next(i + 1 for i, l in enumerate(src) if pat in l)
-    marks = [(find("MDEV void write_obs_row"), "helpers"), (find("MDEV void step_env"), "write_obs_row"),
-             (find("---- phase 2"), "phase1 (orders/arrivals)"), (find("for (int j = 0; j < cn; ++j) {"), "order staging"),
-             (find("---- phase 3"), "phase2 (allocation)"), (find("---- phase 4"), "phase3 (features/costs)"),
-             (10 ** 9, "phase4 (rewards)")]
-
-    def phase(k):
-        f, l = k
-        if f != 'env_core.cuh':
-            return f or "?"
-        try:
-            l = int(l)
-        except ValueError:
-            return "?"
-        for lim, name in marks:
-            if l < lim:
-                return name
-    ph = collections.defaultdict(lambda: [0, 0])
-    for k, v in agg.items():
-        ph[phase(k)][0] += v[0]
-        ph[phase(k)][1] += v[1]
-    print(f"per phase (executed warp instructions {tot}, stall samples {ts}):")
-    for k, v in sorted(ph.items(), key=lambda kv: -kv[1][1]):
-        print(f"  {k:28s} {100 * v[0] / tot:5.1f}% inst {100 * v[1] / ts:5.1f}% samples")
-    print("top source lines by stall samples:")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
-        print(f"  {100 * v[0] / tot:5.1f}% inst {100 * v[1] / ts:5.1f}% smp sass={v[2]:4d} {k[0]}:{k[1]:>4s} {v[3]}")
+            if key in seen or last is None:      # the same SASS row is listed under every file it is attributed to
+                continue
+            seen.add(key)
+            a = per[kern][last]
+            a[0] += ex
+            a[1] += sm
+            a[2] += 1
+    for kern, agg in per.items():
+        tot = sum(v[0] for v in agg.values()) or 1
+        ts = sum(v[1] for v in agg.values()) or 1
+        print(f"\n== {kern}: {tot} warp instructions, {ts} stall samples, {sum(v[2] for v in agg.values())} SASS instructions")
+        reg = collections.defaultdict(lambda: [0, 0])
+        for (f, n), v in agg.items():
+            k = region(f, n)
+            reg[k][0] += v[0]
+            reg[k][1] += v[1]
+        for k, v in sorted(reg.items(), key=lambda kv: -kv[1][0]):
+            if v[0] * 200 > tot or v[1] * 200 > ts:
+                print(f"  {k:52s} {100 * v[0] / tot:5.1f}% inst  {100 * v[1] / ts:5.1f}% samples")
+        print("  top source lines by stall samples:")
+        for (f, n), v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
+            print(f"    {100 * v[0] / tot:5.1f}% inst {100 * v[1] / ts:5.1f}% smp sass={v[2]:4d} {f}:{n:5d} {v[3].strip()[:90]}")
 
 
 if __name__ == "__main__":

@@ -18,7 +18,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 def main(rep, tag="r1"):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
-    open(os.path.join(P, f"{tag}_k1_lean_65536envs.summary.txt"), "w").write(out)
+    open(os.path.join(P, f"{tag}_k1_split_65536envs.summary.txt"), "w").write(out)
     rows = list(csv.reader(open(os.path.join(G, f"{tag}_launches.csv"))))
     hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
     hdr = rows[hi]
@@ -31,7 +31,7 @@ def main(rep, tag="r1"):
         agg[name][0] += 1
         agg[name][1] += float(r[mv].replace(',', ''))
     tot = sum(v[1] for v in agg.values())
-    lines = ["ncu --metrics gpu__time_duration.sum --clock-control none -k regex:env_step|env_reset|gae_kernel|moments|standardize -c 400",
+    lines = ["ncu --metrics gpu__time_duration.sum --clock-control none -k regex:env_place|env_alloc|env_feature|env_reward|env_step|env_reset|gae_kernel|moments|standardize -c 400",
              "command: python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu   (every launch of this library's kernels: recording pass, warm-up, timed segment)",
              "(cold-cache, serialised per-launch times under the profiler: compare shares, not absolutes)", ""]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:15]:
@@ -40,14 +40,19 @@ def main(rep, tag="r1"):
     shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{tag}_launches.csv"))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, r = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
 
-    def val(n):
+    def val(r, n):
         i = hdr.index(n)
         return float(r[i].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(units[i], 1)
-    rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')
-    json.dump(dict(workload="large", envs=65536, kernel="env_step_kernel<32,4,lean>", dram_bytes_per_launch=rd + wr, dram_read=rd,
-                   dram_write=wr, source=f"profiles/{tag}_k1_lean_65536envs.summary.txt (ncu --set full, one launch)"),
+    kernels, rd, wr = [], 0.0, 0.0
+    for r in rows[2:]:
+        a, b = val(r, 'dram__bytes_read.sum'), val(r, 'dram__bytes_write.sum')
+        kernels.append(dict(kernel=r[hdr.index('Kernel Name')].split('(')[0], dram_read=a, dram_write=b))
+        rd, wr = rd + a, wr + b
+    json.dump(dict(workload="large", envs=65536, kernel="split step: env_place + env_alloc + env_feature kernels, team 32",
+                   dram_bytes_per_launch=rd + wr, dram_read=rd, dram_write=wr, kernels=kernels,
+                   source=f"profiles/{tag}_k1_split_65536envs.summary.txt (ncu --set full, one launch of each kernel of one env step)"),
               open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
     for name in ("bench_default", "bench_small", "bench_ippo", "bench_reference"):
         src = os.path.join(G, name + ".json")
