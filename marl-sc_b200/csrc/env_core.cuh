@@ -112,6 +112,9 @@ struct DevSpec {
   const uint8_t* prio_static;  // [R] 1 when the order does not depend on the order's weight
   const uint32_t* home_mask;   // [R] bit w set when region r is warehouse w's home region (W <= 32), else null
   const uint8_t* lead_u8;      // [W*S] expected lead times as bytes
+  const uint16_t* prio_perm;   // [R,perm_chunks,16] availability bits -> priority-order bits (W <= 16), else null
+  int perm_chunks;
+  int pen_uniform;             // every SKU has the same lost-sales penalty rate
   const float* obs_mean;
   const float* obs_std;        // holds 1/std (precomputed on the host in float32)
   // observation block offsets inside one warehouse's vector (before the id prefix); -1 = block disabled

@@ -284,6 +284,9 @@ __global__ void __launch_bounds__(256)
 env_reward_kernel(const __grid_constant__ DevSpec sp, int64_t num_envs, const double* __restrict__ cost_alloc,
                   const double* __restrict__ cost_rows, float* __restrict__ rewards, uint8_t* __restrict__ truncated, int t);
 
+// K1b for one-warp teams (env_alloc.cu): 1 = launched, 0 = not applicable (the caller launches env_alloc_kernel), < 0 = error
+int launch_alloc_warp(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, double* cost_alloc, int t, cudaStream_t s);
+
 // One launcher per (G, SPL); defined through MARLSC_DEFINE_SPLIT in the per-width translation units.
 template <int G, int SPL>
 int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitWork& wk, int t, cudaStream_t s) {
@@ -296,6 +299,14 @@ int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitW
   MARLSC_CUDA(cudaGetLastError());
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[1], s));
 
+  // one-warp teams allocate through the whole-step lane chains of env_alloc.cuh when their scratch fits
+  bool warp_chains = false;
+  if constexpr (G == 32) {
+    const int rc = launch_alloc_warp(SPL, a, io, wk.cost_alloc, t, s);
+    if (rc < 0) return rc;
+    warp_chains = rc == 1;
+  }
+  if (!warp_chains) {
   const size_t smem = step_smem_bytes(a.ds, G);
   if ((int)smem > a.max_smem_optin)
     return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
@@ -313,6 +324,7 @@ int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitW
   const unsigned grid_envs = (unsigned)((a.st.num_envs + Block<G>::teams - 1) / Block<G>::teams);
   env_alloc_kernel<G, SPL><<<grid_envs, Block<G>::threads, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
   MARLSC_CUDA(cudaGetLastError());
+  }
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[2], s));
 
   env_feature_kernel<GR, SPLR><<<grid_rows, 128, 0, s>>>(a.ds, a.st, io, wk.cost_rows, t);

@@ -205,7 +205,8 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
                o_pr = blob_add(off, t.pen_rate), o_sw = blob_add(off, t.skw), o_le = blob_add(off, t.lead_exp),
                o_hm = blob_add(off, t.home), o_cl = blob_add(off, t.closest), o_rm = blob_add(off, t.region_map),
                o_pp = blob_add(off, t.prio), o_ps = blob_add(off, t.prio_static), o_om = blob_add(off, t.obs_mean),
-               o_os = blob_add(off, t.obs_std), o_hk = blob_add(off, t.home_mask), o_l8 = blob_add(off, t.lead_u8);
+               o_os = blob_add(off, t.obs_std), o_hk = blob_add(off, t.home_mask), o_l8 = blob_add(off, t.lead_u8),
+               o_pm = blob_add(off, t.prio_perm);
   std::vector<unsigned char> host(off + 16, 0);
   auto put = [&](size_t at, const void* src, size_t n) { if (n) std::memcpy(host.data() + at, src, n); };
   put(o_amax, t.action_max.data(), t.action_max.size() * 8); put(o_of, t.out_fixed.data(), t.out_fixed.size() * 8);
@@ -217,6 +218,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   put(o_pp, t.prio.data(), t.prio.size()); put(o_ps, t.prio_static.data(), t.prio_static.size());
   put(o_om, t.obs_mean.data(), t.obs_mean.size() * 4); put(o_os, t.obs_std.data(), t.obs_std.size() * 4);
   put(o_hk, t.home_mask.data(), t.home_mask.size() * 4); put(o_l8, t.lead_u8.data(), t.lead_u8.size());
+  put(o_pm, t.prio_perm.data(), t.prio_perm.size() * 2);
   ce = cudaMalloc(&env->d_blob, host.size());
   if (ce == cudaSuccess) ce = cudaMemcpy(env->d_blob, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) {
@@ -232,6 +234,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
               t.home_mask.empty() ? nullptr : reinterpret_cast<const uint32_t*>(b + o_hk), b + o_l8,
               t.obs_mean.empty() ? nullptr : reinterpret_cast<const float*>(b + o_om),
               t.obs_std.empty() ? nullptr : reinterpret_cast<const float*>(b + o_os));
+  env->ds.prio_perm = t.prio_perm.empty() ? nullptr : reinterpret_cast<const uint16_t*>(b + o_pm);
   *out = env;
   return MARLSC_OK;
 }

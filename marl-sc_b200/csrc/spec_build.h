@@ -18,6 +18,9 @@ struct HostTables {
   std::vector<uint8_t> prio, prio_static, lead_u8;
   std::vector<uint32_t> home_mask;
   std::vector<float> obs_mean, obs_std;
+  // W <= 16: warehouse-availability bits (bit w) -> the same bits in region r's priority order (bit v = the v-th
+  // cheapest warehouse), four warehouse bits per lookup: [R][perm_chunks][16] (env_alloc.cuh)
+  std::vector<uint16_t> prio_perm;
 };
 
 inline int pow2ceil(int v) {
@@ -110,6 +113,21 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return tb.out_var[a * R + r] < tb.out_var[b * R + r]; });
     for (int w = 0; w < W; ++w) tb.prio[(size_t)r * Wp + w] = (uint8_t)idx[w];
   }
+  tb.prio_perm.clear();
+  ds.perm_chunks = 0;
+  if (W <= 16) {
+    const int nc = (W + 3) / 4;
+    ds.perm_chunks = nc;
+    tb.prio_perm.assign((size_t)R * nc * 16, 0);
+    for (int r = 0; r < R; ++r)
+      for (int v = 0; v < W; ++v) {
+        const int w = tb.prio[(size_t)r * Wp + v];
+        for (int m = 0; m < 16; ++m)
+          if ((m >> (w % 4)) & 1) tb.prio_perm[((size_t)r * nc + w / 4) * 16 + m] |= (uint16_t)(1u << v);
+      }
+  }
+  ds.pen_uniform = 1;
+  for (int s = 1; s < S; ++s) ds.pen_uniform = ds.pen_uniform && tb.pen_rate[s] == tb.pen_rate[0];
 
   tb.home_mask.clear();
   if (W <= 32) {

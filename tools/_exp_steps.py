@@ -1,0 +1,33 @@
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, numpy as np
+import bench
+import marlsc_b200
+from marlsc_b200.config import environment_config_from_dict
+from marlsc_b200.envs import BatchedInventoryEnv
+E = int(os.environ.get("E", 65536))
+env_dict, cfg_desc = bench.workload("large")
+d = dict(env_dict); d["allow_region_mismatch"] = True
+cfg = environment_config_from_dict(d)
+dev = torch.device("cuda", 0)
+env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False)
+demand = bench.synth_demand(env_dict, E, cfg.episode_length, dev, 99)
+actions = bench.record_base_stock_actions(env, env_dict, demand, 2.0)
+obs = torch.empty_like(env.obs); rew = torch.empty((E, cfg.n_warehouses), device=dev)
+for mode in ("timing", "plain"):
+    env.reset(obs_out=obs)
+    env.set_timing(mode == "timing")
+    rows = []
+    for t in range(cfg.episode_length):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        env.step(actions[t], orders=demand[t], obs_out=obs, rewards_out=rew)
+        b.record()
+        torch.cuda.synchronize()
+        rows.append([a.elapsed_time(b)] + (env.last_step_timing() if mode == "timing" else []))
+    env.set_timing(False)
+    r = np.array(rows)
+    print(mode, "mean", np.round(r.mean(0), 3))
+    for t in (0, 1, 2, 5, 10, 15, 20, 30, 50, 70, 99):
+        print("  t", t, np.round(r[t], 3))
+print("inv mean", float(env.inventory.float().mean()))
