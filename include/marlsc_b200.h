@@ -241,6 +241,14 @@ void marlsc_demand_destroy(marlsc_demand_t* d);
 int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t max_orders_per_env,
                          int32_t* order_counts, int16_t* order_region, uint8_t* order_qty, int32_t* overflow_flag, void* stream);
 
+/* Device lead-time sampler: the distribution of the reference's StochasticLeadTimeSampler.sample
+ * (src/environment/components/lead_time_sampler.py:169-197): actual = max(1, expected[w,s] + U{-d[s]..+d[s]}),
+ * independently per environment, warehouse, SKU and step (the reference also draws every step). expected_lead
+ * int32 [W,S] and max_deviation int32 [S] are DEVICE pointers; actual_lead uint8 [E,W,S] is what
+ * marlsc_step_io.actual_lead takes. Philox stream keyed by (seed, cell, step); not the reference's PCG64 stream. */
+int marlsc_lead_sample(int64_t num_envs, int32_t n_warehouses, int32_t n_skus, const int32_t* expected_lead,
+                       const int32_t* max_deviation, uint64_t seed, int64_t step_index, uint8_t* actual_lead, void* stream);
+
 /* Batched base-stock heuristic (reference: make_bs_newsvendor_action_fn, src/experiments/run_baselines.py:133-207):
  * actions[e,w,s] = 2*clip(level[w,s] - on_hand - in_transit, 0, max_qty[s])/max_qty[s] - 1 evaluated before step t.
  * level: device float32 [W,S]; actions: device float32 [E,W,S]. Direct action space only. */

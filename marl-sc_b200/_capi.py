@@ -115,6 +115,8 @@ def lib() -> C.CDLL:
     L.marlsc_demand_destroy.restype = None
     L.marlsc_demand_sample.argtypes = [vp, i64, C.c_uint64, i64, i32, vp, vp, vp, vp, vp]
     L.marlsc_demand_sample.restype = C.c_int
+    L.marlsc_lead_sample.argtypes = [i64, i32, i32, vp, vp, C.c_uint64, i64, vp, vp]
+    L.marlsc_lead_sample.restype = C.c_int
     L.marlsc_policy_base_stock.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
     L.marlsc_policy_base_stock.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]

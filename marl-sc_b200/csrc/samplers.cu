@@ -116,6 +116,37 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
   if (lane == 0) counts[e] = row;
 }
 
+// K4b: actual lead times of one step, four consecutive cells per thread (one Philox call). A 32-bit word w gives
+// the deviation floor(w * (2d+1) / 2^32) - d: uniform over {-d..+d} up to a bias below (2d+1) / 2^32.
+__global__ void __launch_bounds__(256)
+sample_lead_kernel(const int32_t* __restrict__ expected, const int32_t* __restrict__ max_dev, int S, long long WS,
+                   long long n_cells, uint64_t seed, long long step, uint8_t* __restrict__ actual) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = q * 4;
+  if (i0 >= n_cells) return;
+  uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32) ^ 0x1ead71e5u, (uint32_t)step, (uint32_t)(step >> 32)};
+  philox4x32(c, seed);
+  uint32_t packed = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = i0 + j;
+    int v = 0;
+    if (i < n_cells) {
+      const int cell = (int)(i % WS);
+      const int d = max_dev[cell % S];
+      const int dev = (int)__umulhi(c[j], (uint32_t)(2 * d + 1)) - d;
+      v = expected[cell] + dev;
+      v = v < 1 ? 1 : (v > 255 ? 255 : v);
+    }
+    packed |= (uint32_t)v << (8 * j);
+  }
+  if (i0 + 3 < n_cells && (reinterpret_cast<uintptr_t>(actual) & 3u) == 0) {
+    reinterpret_cast<uint32_t*>(actual)[q] = packed;
+  } else {
+    for (int j = 0; j < 4 && i0 + j < n_cells; ++j) actual[i0 + j] = (uint8_t)(packed >> (8 * j));
+  }
+}
+
 // K5: one thread per (env, warehouse, SKU) cell
 __global__ void __launch_bounds__(256)
 base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
@@ -222,6 +253,19 @@ int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, in
   const unsigned grid = (unsigned)((num_envs + wpb - 1) / wpb);
   sample_demand_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       d->dp, d->R, d->S, num_envs, seed, step_index, max_orders_per_env, order_counts, order_region, order_qty, overflow_flag);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+int marlsc_lead_sample(int64_t num_envs, int32_t n_warehouses, int32_t n_skus, const int32_t* expected_lead,
+                       const int32_t* max_deviation, uint64_t seed, int64_t step_index, uint8_t* actual_lead, void* stream) {
+  if (!expected_lead || !max_deviation || !actual_lead) return set_error(MARLSC_EINVAL, "null argument");
+  if (num_envs < 1 || n_warehouses < 1 || n_skus < 1) return set_error(MARLSC_EINVAL, "num_envs, n_warehouses and n_skus must be positive");
+  const long long WS = (long long)n_warehouses * n_skus, n = num_envs * WS;
+  const unsigned grid = (unsigned)(((n + 3) / 4 + 255) / 256);
+  sample_lead_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(expected_lead, max_deviation, n_skus, WS, n, seed,
+                                                                          step_index, actual_lead);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;

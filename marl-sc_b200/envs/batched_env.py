@@ -135,6 +135,7 @@ class BatchedInventoryEnv:
                 lost_sales=torch.zeros((E, W, S), dtype=torch.float32, device=dev))
         self.timestep = 0
         self._dd = None                      # device demand sampler state (enable_device_demand)
+        self._dl = None                      # device lead-time sampler state (enable_device_leads)
         self._demand_step = 0
         if device_demand:
             self.enable_device_demand(demand_seed, max_orders_per_env)
@@ -189,6 +190,29 @@ class BatchedInventoryEnv:
                                                      d["counts"].data_ptr(), d["region"].data_ptr(), d["qty"].data_ptr(),
                                                      d["overflow"].data_ptr(), self._stream()))
         self._demand_step += 1
+
+    def enable_device_leads(self, seed: int = 0) -> None:
+        """Draw the actual lead times of every step on the device with the distribution of the reference's
+        StochasticLeadTimeSampler (components/lead_time_sampler.py:169-197): expected + U{-d..+d} per cell,
+        clipped to >= 1. Philox stream keyed by (seed, cell, step), not the reference's NumPy stream."""
+        if not self.stochastic_lead:
+            raise ValueError("device lead times need the 'stochastic' lead-time sampler")
+        smp = self.spec.components["lead_time_sampler"]
+        md = np.broadcast_to(np.asarray(smp.max_deviation, dtype=np.int32), (self.n_skus,))
+        dev = self.device
+        self._dl = dict(seed=int(seed), step=0,
+                        expected=torch.from_numpy(np.ascontiguousarray(self.expected_lead_times, dtype=np.int32)).to(dev),
+                        max_dev=torch.from_numpy(np.ascontiguousarray(md)).to(dev),
+                        actual=torch.zeros((self.num_envs, self.n_warehouses, self.n_skus), dtype=torch.uint8, device=dev))
+
+    def sample_device_leads(self) -> torch.Tensor:
+        """Actual lead times [E,W,S] (uint8) of the next step (called by step() when none are passed)."""
+        d = self._dl
+        _capi.check(_capi.lib().marlsc_lead_sample(self.num_envs, self.n_warehouses, self.n_skus, d["expected"].data_ptr(),
+                                                   d["max_dev"].data_ptr(), d["seed"], d["step"], d["actual"].data_ptr(),
+                                                   self._stream()))
+        d["step"] += 1
+        return d["actual"]
 
     def demand_overflowed(self) -> bool:
         """True when some environment drew more orders than max_orders_per_env (the surplus was dropped)."""
@@ -356,6 +380,8 @@ class BatchedInventoryEnv:
         if use_dd:
             self.sample_device_demand()
             orders = self._empty_orders
+        if self.stochastic_lead and actual_lead is None and self._dl is not None:
+            actual_lead = self.sample_device_leads()
         if orders is None:
             host_orders, host_leads = self.sample_host_demand()
             orders = host_orders

@@ -352,6 +352,63 @@ def test_device_demand_matches_reference_distribution():
     env.close()
 
 
+def test_device_lead_times_match_reference_distribution():
+    """K4b against the law of the reference's StochasticLeadTimeSampler (lead_time_sampler.py:169-197):
+    actual = max(1, expected + U{-d[s]..+d[s]}), independent per environment / cell / step; then a stepped
+    environment that draws its own lead times equals one fed the same draws explicitly."""
+    from scipy import stats
+    from marlsc_b200.envs import BatchedInventoryEnv
+    g = Golden("allfeat_ratio_stochastic")
+    cfg, _ = spec_for(g)
+    meta = dict(obs_normalization=g.meta["obs_normalization"], obs_stats=g.obs_stats,
+                include_warehouse_id=g.meta["include_warehouse_id"])
+    E = 6000
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", env_meta=meta, host_samplers=False)
+    env.enable_device_leads(seed=3)
+    a = env.sample_device_leads().cpu().numpy().astype(int)
+    exp = np.asarray(env.expected_lead_times, dtype=int)
+    md = np.array([0, 1, 2, 1, 0])
+    assert a.min() >= 1
+    for w in range(3):
+        for s in range(5):
+            d, x = md[s], a[:, w, s]
+            support = np.arange(exp[w, s] - d, exp[w, s] + d + 1)
+            pmf = np.full(len(support), 1.0 / len(support))
+            clipped = np.maximum(1, support)                     # deviations below 1 pile up on 1
+            vals = np.unique(clipped)
+            p = np.array([pmf[clipped == v].sum() for v in vals])
+            assert set(np.unique(x)) <= set(vals), (w, s)
+            if len(vals) > 1:
+                obs = np.array([(x == v).sum() for v in vals])
+                chi2 = ((obs - E * p) ** 2 / (E * p)).sum()
+                assert chi2 < stats.chi2.ppf(1 - 1e-6, len(vals) - 1), (w, s, chi2)
+    # cells are independent: neighbouring SKUs of the same warehouse are uncorrelated
+    c = np.corrcoef(a[:, 0, 1], a[:, 0, 2])[0, 1]
+    assert abs(c) < 5 / np.sqrt(E)
+    env._dl["step"] = 0
+    b = env.sample_device_leads().clone()
+    assert np.array_equal(b.cpu().numpy(), a)                    # same seed and step -> same draw
+    assert not torch.equal(env.sample_device_leads(), b)         # the next step differs
+    # stepping: own draws vs the same draws fed explicitly
+    fed = BatchedInventoryEnv(cfg, E, device="cuda:0", env_meta=meta, host_samplers=False)
+    init = torch.randint(0, 30, (E, 3, 5), dtype=torch.int32, device="cuda:0")
+    env.reset(init_inventory=init)
+    fed.reset(init_inventory=init)
+    env._dl["step"] = 10
+    from marlsc_b200.demand import pack_orders
+    rng = np.random.default_rng(2)
+    for t in range(6):
+        big = pack_orders([g.orders(i % g.N, t) for i in range(E)], 5)
+        act = torch.from_numpy(rng.uniform(-1, 1, (E, 3, 5)).astype(np.float32)).cuda()
+        ob1, r1, _ = env.step(act, orders=big)
+        ob2, r2, _ = fed.step(act, orders=big, actual_lead=env._dl["actual"])
+        assert torch.equal(env.inventory, fed.inventory) and torch.equal(env.ring_qty, fed.ring_qty)
+        assert torch.equal(env.ring_lead, fed.ring_lead) and torch.equal(ob1, ob2) and torch.equal(r1, r2)
+    assert int(env.ring_lead.max()) > 1
+    env.close()
+    fed.close()
+
+
 def test_step_with_device_demand_equals_same_orders_fed_as_csr():
     """The padded order layout the sampler writes and the CSR layout must drive K1 to the same result."""
     from marlsc_b200.demand import OrderBatch
