@@ -66,6 +66,18 @@ __device__ __forceinline__ uint32_t nonzero_nibble(uint32_t x) {
   return (t * 0x00204081u) >> 28;                                           // bits 7, 15, 23, 31 -> 28..31 (no carries)
 }
 
+// Shared-memory accesses of the chain loop by 32-bit shared-window address: the bases stay in registers and an
+// access is one instruction plus its offset arithmetic (generic pointers were re-derived on every trip).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_shared_add(uint32_t a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ldg_nc_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
 template <int SPL, int NCH>
 __global__ void __launch_bounds__(128, 6)
 env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
@@ -153,9 +165,17 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
     const int pn = imin(kPass, n_orders - p0);
     const int nw = (pn + OPW - 1) / OPW;
     // ---- mask pass ---------------------------------------------------------------------------------
+    static_assert(kPass == 64, "home_orders is one 64-bit mask");
+    unsigned long long home_orders = 0ull;            // bit j: order j goes to some warehouse's home region
 #pragma unroll
-    for (int h = 0; h < kPass / 32; ++h)
-      if (lane + 32 * h < pn) s_reg[lane + 32 * h] = reg[p0 + lane + 32 * h];
+    for (int h = 0; h < kPass / 32; ++h) {
+      int rg = -1;
+      if (lane + 32 * h < pn) {
+        rg = reg[p0 + lane + 32 * h];
+        s_reg[lane + 32 * h] = (int16_t)rg;
+      }
+      home_orders |= (unsigned long long)__ballot_sync(FULL, dh_acc != nullptr && rg >= 0 && t_hmask[rg] != 0u) << (32 * h);
+    }
     __syncwarp();
     const uint8_t* const rows = qty + (long long)p0 * S + lane;     // this lane's column of the pass
     auto mask_word = [&](int wi, auto tail) {
@@ -178,7 +198,7 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < SPL; ++k) word |= (b[oo][k] != 0u ? 1u : 0u) << (oo * NA + k);
         }
-        if (dh_acc && (!kTail || j < pn)) {           // uniform: the region belongs to the order
+        if ((home_orders >> j) & 1ull) {              // uniform: the region belongs to the order
           uint32_t hm = t_hmask[s_reg[j]];
           while (hm) {
             const int w = lowest_bit(hm);
@@ -196,62 +216,70 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
     for (int wi = 0; wi < nfull; ++wi) mask_word(wi, std::false_type());
     if (nfull < nw) mask_word(nfull, std::true_type());
     // ---- chain pass --------------------------------------------------------------------------------
-    int wi = 0;
-    uint32_t cur = s_mask[lane];
-    int rem = 0, r = 0, s = 0;
-    uint32_t am = 0u, cand = 0u;                      // warehouses holding s (bit w); the same in r's priority order
-    int n_q = 0;
-    unsigned n_k = 0, n_oj = 0;                       // the line after the current one: SKU slot, order
+    const uint8_t* rows_l = rows;
+    uint32_t a_mask = smem_addr(s_mask) + 4u * lane, a_reg = smem_addr(s_reg), a_avail = smem_addr(s_avail) + 2u * lane,
+             a_perm = smem_addr(t_perm), a_prio = smem_addr(t_prio), a_inv = smem_addr(s_inv) + 4u * lane,
+             a_shipq = smem_addr(s_shipq), a_lostU = smem_addr(s_lostU);
+    uint32_t Wp_l = Wp, SP4 = 4u * SP, S_l = S, R4 = 4u * R;
+    asm volatile("" : "+l"(rows_l), "+r"(a_mask), "+r"(a_reg), "+r"(a_avail), "+r"(a_perm), "+r"(a_prio), "+r"(a_inv),
+                 "+r"(a_shipq), "+r"(a_lostU), "+r"(Wp_l), "+r"(SP4), "+r"(S_l), "+r"(R4));   // keep them in registers
+    const uint32_t a_mask_end = a_mask + 128u * (nw - 1);
+    uint32_t cur = lds_u32(a_mask);
+    int rem = 0;
+    uint32_t r = 0, k32 = 0;                          // region; 32 * SKU slot of the current line
+    uint32_t am = 0u, cand = 0u;                      // warehouses holding the SKU (bit w); the same in r's priority order
+    uint32_t n_q = 0, n_k32 = 0, n_oj = 0;            // the line after the current one: quantity, 32 * SKU slot, order
     bool n_ok = false;
-    while (true) {
-      if (rem == 0 && n_ok) {                         // take the requested line
-        rem = n_q;
-        s = lane + 32 * (int)n_k;
-        r = s_reg[n_oj];
-        n_ok = false;
-        am = s_avail[s];
-        const uint16_t* pm = t_perm + r * (NCH * 16);
-        cand = pm[am & 15u];
-        if (NCH > 1) cand |= pm[16 + ((am >> 4) & 15u)];
-        if (NCH > 2) cand |= pm[32 + ((am >> 8) & 15u)];
-        if (NCH > 3) cand |= pm[48 + ((am >> 12) & 15u)];
+    auto request = [&]() {                            // find the lane's next line and ask for its quantity
+      while (cur == 0u && a_mask != a_mask_end) cur = lds_u32(a_mask += 128u);
+      n_ok = cur != 0u;
+      if (n_ok) {
+        const uint32_t bit = (uint32_t)lowest_bit(cur);
+        cur &= cur - 1;
+        n_oj = ((uint32_t)(nw - 1) - ((a_mask_end - a_mask) >> 7)) * OPW + bit / NA;
+        n_k32 = 32u * (bit % NA);
+        n_q = ldg_nc_u8(rows_l + (n_oj * S_l + n_k32));
       }
-      if (!n_ok) {                                    // request the one after it
-        if (cur == 0u && wi + 1 < nw) cur = s_mask[(++wi) * 32 + lane];
-        if (cur != 0u) {
-          const unsigned bit = (unsigned)lowest_bit(cur);
-          cur &= cur - 1;
-          n_oj = (unsigned)wi * OPW + bit / NA;
-          n_k = bit % NA;
-          n_q = rows[n_oj * (unsigned)S + 32u * n_k];
-          n_ok = true;
-        }
+    };
+    request();
+    while (true) {
+      if (rem == 0 && n_ok) {                         // take the requested line, request the one after it
+        rem = (int)n_q;
+        k32 = n_k32;
+        r = (uint32_t)lds_s16(a_reg + 2u * n_oj);
+        am = lds_u16(a_avail + 2u * k32);
+        const uint32_t pm = a_perm + r * (NCH * 32u);
+        cand = lds_u16(pm + 2u * (am & 15u));
+        if (NCH > 1) cand |= lds_u16(pm + 32u + 2u * ((am >> 4) & 15u));
+        if (NCH > 2) cand |= lds_u16(pm + 64u + 2u * ((am >> 8) & 15u));
+        if (NCH > 3) cand |= lds_u16(pm + 96u + 2u * ((am >> 12) & 15u));
+        request();
       }
       if (rem > 0) {
         if (cand != 0u) {                             // ship from the cheapest warehouse that has the SKU
-          const int v = lowest_bit(cand);
+          const uint32_t v = (uint32_t)lowest_bit(cand);
           cand &= cand - 1;
-          const int w = t_prio[r * Wp + v];
-          const int cell = w * SP + s;
-          const int a = s_inv[cell];                  // the cells of a line's SKU belong to this lane
+          const uint32_t w = lds_u8(a_prio + r * Wp_l + v);
+          const uint32_t cell = a_inv + w * SP4 + 4u * k32;
+          const int a = (int)lds_u32(cell);           // the cells of a line's SKU belong to this lane
           const int f = imin(rem, a);
-          s_inv[cell] = a - f;
-          atomicAdd(&s_shipq[w * R + r], f);
+          sts_u32(cell, (uint32_t)(a - f));
+          red_shared_add(a_shipq + w * R4 + 4u * r, f);
           rem -= f;
           if (a == f) {                               // emptied
             am &= ~(1u << w);
-            s_avail[s] = (uint16_t)am;
+            sts_u16(a_avail + 2u * k32, am);
           }
         }
         if (rem > 0 && cand == 0u) {
           // no warehouse can supply the rest: lost (demand_allocator.py:205-208); units are enough when every
           // SKU carries the same penalty rate
-          atomicAdd(&s_lostU[r], rem);
-          if (!pen_uniform) atomicAdd(&s_lostP[r], (double)rem * sp.pen_rate[s]);
+          red_shared_add(a_lostU + 4u * r, rem);
+          if (!pen_uniform) atomicAdd(&s_lostP[r], (double)rem * sp.pen_rate[lane + k32]);
           rem = 0;
         }
       }
-      if (!__any_sync(FULL, rem > 0 || n_ok || cur != 0u || wi + 1 < nw)) break;
+      if (!__any_sync(FULL, rem > 0 || n_ok)) break;
     }
     __syncwarp();
   }
@@ -279,11 +307,16 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
       int shipped_r = 0;
       if (lost)
         for (int w = 0; w < W; ++w) shipped_r += s_shipq[w * R + r];
+      // shipment handler (lost_sales_handler.py:113-148): region r's lost volume goes to the warehouses in
+      // proportion to what they shipped there; one division per region
+      const bool by_share = lost && sp.lost_type == MARLSC_LOST_SHIPMENT && shipped_r > 0;
+      const double lp_unit = by_share ? lp / (double)shipped_r : 0.0;
       for (int w = 0; w < W; ++w) {
         const int sq = s_shipq[w * R + r];
         double c = 0.0;
         if (sq > 0) c = (double)sq * sp.out_var[w * R + r];
-        if (lost) c += lost_weight<CAPS>(sp, s_shipq, s_lostU, nullptr, w, r, shipped_r) * lp;
+        if (by_share) c += (double)sq * lp_unit;
+        else if (lost) c += lost_weight<CAPS>(sp, s_shipq, s_lostU, nullptr, w, r, shipped_r) * lp;
         if (sq > 0 || lost) tile[w * 33 + lane] += c;
       }
     }
