@@ -115,6 +115,7 @@ struct DevSpec {
   const uint16_t* prio_perm;   // [R,perm_chunks,16] availability bits -> priority-order bits (W <= 16), else null
   int perm_chunks;
   int pen_uniform;             // every SKU has the same lost-sales penalty rate
+  int row_rates_uniform;       // holding / weight / inbound rates do not vary over the SKUs of a warehouse
   const float* obs_mean;
   const float* obs_std;        // holds 1/std (precomputed on the host in float32)
   // observation block offsets inside one warehouse's vector (before the id prefix); -1 = block disabled
@@ -204,7 +205,10 @@ struct Team {
     }
     return v;
   }
-  __device__ __forceinline__ int sum(int v) const { return sum_t(v); }
+  __device__ __forceinline__ int sum(int v) const {
+    if (G == 32) return __reduce_add_sync(0xffffffffu, v);   // one REDUX instead of five shuffle rounds
+    return sum_t(v);
+  }
   __device__ __forceinline__ float sum(float v) const { return sum_t(v); }
   __device__ __forceinline__ double sum(double v) const { return sum_t(v); }
 #else

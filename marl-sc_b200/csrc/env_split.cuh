@@ -49,12 +49,13 @@ env_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
                  const __grid_constant__ marlsc_step_io_t io, int t) {
   constexpr uint32_t CAPS = kCapsLean;
   const int W = sp.W, S = sp.S, D = sp.D, WS = W * S;
-  const int64_t row = (int64_t)blockIdx.x * (128 / G) + threadIdx.x / G;
-  if (row >= st.num_envs * W) return;
+  const unsigned row = blockIdx.x * (128u / G) + threadIdx.x / G;     // rows fit 32 bits (split_ok, env_step.cu)
+  if (row >= (unsigned)st.num_envs * (unsigned)W) return;
   Team<G> tm;
   tm.init();
-  const int64_t e = row / W;
-  const int w = (int)(row - e * W);
+  const unsigned eu = row / (unsigned)W;
+  const int64_t e = eu;
+  const int w = (int)(row - eu * (unsigned)W);
   const Tables tb = global_tables(sp);
   const EnvPtrs p = env_ptrs(sp, st, e);
   const float* act = pinned(io.actions + e * WS);
@@ -232,17 +233,21 @@ env_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ m
                    const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_rows, int t) {
   constexpr uint32_t CAPS = kCapsLean;
   const int W = sp.W, S = sp.S, D = sp.D, WS = W * S;
-  const int64_t row = (int64_t)blockIdx.x * (128 / G) + threadIdx.x / G;
-  if (row >= st.num_envs * W) return;
+  const unsigned row = blockIdx.x * (128u / G) + threadIdx.x / G;     // rows fit 32 bits (split_ok, env_step.cu)
+  if (row >= (unsigned)st.num_envs * (unsigned)W) return;
   Team<G> tm;
   tm.init();
-  const int64_t e = row / W;
-  const int w = (int)(row - e * W);
+  const unsigned eu = row / (unsigned)W;
+  const int64_t e = eu;
+  const int w = (int)(row - eu * (unsigned)W);
   const Tables tb = global_tables(sp);
   const EnvPtrs p = env_ptrs(sp, st, e);
   const int32_t* ring_new = pinned(p.ring_q + (t % D) * WS);
   const int hist_n = imin(t + 1, kWindow);
   const int base = w * S;
+  const int32_t* hist_old[kWindow - 1];             // the older planes of the window, newest first
+  MARLSC_UNROLL
+  for (int back = 1; back < kWindow; ++back) hist_old[back - 1] = p.hist + pmod(t - back, kWindow) * WS + base;
   int vI[SPL], vdh[SPL], vz[SPL], vq[SPL], hsum[SPL];
   float vrm[SPL], vf[SPL];
   MARLSC_UNROLL
@@ -258,23 +263,38 @@ env_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ m
         vdh[j] = load_cg(&p.hist[(t % kWindow) * WS + i]);     // accumulated by K1b with fire-and-forget adds
         MARLSC_UNROLL
         for (int back = 1; back < kWindow; ++back)
-          if (back < hist_n) hsum[j] += p.hist[pmod(t - back, kWindow) * WS + i];
+          if (back < hist_n) hsum[j] += hist_old[back - 1][s];
       }
     }
   }
   double cost = 0.0;
+  const bool by_row = sp.row_rates_uniform != 0;      // rates constant over the row: integer sums, three products
+  int nI = 0, nQ = 0, nPos = 0;
   MARLSC_UNROLL
   for (int j = 0; j < SPL; ++j) {
     const int s = tm.gl + G * j;
     if (s < S) {
       const int i = base + s;
-      cost += (double)vI[j] * tb.hold[s];                                                     // holding
-      if (vq[j] > 0) cost += sp.in_fixed[i] + ((double)vq[j] * tb.skw[s]) * sp.in_var[i];    // inbound
+      if (by_row) {
+        nI += vI[j];
+        nQ += vq[j];
+        nPos += vq[j] > 0 ? 1 : 0;
+      } else {
+        cost += (double)vI[j] * tb.hold[s];                                                     // holding
+        if (vq[j] > 0) cost += sp.in_fixed[i] + ((double)vq[j] * tb.skw[s]) * sp.in_var[i];    // inbound
+      }
       // integer-valued float32 sum over the window is exact in any order (multi_env.py:785-787)
       if (sp.need_hist) vrm[j] = f_div((float)(hsum[j] + vdh[j]), (float)hist_n);
     }
   }
-  cost = tm.sum(cost);
+  if (by_row) {
+    nI = tm.sum(nI);
+    nQ = tm.sum(nQ);
+    nPos = tm.sum(nPos);
+    cost = (double)nI * tb.hold[0] + ((double)nPos * sp.in_fixed[base] + ((double)nQ * tb.skw[0]) * sp.in_var[base]);
+  } else {
+    cost = tm.sum(cost);
+  }
   if (tm.gl == 0) cost_rows[row] = cost;
   write_obs_row<G, SPL, CAPS>(sp, tb, tm, p, io.obs + row * (int64_t)sp.obs_dim, w, t, hist_n, vI, vdh, vz, vz, vrm, vf);
 }

@@ -332,7 +332,8 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool lean = !env->force_generic && (required_caps(env->ds, env->tb, io) & ~kCapsLean) == 0;
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
-  if (lean && split_ok(env)) {
+  // the row kernels of the split step index (environment, warehouse) rows with 32 bits
+  if (lean && split_ok(env) && state->num_envs * (int64_t)env->ds.W < (int64_t)0xffffffffLL) {
     rc = ensure_work(env, state->num_envs);
     if (rc) return rc;
     const SplitWork wk{env->d_work, env->d_work + (size_t)env->work_envs * env->ds.W, env->timing ? env->marks : nullptr};

@@ -128,6 +128,12 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
   }
   ds.pen_uniform = 1;
   for (int s = 1; s < S; ++s) ds.pen_uniform = ds.pen_uniform && tb.pen_rate[s] == tb.pen_rate[0];
+  // holding and inbound rates that do not vary over the SKUs of a warehouse row: K1c sums integers per row
+  ds.row_rates_uniform = 1;
+  for (int s = 1; s < S; ++s) ds.row_rates_uniform = ds.row_rates_uniform && tb.hold_rate[s] == tb.hold_rate[0] && tb.skw[s] == tb.skw[0];
+  for (int w = 0; w < W; ++w)
+    for (int s = 1; s < S; ++s)
+      ds.row_rates_uniform = ds.row_rates_uniform && tb.in_fixed[w * S + s] == tb.in_fixed[w * S] && tb.in_var[w * S + s] == tb.in_var[w * S];
 
   tb.home_mask.clear();
   if (W <= 32) {
