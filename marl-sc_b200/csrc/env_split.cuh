@@ -21,6 +21,10 @@
 #pragma once
 #include "env_kernels.cuh"
 
+#ifndef MARLSC_ROW_MIN_BLOCKS
+#define MARLSC_ROW_MIN_BLOCKS 1   // resident CTAs per SM the row kernels (K1a, K1c) are compiled for
+#endif
+
 namespace marlsc {
 
 struct SplitWork {
@@ -44,7 +48,7 @@ MDEV Tables global_tables(const DevSpec& sp) {
 
 // ---- K1a ------------------------------------------------------------------------------------------
 template <int G, int SPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MARLSC_ROW_MIN_BLOCKS)
 env_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                  const __grid_constant__ marlsc_step_io_t io, int t) {
   constexpr uint32_t CAPS = kCapsLean;
@@ -228,7 +232,7 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
 
 // ---- K1c ------------------------------------------------------------------------------------------
 template <int G, int SPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MARLSC_ROW_MIN_BLOCKS)
 env_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                    const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_rows, int t) {
   constexpr uint32_t CAPS = kCapsLean;
