@@ -225,35 +225,38 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
                  "+r"(a_shipq), "+r"(a_lostU), "+r"(Wp_l), "+r"(SP4), "+r"(S_l), "+r"(R4));   // keep them in registers
     const uint32_t a_mask_end = a_mask + 128u * (nw - 1);
     uint32_t cur = lds_u32(a_mask);
+    uint32_t oj_base = 0;                             // first order of the lane's current mask word
     int rem = 0;
     uint32_t r = 0, k32 = 0;                          // region; 32 * SKU slot of the current line
     uint32_t am = 0u, cand = 0u;                      // warehouses holding the SKU (bit w); the same in r's priority order
     uint32_t n_q = 0, n_k32 = 0, n_oj = 0;            // the line after the current one: quantity, 32 * SKU slot, order
     bool n_ok = false;
-    auto request = [&]() {                            // find the lane's next line and ask for its quantity
-      while (cur == 0u && a_mask != a_mask_end) cur = lds_u32(a_mask += 128u);
-      n_ok = cur != 0u;
-      if (n_ok) {
-        const uint32_t bit = (uint32_t)lowest_bit(cur);
-        cur &= cur - 1;
-        n_oj = ((uint32_t)(nw - 1) - ((a_mask_end - a_mask) >> 7)) * OPW + bit / NA;
-        n_k32 = 32u * (bit % NA);
-        n_q = ldg_nc_u8(rows_l + (n_oj * S_l + n_k32));
-      }
-    };
-    request();
     while (true) {
-      if (rem == 0 && n_ok) {                         // take the requested line, request the one after it
-        rem = (int)n_q;
-        k32 = n_k32;
-        r = (uint32_t)lds_s16(a_reg + 2u * n_oj);
-        am = lds_u16(a_avail + 2u * k32);
-        const uint32_t pm = a_perm + r * (NCH * 32u);
-        cand = lds_u16(pm + 2u * (am & 15u));
-        if (NCH > 1) cand |= lds_u16(pm + 32u + 2u * ((am >> 4) & 15u));
-        if (NCH > 2) cand |= lds_u16(pm + 64u + 2u * ((am >> 8) & 15u));
-        if (NCH > 3) cand |= lds_u16(pm + 96u + 2u * ((am >> 12) & 15u));
-        request();
+      if (rem == 0) {
+        if (n_ok) {                                   // take the requested line
+          rem = (int)n_q;
+          k32 = n_k32;
+          r = (uint32_t)lds_s16(a_reg + 2u * n_oj);
+          am = lds_u16(a_avail + 2u * k32);
+          const uint32_t pm = a_perm + r * (NCH * 32u);
+          cand = lds_u16(pm + 2u * (am & 15u));
+          if (NCH > 1) cand |= lds_u16(pm + 32u + 2u * ((am >> 4) & 15u));
+          if (NCH > 2) cand |= lds_u16(pm + 64u + 2u * ((am >> 8) & 15u));
+          if (NCH > 3) cand |= lds_u16(pm + 96u + 2u * ((am >> 12) & 15u));
+        }
+        // find the lane's next line and ask for its quantity (an all-zero word costs the lane one idle trip)
+        if (cur == 0u && a_mask != a_mask_end) {
+          cur = lds_u32(a_mask += 128u);
+          oj_base += OPW;
+        }
+        n_ok = cur != 0u;
+        if (n_ok) {
+          const uint32_t bit = (uint32_t)lowest_bit(cur);
+          cur &= cur - 1;
+          n_oj = oj_base + bit / NA;
+          n_k32 = 32u * (bit % NA);
+          n_q = ldg_nc_u8(rows_l + (n_oj * S_l + n_k32));
+        }
       }
       if (rem > 0) {
         if (cand != 0u) {                             // ship from the cheapest warehouse that has the SKU
@@ -279,7 +282,7 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
           rem = 0;
         }
       }
-      if (!__any_sync(FULL, rem > 0 || n_ok)) break;
+      if (!__any_sync(FULL, rem > 0 || n_ok || a_mask != a_mask_end)) break;
     }
     __syncwarp();
   }
@@ -292,39 +295,51 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
       if (s < S) p.inv[w * S + s] = s_inv[w * SP + s];
     }
   __syncwarp();
-  // Outbound cost and lost-sales penalty of every warehouse (reward_calculator.py:150-175). Lanes take regions;
-  // a lane's partial sums per warehouse go to a [W][33] tile laid over the stock scratch (written back above),
-  // then lane w adds up row w.
+  // Outbound cost and lost-sales penalty of every warehouse (reward_calculator.py:150-175). Lanes take regions
+  // (two per lane cover R <= 64). Per region the lost volume's cost lp is either spread over the warehouses in
+  // proportion to what they shipped there (shipment handler, lost_sales_handler.py:113-148: a rate per shipped unit,
+  // one division per region) or goes to the closest warehouse (closest handler, and the shipment handler's fallback
+  // when nothing was shipped). Then warehouse by warehouse: the lanes' partial sums meet in a shuffle reduction.
   const double pen0 = sp.pen_rate[0];
-  const bool tiled = W * 33 * 8 <= W * SP * 4 && W <= 32;
-  if (tiled) {
-    double* const tile = reinterpret_cast<double*>(s_inv);
-    for (int w = 0; w < W; ++w) tile[w * 33 + lane] = 0.0;
-    for (int r = lane; r < R; r += 32) {
-      const int lu = s_lostU[r];
-      const bool lost = lu > 0;
-      const double lp = !lost ? 0.0 : (pen_uniform ? (double)lu * pen0 : s_lostP[r]);
-      int shipped_r = 0;
-      if (lost)
-        for (int w = 0; w < W; ++w) shipped_r += s_shipq[w * R + r];
-      // shipment handler (lost_sales_handler.py:113-148): region r's lost volume goes to the warehouses in
-      // proportion to what they shipped there; one division per region
-      const bool by_share = lost && sp.lost_type == MARLSC_LOST_SHIPMENT && shipped_r > 0;
-      const double lp_unit = by_share ? lp / (double)shipped_r : 0.0;
-      for (int w = 0; w < W; ++w) {
-        const int sq = s_shipq[w * R + r];
-        double c = 0.0;
-        if (sq > 0) c = (double)sq * sp.out_var[w * R + r];
-        if (by_share) c += (double)sq * lp_unit;
-        else if (lost) c += lost_weight<CAPS>(sp, s_shipq, s_lostU, nullptr, w, r, shipped_r) * lp;
-        if (sq > 0 || lost) tile[w * 33 + lane] += c;
+  constexpr int kRL = 2;                                // regions per lane in the fast path
+  if (R <= 32 * kRL) {
+    double rate[kRL], lump[kRL];                        // per shipped unit; to the closest warehouse
+    int close_w[kRL];
+#pragma unroll
+    for (int q = 0; q < kRL; ++q) {
+      const int r = lane + 32 * q;
+      rate[q] = lump[q] = 0.0;
+      close_w[q] = -1;
+      if (r < R) {
+        const int lu = s_lostU[r];
+        if (lu > 0) {
+          const double lp = pen_uniform ? (double)lu * pen0 : s_lostP[r];
+          int shipped_r = 0;
+          if (sp.lost_type == MARLSC_LOST_SHIPMENT)
+            for (int w = 0; w < W; ++w) shipped_r += s_shipq[w * R + r];
+          if (shipped_r > 0) {
+            rate[q] = lp / (double)shipped_r;
+          } else {
+            lump[q] = lp;
+            close_w[q] = sp.closest[r];
+          }
+        }
       }
     }
-    __syncwarp();
-    if (lane < W) {
+    for (int w = 0; w < W; ++w) {
       double c = 0.0;
-      for (int l = 0; l < 32; ++l) c += tile[lane * 33 + l];
-      cost_alloc[e * W + lane] = c;
+#pragma unroll
+      for (int q = 0; q < kRL; ++q) {
+        const int r = lane + 32 * q;
+        if (r < R) {
+          const int sq = s_shipq[w * R + r];
+          if (sq > 0) c += (double)sq * (sp.out_var[w * R + r] + rate[q]);
+          if (close_w[q] == w) c += lump[q];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+      if (lane == 0) cost_alloc[e * W + w] = c;
     }
   } else {
     for (int w = 0; w < W; ++w) {
