@@ -11,6 +11,8 @@
 //
 // K5 evaluates the reference's base-stock heuristic (src/experiments/run_baselines.py:133-207) for every
 // environment: qty = clip(S[w,k] - on_hand - in_transit, 0, max_qty), action = 2 qty / max_qty - 1 (float32).
+#include <cmath>
+
 #include "env_kernels.cuh"
 
 namespace marlsc {
@@ -54,11 +56,33 @@ __device__ __forceinline__ int poisson_from(float lambda, float u, float u2) {
   return v < 0.f ? 0 : (int)v;
 }
 
+constexpr int kCdf = 16;     // tabulated Poisson CDF entries per (region, SKU): P(X <= k), k < kCdf
 struct DemandParams {
   const float* lam_orders;   // [R]
   const float* prob;         // [R]
   const float* lam_qty;      // [R,S]
+  const float* cdf_qty;      // [R,S,kCdf]
 };
+
+// Quantity max(1, Poisson(lambda)) by inversion: the smallest k with u <= P(X <= k), found by a four-step search of the
+// tabulated CDF (same result as poisson_from's sequential search up to float rounding of the table); beyond the table
+// the sequential search continues from its last entry. lambda >= 30 keeps the rounded-normal branch.
+__device__ __forceinline__ int quantity_from(const float* __restrict__ cdf, float lambda, float u, float u2) {
+  if (lambda >= 30.f || lambda <= 0.f) return poisson_from(lambda, u, u2);
+  int k = u > cdf[7] ? 8 : 0;
+  k += u > cdf[k + 3] ? 4 : 0;
+  k += u > cdf[k + 1] ? 2 : 0;
+  k += u > cdf[k] ? 1 : 0;
+  if (k == kCdf - 1 && u > cdf[kCdf - 1]) {            // tail: P(X > 15) (1e-4 at lambda 5)
+    float F = cdf[kCdf - 1], p = F - cdf[kCdf - 2];
+    while (u > F && k < 200) {
+      ++k;
+      p *= lambda / (float)k;
+      F += p;
+    }
+  }
+  return k;
+}
 
 // one warp per environment
 __global__ void __launch_bounds__(128)
@@ -102,7 +126,7 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
               const float uq = (float)(c[j] >> 12) * (1.0f / 1048576.0f);
               int q = 0;
               if (ub < p) {
-                q = poisson_from(dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
+                q = quantity_from(dp.cdf_qty + (size_t)(rr * S + s) * kCdf, dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
                 q = q < 1 ? 1 : (q > 255 ? 255 : q);
               }
               qty_e[(long long)row * S + s] = (uint8_t)q;
@@ -147,32 +171,43 @@ sample_lead_kernel(const int32_t* __restrict__ expected, const int32_t* __restri
   }
 }
 
-// K5: one thread per (env, warehouse, SKU) cell
+// K5: one thread per (env, warehouse, SKU) cell; IDX is 32-bit whenever the batch has fewer than 2^32 cells. The
+// in-transit planes of a cell are read four at a time (independent loads in flight instead of a chain of le).
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                          const float* __restrict__ level, int t, float* __restrict__ actions) {
-  const long long WS = (long long)sp.W * sp.S;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= st.num_envs * WS) return;
-  const long long e = idx / WS;
+  const IDX WS = (IDX)(sp.W * sp.S);
+  const IDX idx = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;
+  if (idx >= (IDX)st.num_envs * WS) return;
+  const IDX e = idx / WS;
   const int i = (int)(idx - e * WS);
-  const int32_t* ring = st.ring_qty + e * WS * sp.D;
+  const int D = sp.D;
+  const int32_t* ring = st.ring_qty + (long long)e * (long long)WS * D + i;
   const int le = sp.lead_exp[i];
   int pending = 0;                                     // units ordered and not yet arrived before step t
   if (sp.lead_mode == MARLSC_LEAD_FIXED) {
-    int row = (t - 1) % sp.D;                          // plane of the order placed one step ago, then backwards
+    int row = (t - 1) % D;                             // plane of the order placed one step ago, then backwards
     const int n = le < t ? le : t;
-    for (int a = 0; a < n; ++a) {
-      pending += ring[(long long)row * WS + i];
-      row = row == 0 ? sp.D - 1 : row - 1;
+    for (int a0 = 0; a0 < n; a0 += 4) {
+      int v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int rr = row - k;
+        rr += rr < 0 ? D : 0;
+        v[k] = a0 + k < n ? ring[(long long)rr * (long long)WS] : 0;
+      }
+      pending += (v[0] + v[1]) + (v[2] + v[3]);
+      row -= 4;
+      row += row < 0 ? D : 0;
     }
   } else {
-    const uint8_t* rl = st.ring_lead + e * WS * sp.D;
-    for (int d = 0; d < sp.D; ++d) {
-      const int tau = (t - 1) - (((t - 1 - d) % sp.D + sp.D) % sp.D);
+    const uint8_t* rl = st.ring_lead + (long long)e * (long long)WS * D + i;
+    for (int d = 0; d < D; ++d) {
+      const int tau = (t - 1) - (((t - 1 - d) % D + D) % D);
       if (tau < 0) continue;
-      const int q = ring[(long long)d * WS + i];
-      if (q > 0 && tau + (int)rl[(long long)d * WS + i] >= t) pending += q;
+      const int q = ring[(long long)d * (long long)WS];
+      if (q > 0 && tau + (int)rl[(long long)d * (long long)WS] >= t) pending += q;
     }
   }
   const double mx = sp.action_max[i % sp.S];
@@ -185,7 +220,8 @@ int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const flo
                       cudaStream_t s) {
   const long long n = st.num_envs * (long long)ds.W * ds.S;
   const unsigned grid = (unsigned)((n + 255) / 256);
-  base_stock_policy_kernel<<<grid, 256, 0, s>>>(ds, st, level, t, actions);
+  if (n < (1LL << 32)) base_stock_policy_kernel<unsigned><<<grid, 256, 0, s>>>(ds, st, level, t, actions);
+  else base_stock_policy_kernel<long long><<<grid, 256, 0, s>>>(ds, st, level, t, actions);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;
@@ -207,7 +243,8 @@ int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda
                          const double* lambda_quantity, int device, marlsc_demand_t** out) {
   if (!out || !lambda_orders || !probability_skus || !lambda_quantity) return set_error(MARLSC_EINVAL, "null argument");
   if (n_regions < 1 || n_skus < 1) return set_error(MARLSC_EINVAL, "n_regions and n_skus must be positive");
-  std::vector<float> host((size_t)2 * n_regions + (size_t)n_regions * n_skus);
+  const size_t n_cells = (size_t)n_regions * n_skus;
+  std::vector<float> host((size_t)2 * n_regions + n_cells * (1 + kCdf));
   for (int r = 0; r < n_regions; ++r) {
     if (!(lambda_orders[r] >= 0.0) || !(probability_skus[r] >= 0.0 && probability_skus[r] <= 1.0))
       return set_error(MARLSC_EINVAL, "lambda_orders must be >= 0 and probability_skus in [0,1]");
@@ -217,6 +254,16 @@ int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda
   for (size_t i = 0; i < (size_t)n_regions * n_skus; ++i) {
     if (!(lambda_quantity[i] >= 0.0)) return set_error(MARLSC_EINVAL, "lambda_quantity must be >= 0");
     host[2 * n_regions + i] = (float)lambda_quantity[i];
+    // P(X <= k) for the float32 rate the kernel sees, accumulated in double
+    const double lam = (double)(float)lambda_quantity[i];
+    double pk = std::exp(-lam), F = pk;
+    for (int k = 0; k < kCdf; ++k) {
+      if (k > 0) {
+        pk *= lam / k;
+        F += pk;
+      }
+      host[2 * n_regions + n_cells + i * kCdf + k] = (float)F;
+    }
   }
   marlsc_demand* d = new (std::nothrow) marlsc_demand();
   if (!d) return set_error(MARLSC_ENOMEM, "out of host memory");
@@ -234,6 +281,7 @@ int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda
   d->dp.lam_orders = d->blob;
   d->dp.prob = d->blob + n_regions;
   d->dp.lam_qty = d->blob + 2 * n_regions;
+  d->dp.cdf_qty = d->blob + 2 * n_regions + n_cells;
   *out = d;
   return MARLSC_OK;
 }
