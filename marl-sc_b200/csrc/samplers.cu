@@ -140,6 +140,47 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
   if (lane == 0) counts[e] = row;
 }
 
+// K4 for small SKU counts: one thread per environment (a warp per environment leaves 30 of 32 lanes idle at two
+// SKUs). Same Philox counters and words as sample_demand_kernel, so both kernels draw identical orders.
+__global__ void __launch_bounds__(128)
+sample_demand_thread_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, long long step, int omax,
+                            int32_t* __restrict__ counts, int16_t* __restrict__ region, uint8_t* __restrict__ qty,
+                            int32_t* __restrict__ overflow) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int16_t* reg_e = region + e * omax;
+  uint8_t* qty_e = qty + e * (long long)omax * S;
+  int row = 0;
+  for (int r = 0; r < R; ++r) {
+    uint32_t c[4] = {(uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)step, (uint32_t)r};
+    philox4x32(c, seed);
+    const int nr = poisson_from(dp.lam_orders[r], u01(c[0]), u01(c[1]));
+    const float p = dp.prob[r];
+    for (int i = 0; i < nr; ++i) {
+      if (row >= omax) {
+        atomicExch(overflow, 1);
+        continue;
+      }
+      reg_e[row] = (int16_t)r;
+      for (int s = 0; s < S; ++s) {
+        const int s0 = s & ~127, lane = s & 31, j = (s >> 5) & 3;   // the warp kernel's (block, lane, word) of SKU s
+        uint32_t d[4] = {(uint32_t)e, (uint32_t)row | 0x80000000u, (uint32_t)step, (uint32_t)(s0 + lane)};
+        philox4x32(d, seed);
+        const float ub = (float)(d[j] & 0xfffu) * (1.0f / 4096.0f);
+        const float uq = (float)(d[j] >> 12) * (1.0f / 1048576.0f);
+        int q = 0;
+        if (ub < p) {
+          q = quantity_from(dp.cdf_qty + (size_t)(r * S + s) * kCdf, dp.lam_qty[r * S + s], uq, ub * (1.0f / p));
+          q = q < 1 ? 1 : (q > 255 ? 255 : q);
+        }
+        qty_e[(long long)row * S + s] = (uint8_t)q;
+      }
+      ++row;
+    }
+  }
+  counts[e] = row;
+}
+
 // K4b: actual lead times of one step, four consecutive cells per thread (one Philox call). A 32-bit word w gives
 // the deviation floor(w * (2d+1) / 2^32) - d: uniform over {-d..+d} up to a bias below (2d+1) / 2^32.
 __global__ void __launch_bounds__(256)
@@ -297,10 +338,15 @@ int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, in
   if (!d || !order_counts || !order_region || !order_qty || !overflow_flag) return set_error(MARLSC_EINVAL, "null argument");
   if (num_envs < 1 || max_orders_per_env < 1) return set_error(MARLSC_EINVAL, "num_envs and max_orders_per_env must be positive");
   MARLSC_CUDA(cudaSetDevice(d->device));
-  const int wpb = 4;
-  const unsigned grid = (unsigned)((num_envs + wpb - 1) / wpb);
-  sample_demand_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      d->dp, d->R, d->S, num_envs, seed, step_index, max_orders_per_env, order_counts, order_region, order_qty, overflow_flag);
+  if (d->S <= 16) {   // few SKUs: a thread per environment
+    sample_demand_thread_kernel<<<(unsigned)((num_envs + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d->dp, d->R, d->S, num_envs, seed, step_index, max_orders_per_env, order_counts, order_region, order_qty, overflow_flag);
+  } else {
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((num_envs + wpb - 1) / wpb);
+    sample_demand_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        d->dp, d->R, d->S, num_envs, seed, step_index, max_orders_per_env, order_counts, order_region, order_qty, overflow_flag);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;

@@ -577,3 +577,138 @@ def test_cuda_edge_cases_vs_oracle(team):
             np.testing.assert_allclose(ob[i], out["obs_local"], rtol=1e-5, atol=2e-5, err_msg=f"obs t={t} env={i}")
             assert bool(trunc) == bool(out["trunc"])
     env.close()
+
+
+@pytest.mark.parametrize("W,S,R,lost,pen_uniform,max_orders", [
+    (3, 20, 5, "shipment", True, 9),       # one SKU per lane, one permutation chunk
+    (7, 70, 9, "closest", False, 9),       # four SKUs per lane (ragged: S % 32 != 0), per-SKU penalties -> fp64 lost sums
+    (10, 100, 50, "shipment", False, 80),  # the large shape; more than 64 orders in a step -> two mask passes
+    (16, 200, 70, "shipment", True, 12),   # eight SKUs per lane, four permutation chunks, R > 64 -> generic cost epilogue
+])
+def test_one_warp_split_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders):
+    """The split step with one-warp teams (K1a / env_alloc_warp_kernel / K1c) against the oracle on shapes that reach every
+    instantiation of the allocation kernel, with scarce stock (most lines are split or lost), environments without
+    orders, all-zero orders, a batch that does not fill the last CTA and a mid-run reset."""
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.demand import pack_orders
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from oracle.inventory_oracle import OracleEnv
+    rng = np.random.default_rng(W * 1000 + S)
+    out_var = np.stack([rng.permutation(W) for _ in range(R)], 1) * 0.05 + 0.05          # tie-free -> static priority
+    pen = 4.0 if pen_uniform else [float(x) for x in rng.integers(1, 9, S)]
+    env_dict = dict(
+        action_space=dict(type="direct", params=dict(max_order_quantities=[int(x) for x in rng.integers(5, 30, S)])),
+        n_warehouses=W, n_skus=S, n_regions=R, episode_length=9, max_wh_capacities=[1e7] * W,
+        initial_inventory=dict(type="custom", params=dict(values=6)),
+        cost_structure=dict(
+            holding_cost=0.5, penalty_cost=pen,
+            shipment_cost=dict(outbound_fixed=np.zeros((W, R)).tolist(), outbound_variable=out_var.tolist(),
+                               inbound_fixed=np.full((W, S), 0.5).tolist(), inbound_variable=np.full((W, S), 0.25).tolist()),
+            sku_weights=[1.0] * S, distances=(rng.integers(10, 500, (W, R)) * 1.0).tolist()),
+        components=dict(
+            demand_sampler=dict(type="poisson", params=dict(lambda_orders=1.0, probability_skus=0.3, lambda_quantity=5.0)),
+            demand_allocator=dict(type="greedy", params=dict(max_splits=W - 1)),
+            lead_time_sampler=dict(type="fixed", params=dict(expected_lead_times=rng.integers(1, 4, (W, S)).tolist())),
+            lost_sales_handler=dict(type=lost, params=None),
+            reward_calculator=dict(type="cost", params=dict(scope="agent", scale_factor=0.1, cost_weights=[0.25] * 4))),
+        data_source=dict(type="custom"),
+        features=dict(inventory=True, pipeline=True, incoming_demand_home=False, units_shipped_home=False, units_shipped_away=False,
+                      stockout=False, rolling_demand_mean=True, demand_forecast=False, days_of_supply=False,
+                      net_inventory_position=False, demand_variability=False, demand_history=False, inventory_aggregate=True,
+                      pipeline_aggregate=False, incoming_demand_home_aggregate=False, units_shipped_away_aggregate=False,
+                      rolling_demand_mean_aggregate=False, demand_forecast_aggregate=False))
+    cfg = environment_config_from_dict(dict(env_dict, allow_region_mismatch=True))
+    E, T = 6, 13
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, team_size=32)
+    assert env.team_size == 32
+    oracles = [OracleEnv(env_dict) for _ in range(E)]
+
+    def reset_all():
+        obs = env.reset().cpu().numpy()
+        for i, o in enumerate(oracles):
+            np.testing.assert_allclose(obs[i], o.reset(np.full((W, S), 6)), rtol=1e-5, atol=1e-6)
+    reset_all()
+    lost_any = False
+    for t in range(T):
+        if t == 9:
+            reset_all()
+        per_env = []
+        for i in range(E):
+            if i == 1 or (i == 3 and t % 2):
+                per_env.append([])
+                continue
+            orders = []
+            for _ in range(int(rng.integers(max_orders // 2, max_orders + 1))):
+                q = np.where(rng.random(S) < 0.3, rng.integers(1, 12, S), 0)
+                if rng.random() < 0.1:
+                    q[:] = 0
+                orders.append((int(rng.integers(0, R)), q.astype(float)))
+            per_env.append(orders)
+        batch = pack_orders(per_env, S)
+        assert batch.qty_bytes == 1
+        act = rng.uniform(-1, 1, (E, W, S)).astype(np.float32)
+        obs, rew, trunc = env.step(torch.from_numpy(act).cuda(), orders=batch)
+        inv, r, ob = env.inventory.cpu().numpy(), rew.cpu().numpy(), obs.cpu().numpy()
+        for i, o in enumerate(oracles):
+            out = o.step(act[i], per_env[i])
+            assert np.array_equal(inv[i], out["inventory"]), (t, i)
+            np.testing.assert_allclose(r[i], out["rewards"], rtol=1e-5, atol=1e-5, err_msg=f"rewards t={t} env={i}")
+            np.testing.assert_allclose(ob[i], out["obs_local"], rtol=1e-5, atol=2e-5, err_msg=f"obs t={t} env={i}")
+            assert bool(trunc) == bool(out["trunc"])
+            lost_any = lost_any or out["lost_orders"].sum() > 0
+    assert lost_any, "workload was meant to lose sales"
+    env.close()
+
+
+def test_device_obs_statistics_match_the_reference_estimator():
+    """compute_obs_statistics (reference: src/utils/obs_stats.py:11-168) on the device: its float64 column sums must
+    reproduce np.mean / np.std (the reference's estimator) of the very observations the same seeds produce, both per
+    column and grouped, and an environment normalised with them must come out standardised."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from marlsc_b200.rollout import compute_obs_statistics
+    from marlsc_b200.seeds import EXPERIMENT_SEEDS, SeedManager
+    cfg = environment_config_from_dict(small_default())
+    n_ep = 64
+    mean, std = compute_obs_statistics(cfg, SeedManager(root_seed=11, seed_registry=EXPERIMENT_SEEDS), n_episodes=n_ep)
+    gmean, gstd = compute_obs_statistics(cfg, SeedManager(root_seed=11, seed_registry=EXPERIMENT_SEEDS), mode="meanstd_grouped",
+                                         n_episodes=n_ep)
+    # the same loop by hand, observations kept
+    env_seed, action_seed = SeedManager(root_seed=11, seed_registry=EXPERIMENT_SEEDS).spawn_child_seeds("obs_stats", 2)
+    env = BatchedInventoryEnv(cfg, n_ep, device="cuda:0", host_samplers=False)
+    env.enable_device_demand(seed=int(env_seed))
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(int(action_seed))
+    rows = [env.reset().reshape(-1, env.obs_dim).cpu().numpy().copy()]
+    for _ in range(env.episode_length):
+        act = torch.rand((n_ep, 3, 2), device="cuda:0", generator=gen) * 2.0 - 1.0
+        rows.append(env.step(act)[0].reshape(-1, env.obs_dim).cpu().numpy().copy())
+    allobs = np.concatenate(rows).astype(np.float32)
+    assert allobs.shape[0] == n_ep * (cfg.episode_length + 1) * 3
+    np.testing.assert_allclose(mean, allobs.astype(np.float64).mean(0), rtol=1e-5, atol=1e-6)
+    ref_std = allobs.astype(np.float64).std(0)
+    np.testing.assert_allclose(std, np.where(ref_std < 1e-8, 1.0, ref_std), rtol=1e-4, atol=1e-6)
+    # grouped: inventory (2 SKU columns + aggregate), pipeline (3 x 2), rolling mean (2) for the default features
+    S, L = 2, env.max_expected_lead_time
+    assert gmean[0] == gmean[1] and gstd[0] == gstd[1]
+    np.testing.assert_allclose(gmean[0], allobs[:, :S].astype(np.float64).mean(), rtol=1e-5)
+    np.testing.assert_allclose(gstd[0], allobs[:, :S].astype(np.float64).std(), rtol=1e-4)
+    np.testing.assert_allclose(gmean[S], allobs[:, S].astype(np.float64).mean(), rtol=1e-5)          # the aggregate column
+    pipe = allobs[:, S + 1:S + 1 + L * S].astype(np.float64)
+    np.testing.assert_allclose(gmean[S + 1:S + 1 + L * S], pipe.mean(), rtol=1e-5)
+    np.testing.assert_allclose(gstd[S + 1:S + 1 + L * S], pipe.std(), rtol=1e-4)
+    env.close()
+    # an environment normalised with the statistics comes out standardised on the same trajectory
+    norm = BatchedInventoryEnv(cfg, n_ep, device="cuda:0", host_samplers=False,
+                               env_meta=dict(obs_normalization="meanstd_custom", obs_stats=(mean, std)))
+    norm.enable_device_demand(seed=int(env_seed))
+    gen.manual_seed(int(action_seed))
+    rows = [norm.reset().reshape(-1, norm.obs_dim).cpu().numpy().copy()]
+    for _ in range(norm.episode_length):
+        act = torch.rand((n_ep, 3, 2), device="cuda:0", generator=gen) * 2.0 - 1.0
+        rows.append(norm.step(act)[0].reshape(-1, norm.obs_dim).cpu().numpy().copy())
+    z = np.concatenate(rows).astype(np.float64)
+    live = ref_std >= 1e-8
+    assert np.abs(z.mean(0)[live]).max() < 1e-3 and np.abs(z.std(0)[live] - 1).max() < 1e-3
+    norm.close()

@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -x -q -k "device_demand or baseline or config1" 2>&1 | tail -3
-python tools/_exp_k4.py 2>&1 | tail -5
+python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -15
+python bench.py --workload ippo --steps 2 --warmup 2 2>/dev/null | cut -c1-330
+python bench.py --workload mappo --steps 2 --warmup 2 2>/dev/null | cut -c1-330
