@@ -10,7 +10,7 @@ namespace {
 template <int SPL, int NCH>
 int launch_tt(const LaunchArgs& a, const marlsc_step_io_t& io, double* cost_alloc, int t, cudaStream_t s) {
   using Cfg = AllocCfg<SPL>;
-  const AllocLayout l = alloc_layout(a.ds.W, a.ds.S, a.ds.R, NCH, Cfg::MW, Cfg::kPass);
+  const AllocLayout l = alloc_layout(a.ds.W, a.ds.S, a.ds.R, NCH, Cfg::MW, Cfg::kPass, SPL);
   const size_t smem = (size_t)l.t_bytes + 4 * (size_t)l.team_bytes;
   if ((int)smem > a.max_smem_optin) return 0;
   static thread_local size_t configured = 0;

@@ -40,7 +40,7 @@ struct AllocLayout {
   int lostP, inv, shipq, lostU, mask, reg, avail, team_bytes;  // per team, from the team's base
   int SP;                                                      // stock row stride
 };
-__host__ __device__ inline AllocLayout alloc_layout(int W, int S, int R, int nch, int MW, int kPass) {
+__host__ __device__ inline AllocLayout alloc_layout(int W, int S, int R, int nch, int MW, int kPass, int spl) {
   AllocLayout l;
   int o = 0;
   l.t_prio = o; o += (R * ((W + 3) & ~3) + 15) & ~15;
@@ -55,7 +55,7 @@ __host__ __device__ inline AllocLayout alloc_layout(int W, int S, int R, int nch
   l.lostU = o; o += R * 4;
   l.mask = o; o += MW * 32 * 4;
   l.reg = o; o += kPass * 2;
-  l.avail = o; o += ((S + 31) & ~31) * 2;
+  l.avail = o; o += 32 * spl * 2;                        // one entry per (lane, SKU slot), also the slots beyond S
   l.team_bytes = (o + 15) & ~15;
   return l;
 }
@@ -88,7 +88,7 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem[];
   const int W = sp.W, S = sp.S, R = sp.R, WS = W * S, Wp = (W + 3) & ~3;
-  const AllocLayout lay = alloc_layout(W, S, R, NCH, MW, kPass);
+  const AllocLayout lay = alloc_layout(W, S, R, NCH, MW, kPass, SPL);
   {  // per-CTA tables: warehouse priority per region (rows padded to whole words), availability -> priority-order
      // permutation, home-warehouse masks
     const int n_prio = (R * Wp) >> 2, n_perm = (R * NCH * 16) >> 1;

@@ -202,7 +202,7 @@ class BatchedInventoryEnv:
         dev = self.device
         self._dl = dict(seed=int(seed), step=0,
                         expected=torch.from_numpy(np.ascontiguousarray(self.expected_lead_times, dtype=np.int32)).to(dev),
-                        max_dev=torch.from_numpy(np.ascontiguousarray(md)).to(dev),
+                        max_dev=torch.from_numpy(np.array(md, dtype=np.int32)).to(dev),
                         actual=torch.zeros((self.num_envs, self.n_warehouses, self.n_skus), dtype=torch.uint8, device=dev))
 
     def sample_device_leads(self) -> torch.Tensor:

@@ -583,7 +583,7 @@ def test_cuda_edge_cases_vs_oracle(team):
     (3, 20, 5, "shipment", True, 9),       # one SKU per lane, one permutation chunk
     (7, 70, 9, "closest", False, 9),       # four SKUs per lane (ragged: S % 32 != 0), per-SKU penalties -> fp64 lost sums
     (10, 100, 50, "shipment", False, 80),  # the large shape; more than 64 orders in a step -> two mask passes
-    (16, 200, 70, "shipment", True, 12),   # eight SKUs per lane, four permutation chunks, R > 64 -> generic cost epilogue
+    (16, 200, 70, "shipment", True, 40),   # eight SKUs per lane, four permutation chunks, R > 64 -> generic cost epilogue
 ])
 def test_one_warp_split_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders):
     """The split step with one-warp teams (K1a / env_alloc_warp_kernel / K1c) against the oracle on shapes that reach every
