@@ -249,27 +249,37 @@ env_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ m
   const int32_t* ring_new = pinned(p.ring_q + (t % D) * WS);
   const int hist_n = imin(t + 1, kWindow);
   const int base = w * S;
-  const int32_t* hist_old[kWindow - 1];             // the older planes of the window, newest first
+  // Every load of the row is issued before any of them is consumed: one pointer per plane (this lane's first cell),
+  // the lane's other cells at constant offsets, predicates instead of branches. (Summing the window inside the
+  // load loop made each cell wait for its own loads - 7 in flight per lane instead of 28.)
+  const bool need_hist = sp.need_hist != 0;
+  const int32_t* const inv_l = p.inv + base + tm.gl;
+  const int32_t* const ring_l = ring_new + base + tm.gl;
+  const int32_t* hist_l[kWindow];                   // plane of step t, then the older planes, newest first
   MARLSC_UNROLL
-  for (int back = 1; back < kWindow; ++back) hist_old[back - 1] = p.hist + pmod(t - back, kWindow) * WS + base;
-  int vI[SPL], vdh[SPL], vz[SPL], vq[SPL], hsum[SPL];
+  for (int back = 0; back < kWindow; ++back)
+    hist_l[back] = need_hist ? p.hist + pmod(t - back, kWindow) * WS + base + tm.gl : nullptr;
+  bool own[SPL];
+  MARLSC_UNROLL
+  for (int j = 0; j < SPL; ++j) own[j] = tm.gl + G * j < S;
+  int vI[SPL], vdh[SPL], vz[SPL], vq[SPL], hsum[SPL], hv[SPL][kWindow - 1];
   float vrm[SPL], vf[SPL];
   MARLSC_UNROLL
-  for (int j = 0; j < SPL; ++j) {                   // loads first
-    const int s = tm.gl + G * j;
-    vI[j] = vdh[j] = vz[j] = vq[j] = hsum[j] = 0;
+  for (int j = 0; j < SPL; ++j) {
+    vz[j] = 0;
     vrm[j] = vf[j] = 0.f;
-    if (s < S) {
-      const int i = base + s;
-      vI[j] = p.inv[i];
-      vq[j] = ring_new[i];
-      if (sp.need_hist) {
-        vdh[j] = load_cg(&p.hist[(t % kWindow) * WS + i]);     // accumulated by K1b with fire-and-forget adds
-        MARLSC_UNROLL
-        for (int back = 1; back < kWindow; ++back)
-          if (back < hist_n) hsum[j] += hist_old[back - 1][s];
-      }
-    }
+    vI[j] = own[j] ? inv_l[G * j] : 0;
+    vq[j] = own[j] ? ring_l[G * j] : 0;
+    vdh[j] = own[j] && need_hist ? load_cg(hist_l[0] + G * j) : 0;   // accumulated by K1b with fire-and-forget adds
+    MARLSC_UNROLL
+    for (int back = 1; back < kWindow; ++back)
+      hv[j][back - 1] = own[j] && need_hist && back < hist_n ? hist_l[back][G * j] : 0;
+  }
+  MARLSC_UNROLL
+  for (int j = 0; j < SPL; ++j) {
+    hsum[j] = 0;
+    MARLSC_UNROLL
+    for (int back = 1; back < kWindow; ++back) hsum[j] += hv[j][back - 1];
   }
   double cost = 0.0;
   const bool by_row = sp.row_rates_uniform != 0;      // rates constant over the row: integer sums, three products
