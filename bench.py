@@ -485,7 +485,7 @@ def run_ours(args):
             # algorithmic bytes per env step of each launch (int32 state, fp32 obs), including what the split itself adds
             # (inventory and the home-demand plane pass through HBM between the kernels)
             parts = [("env_place_kernel (K1a)", 4 * WS * (2 * Lmax + 6), "hbm"),
-                     ("env_alloc_kernel (K1b)", 8 * WS + mean_orders * (S + 2) + 8 * W, "issue"),
+                     ("env_alloc_warp_kernel (K1b)", 8 * WS + mean_orders * (S + 2) + 8 * W, "issue"),
                      ("env_feature_kernel (K1c)", 4 * WS * 7 + 4 * W * (od - Lmax * S) + 8 * W, "hbm"),
                      ("env_reward_kernel (K1d)", 20 * W + 1, "latency")]
         else:
