@@ -211,10 +211,60 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
       }
       s_mask[wi * 32 + lane] = word;                  // read back by this lane only
     };
+    // Four SKUs per lane and rows that are whole aligned words: lane q reads WORD q of a row (SKUs 4q..4q+3, one
+    // coalesced load per order instead of four byte loads), packs the non-zero nibbles of eight orders into one
+    // register, and every lane fetches the four registers that hold its own SKUs (l + 32k lives in word l/4 + 8k,
+    // byte l%4) with shuffles. The home-demand adds are done by the lane that holds the bytes.
+    auto mask_word_w = [&](int wi, auto tail) {
+      constexpr bool kTail = decltype(tail)::value;
+      const uint32_t* rp = reinterpret_cast<const uint32_t*>(qty + (long long)p0 * S + (unsigned)(wi * OPW) * (unsigned)S) + lane;
+      const bool has_word = 4 * lane < S;
+      uint32_t x[OPW];
+#pragma unroll
+      for (int oo = 0; oo < OPW; ++oo) {
+        x[oo] = (has_word && (!kTail || wi * OPW + oo < pn)) ? *rp : 0u;
+        rp += S >> 2;
+      }
+      uint32_t packed = 0u;
+#pragma unroll
+      for (int oo = 0; oo < OPW; ++oo) {
+        const int j = wi * OPW + oo;
+        packed |= nonzero_nibble(x[oo]) << (oo * 4);
+        if ((home_orders >> j) & 1ull) {              // uniform: the region belongs to the order
+          uint32_t hm = t_hmask[s_reg[j]];
+          while (hm) {
+            const int w = lowest_bit(hm);
+            hm &= hm - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int v = (int)((x[oo] >> (8 * q)) & 0xffu);
+              if (v != 0) global_add(&dh_acc[w * S + 4 * lane + q], v);   // nobody waits for the sum
+            }
+          }
+        }
+      }
+      uint32_t word = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t pk = __shfl_sync(FULL, packed, (lane >> 2) + 8 * k);
+        word |= ((pk >> (lane & 3)) & 0x11111111u) << k;
+      }
+      s_mask[wi * 32 + lane] = word;
+    };
     const int nfull = pn / OPW;
+    bool by_words = false;
+    if constexpr (SPL == 4 && OPW == 8) by_words = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(io.order_qty) & 3u) == 0;
+    if (by_words) {
+      if constexpr (SPL == 4 && OPW == 8) {
 #pragma unroll 1
-    for (int wi = 0; wi < nfull; ++wi) mask_word(wi, std::false_type());
-    if (nfull < nw) mask_word(nfull, std::true_type());
+        for (int wi = 0; wi < nfull; ++wi) mask_word_w(wi, std::false_type());
+        if (nfull < nw) mask_word_w(nfull, std::true_type());
+      }
+    } else {
+#pragma unroll 1
+      for (int wi = 0; wi < nfull; ++wi) mask_word(wi, std::false_type());
+      if (nfull < nw) mask_word(nfull, std::true_type());
+    }
     // ---- chain pass --------------------------------------------------------------------------------
     const uint8_t* rows_l = rows;
     uint32_t a_mask = smem_addr(s_mask) + 4u * lane, a_reg = smem_addr(s_reg), a_avail = smem_addr(s_avail) + 2u * lane,
