@@ -1,3 +1,8 @@
+"""Timings of the on-device demand sampler (K4), the base-stock policy kernel (K5) and a step that draws its own
+demand, at the bench workload (large network, 65,536 envs).
+
+    python tools/sampler_timings.py       # on a B200
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np

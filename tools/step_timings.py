@@ -1,3 +1,9 @@
+"""Per-step timings of the split env step over one episode of the bench workload (large network, 65,536 envs,
+base-stock replay): whole step by CUDA events, then the library's per-launch events (K1a, K1b, K1c, K1d).
+Also the command the ncu captures of one steady-state launch use (--launch-skip 140).
+
+    python tools/step_timings.py          # on a B200
+"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
