@@ -86,4 +86,43 @@ int emu_env_step(void* h, const marlsc_env_state_t* st, const marlsc_step_io_t* 
   for (int64_t i = 0; i < st->num_envs; ++i) step_env<1, kEmuSpl, kCapsAll>(e->ds, e->tabs, tm, sc, *st, *io, i, t);
   return MARLSC_OK;
 }
+
+// The allocation as env_alloc.cuh runs it (one SKU column at a time: availability mask -> priority-order candidates
+// through DevSpec::prio_perm -> one shipment per candidate), restated for the host on the library's own tables.
+// inv [W,S] in/out, region [n], qty [n,S] one-byte rows, shipq [W,R] and lost_units [R] out (caller-zeroed).
+int emu_alloc_avail(void* h, int32_t* inv, int n_orders, const int16_t* region, const uint8_t* qty, int32_t* shipq,
+                    int32_t* lost_units) {
+  EmuEnv* e = static_cast<EmuEnv*>(h);
+  const DevSpec& ds = e->ds;
+  const int W = ds.W, S = ds.S, R = ds.R, Wp = (W + 3) & ~3, nc = ds.perm_chunks;
+  if (e->tb.prio_perm.empty()) {
+    g_err = "no permutation table (W > 16)";
+    return MARLSC_EUNSUPPORTED;
+  }
+  const uint16_t* perm = e->tb.prio_perm.data();
+  const uint8_t* prio = e->tb.prio.data();
+  for (int s = 0; s < S; ++s) {
+    uint32_t am = 0u;
+    for (int w = 0; w < W; ++w) am |= (inv[w * S + s] > 0 ? 1u : 0u) << w;
+    for (int j = 0; j < n_orders; ++j) {
+      int rem = qty[(size_t)j * S + s];
+      if (rem == 0) continue;
+      const int r = region[j];
+      uint32_t cand = 0u;
+      for (int c = 0; c < nc; ++c) cand |= perm[((size_t)r * nc + c) * 16 + ((am >> (4 * c)) & 15u)];
+      while (rem > 0 && cand != 0u) {
+        const int v = __builtin_ctz(cand);
+        cand &= cand - 1;
+        const int w = prio[r * Wp + v];
+        const int a = inv[w * S + s], f = rem < a ? rem : a;
+        inv[w * S + s] = a - f;
+        shipq[w * R + r] += f;
+        rem -= f;
+        if (a == f) am &= ~(1u << w);
+      }
+      if (rem > 0) lost_units[r] += rem;
+    }
+  }
+  return MARLSC_OK;
+}
 }

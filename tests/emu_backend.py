@@ -37,6 +37,7 @@ def emu_lib(lanes: bool = False):
     L.emu_env_reset.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.c_void_p, C.c_int, C.c_void_p]
     L.emu_env_step.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.POINTER(_capi.StepIOC), C.c_int]
     L.emu_env_step_lean.argtypes = [C.c_void_p, C.POINTER(_capi.EnvStateC), C.POINTER(_capi.StepIOC), C.c_int]
+    L.emu_alloc_avail.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emu_env_destroy.argtypes = [C.c_void_p]
     L.emu_env_destroy.restype = None
     for fn in ("emu_env_obs_dim", "emu_env_needs_history", "emu_env_needs_forecast"):
@@ -105,6 +106,19 @@ class EmuBatch:
         assert self.L.emu_env_step(self.h, C.byref(self.state), C.byref(io), t) == 0
         o["inventory"] = self.inv.copy()
         return o
+
+    def alloc_avail(self, inv: np.ndarray, region: np.ndarray, qty: np.ndarray):
+        """One environment's allocation the way env_alloc.cuh does it (availability masks + the library's permutation
+        table): returns (inventory after, shipped units [W,R], lost units [R])."""
+        inv = np.ascontiguousarray(inv, dtype=np.int32).copy()
+        region = np.ascontiguousarray(region, dtype=np.int16)
+        qty = np.ascontiguousarray(qty, dtype=np.uint8)
+        shipq = np.zeros((self.W, self.R), np.int32)
+        lost = np.zeros(self.R, np.int32)
+        rc = self.L.emu_alloc_avail(self.h, _p(inv), len(region), _p(region), _p(qty), _p(shipq), _p(lost))
+        if rc != 0:
+            raise ValueError(self.L.emu_last_error().decode())
+        return inv, shipq, lost
 
     def close(self):
         self.L.emu_env_destroy(self.h)
