@@ -1,4 +1,5 @@
 from .batched_env import BatchedInventoryEnv, DeviceOrders, HostRollout
 from .multi_env import InventoryEnvironment
+from .single_env import CentralizedEnvWrapper
 
-__all__ = ["BatchedInventoryEnv", "DeviceOrders", "HostRollout", "InventoryEnvironment"]
+__all__ = ["BatchedInventoryEnv", "CentralizedEnvWrapper", "DeviceOrders", "HostRollout", "InventoryEnvironment"]

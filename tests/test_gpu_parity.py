@@ -169,6 +169,25 @@ def test_dict_adapter_matches_reference():
         assert not any(term.values()) and not any(trunc.values())
 
 
+def test_centralized_wrapper_matches_reference_trajectory():
+    """CentralizedEnvWrapper (reference: src/environment/envs/single_env.py): global observation, flat joint action,
+    summed reward - against the same golden trajectory as the dict adapter."""
+    from marlsc_b200.envs import CentralizedEnvWrapper
+    g = Golden("small_default")
+    cfg, _ = spec_for(g)
+    env = CentralizedEnvWrapper(cfg, seed=int(g["env_seeds"][5]))
+    obs, info = env.reset()
+    assert obs.shape == env.observation_space.shape == (g.W * env._local_obs_dim,)
+    assert env.action_space.shape == (g.W * g.S,)
+    np.testing.assert_allclose(obs, g["obs0_local"][5].reshape(-1), rtol=1e-5, atol=1e-6)
+    for t in range(12):
+        obs, rew, term, trunc, info = env.step(g["actions"][5, t].reshape(-1))
+        np.testing.assert_allclose(obs, g["obs_local"][5, t].reshape(-1), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rew, g["rewards"][5, t].sum(), rtol=1e-5, atol=1e-6)
+        assert not term and not trunc
+    assert env.agents == ["warehouse_0", "warehouse_1", "warehouse_2"] and env.episode_length == cfg.episode_length
+
+
 def test_errors_are_loud():
     from marlsc_b200.envs import BatchedInventoryEnv
     g = Golden("small_default")
