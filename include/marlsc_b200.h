@@ -271,6 +271,19 @@ int marlsc_gae(const float* rewards, const float* values, const uint8_t* cut, co
 size_t marlsc_standardize_workspace_bytes(void);
 int marlsc_standardize(float* x, int64_t n, void* workspace, void* stream);
 
+/* K6 - PPO objective of one minibatch, forward and backward (RLlib PPOTorchLearner as the reference configures it,
+ * src/algorithms/ippo.py:145-160; hysteretic_beta < 0 disables the weighting of learners/hysteretic_learner.py:39-42):
+ *   L = -mean(min(ratio adv, clip(ratio, 1-c, 1+c) adv)) + vf_loss_coeff mean(min((value - target)^2, vf_clip_param))
+ * with ratio = exp(logp(actions | mean, max(log_std, logstd_floor)) - logp_old) of a diagonal Gaussian. All arrays on the
+ * device: mean, actions, grad_mean [n_samples, action_dim]; logp_old, adv, value, targets, grad_value [n_samples];
+ * log_std [action_dim]. Writes dL/dmean and dL/dvalue; sums (float64 [2 + action_dim], zeroed by the call) receives
+ * sum of the surrogate, sum of the clipped value loss, and dL/dlog_std. The entropy bonus only depends on log_std and is
+ * left to the caller. */
+int marlsc_ppo_loss(const float* mean, const float* actions, const float* log_std, float logstd_floor, const float* logp_old,
+                    const float* adv, const float* value, const float* targets, int64_t n_samples, int32_t action_dim,
+                    float clip_param, float vf_clip_param, float vf_loss_coeff, float hysteretic_beta, float* grad_mean,
+                    float* grad_value, double* sums, void* stream);
+
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char* marlsc_last_error(void);
 int32_t marlsc_abi_version(void);

@@ -121,6 +121,9 @@ def lib() -> C.CDLL:
     L.marlsc_policy_base_stock.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.marlsc_gae.restype = C.c_int
+    L.marlsc_ppo_loss.argtypes = [vp, vp, vp, C.c_float, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  vp, vp, vp, vp]
+    L.marlsc_ppo_loss.restype = C.c_int
     L.marlsc_standardize_workspace_bytes.argtypes = []
     L.marlsc_standardize_workspace_bytes.restype = C.c_size_t
     L.marlsc_standardize.argtypes = [vp, i64, vp, vp]

@@ -10,15 +10,54 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from .. import _capi
 from .collector import Rollout
 from .policy import ActorCritic
+
+
+class _FusedPPOObjective(torch.autograd.Function):
+    """Clipped surrogate + clipped value loss through K6 (``marlsc_ppo_loss``): one kernel computes the two loss terms and
+    the gradients with respect to the action means, ``log_std`` and the values; backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, mean, log_std, value, actions, logp_old, adv, targets, floor, clip, vf_clip, vf_coeff, beta):
+        S = mean.shape[-1]
+        mean_c, value_c = mean.contiguous(), value.contiguous()
+        n = value_c.numel()
+        if mean_c.numel() != n * S or mean_c.dtype != torch.float32 or not mean_c.is_cuda:
+            raise ValueError("mean must be a float32 CUDA tensor [..., S] matching value [...]")
+        args = [t.detach().to(torch.float32).contiguous() for t in (actions, logp_old, adv, targets)]
+        if args[0].numel() != n * S or any(a.numel() != n for a in args[1:]):
+            raise ValueError("actions / logp_old / adv / targets do not match the minibatch shape")
+        ls = log_std.detach().contiguous()
+        g_mean = torch.empty_like(mean_c)
+        g_value = torch.empty_like(value_c)
+        sums = torch.empty(2 + S, dtype=torch.float64, device=mean.device)
+        _capi.check(_capi.lib().marlsc_ppo_loss(
+            mean_c.data_ptr(), args[0].data_ptr(), ls.data_ptr(), float(floor), args[1].data_ptr(), args[2].data_ptr(),
+            value_c.data_ptr(), args[3].data_ptr(), n, S, float(clip), float(vf_clip), float(vf_coeff),
+            -1.0 if beta is None else float(beta), g_mean.data_ptr(), g_value.data_ptr(), sums.data_ptr(),
+            torch.cuda.current_stream(mean.device).cuda_stream))
+        g_ls = (sums[2:] * (ls >= floor)).to(torch.float32)          # clamp(min=floor) passes the gradient where it does not bind
+        ctx.save_for_backward(g_mean, g_ls, g_value)
+        ctx.shapes = (mean.shape, value.shape)
+        policy = (-sums[0] / n).to(torch.float32)
+        vf = (sums[1] / n).to(torch.float32)
+        return policy + vf_coeff * vf, policy, vf
+
+    @staticmethod
+    def backward(ctx, g, _gp, _gv):
+        g_mean, g_ls, g_value = ctx.saved_tensors
+        return (g_mean.reshape(ctx.shapes[0]) * g, g_ls * g, g_value.reshape(ctx.shapes[1]) * g) + (None,) * 9
 
 
 class PPOLearner:
     def __init__(self, policy: ActorCritic, lr: float = 5e-4, clip_param: float = 0.2, vf_clip_param: float = 10.0,
                  vf_loss_coeff: float = 1.0, entropy_coeff: float = 0.01, grad_clip: Optional[float] = None,
-                 hysteretic_beta: Optional[float] = None):
+                 hysteretic_beta: Optional[float] = None, fused_loss: Optional[bool] = None):
         self.policy = policy
+        # K6 on CUDA parameters unless asked otherwise; loss_reference() keeps the plain PyTorch form
+        self.fused = next(policy.parameters()).is_cuda if fused_loss is None else bool(fused_loss)
         self.opt = torch.optim.Adam(policy.parameters(), lr=lr)
         self.clip, self.vf_clip, self.vf_coeff, self.ent_coeff = clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff
         self.grad_clip, self.beta = grad_clip, hysteretic_beta
@@ -32,6 +71,16 @@ class PPOLearner:
                    entropy_coeff=sp.entropy_coeff, grad_clip=sp.grad_clip, hysteretic_beta=getattr(sp, "hysteretic_beta", None))
 
     def loss(self, obs, actions, logp_old, adv, targets) -> Dict[str, torch.Tensor]:
+        if not self.fused:
+            return self.loss_reference(obs, actions, logp_old, adv, targets)
+        pol = self.policy
+        partial, policy, vf = _FusedPPOObjective.apply(pol.action_mean(obs), pol.log_std, pol.value(obs), actions, logp_old, adv,
+                                                        targets, pol.logstd_floor, self.clip, self.vf_clip, self.vf_coeff, self.beta)
+        ent = pol.entropy()
+        return dict(total=partial - self.ent_coeff * ent, policy=policy.detach(), vf=vf.detach(), entropy=ent)
+
+    def loss_reference(self, obs, actions, logp_old, adv, targets) -> Dict[str, torch.Tensor]:
+        """The same objective in plain PyTorch (autograd): the numerical reference of K6."""
         pol = self.policy
         mean = pol.action_mean(obs)
         logp = pol.log_prob(mean, actions)

@@ -731,3 +731,38 @@ def test_device_obs_statistics_match_the_reference_estimator():
     live = ref_std >= 1e-8
     assert np.abs(z.mean(0)[live]).max() < 1e-3 and np.abs(z.std(0)[live] - 1).max() < 1e-3
     norm.close()
+
+
+@pytest.mark.parametrize("S,beta", [(2, None), (2, 0.4), (37, None)])
+def test_fused_ppo_loss_matches_pytorch(S, beta):
+    """K6 (marlsc_ppo_loss) against the same objective in plain PyTorch fp32 with autograd: loss terms and the
+    gradients of every parameter, with ratios on both sides of the clip range, advantages of both signs, value errors
+    beyond vf_clip and a log_std entry below its floor. rtol 1e-4 (fp32 sums in a different order)."""
+    from marlsc_b200.rollout import ActorCritic, PPOLearner
+    torch.manual_seed(3)
+    W, D, B = 3, 11, 700
+    pol = ActorCritic(D, W, S, actor_hidden=(32,), critic_hidden=(32,), logstd_floor=-1.0).cuda()
+    with torch.no_grad():
+        pol.log_std.copy_(torch.linspace(-1.5, 0.5, S))            # the first entries sit below the floor
+    obs = torch.randn(B, W, D, device="cuda")
+    with torch.no_grad():
+        mean = pol.action_mean(obs)
+        actions = mean + torch.randn_like(mean) * 0.8
+        logp_old = pol.log_prob(mean, actions) + torch.randn(B, W, device="cuda") * 0.3     # ratios well outside [0.8, 1.2] too
+        adv = torch.randn(B, W, device="cuda")
+        targets = pol.value(obs) + torch.randn(B, W, device="cuda") * 4.0                    # squared errors beyond vf_clip = 10
+    fused = PPOLearner(pol, hysteretic_beta=beta, fused_loss=True)
+    ref = PPOLearner(pol, hysteretic_beta=beta, fused_loss=False)
+    out_f = fused.loss(obs, actions, logp_old, adv, targets)
+    pol.zero_grad()
+    out_f["total"].backward()
+    g_f = [p.grad.clone() for p in pol.parameters()]
+    out_r = ref.loss(obs, actions, logp_old, adv, targets)
+    pol.zero_grad()
+    out_r["total"].backward()
+    g_r = [p.grad.clone() for p in pol.parameters()]
+    for k in ("total", "policy", "vf", "entropy"):
+        np.testing.assert_allclose(float(out_f[k].detach()), float(out_r[k].detach()), rtol=1e-4, atol=1e-6, err_msg=k)
+    assert float((pol.log_std.grad != 0).sum()) > 0
+    for (name, _), a, b in zip(pol.named_parameters(), g_f, g_r):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-6, err_msg=name)
