@@ -117,23 +117,28 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
   const int SP = lay.SP;
   const EnvPtrs p = env_ptrs(sp, st, e);
   const bool pen_uniform = sp.pen_uniform != 0;
+  // CSR (offsets) or padded layout (row e * stride, count[e]); the latter is what the device sampler writes. Read
+  // first: everything the mask pass loads hangs on these two values.
+  const long long o_begin = io.order_counts ? e * (long long)io.order_stride : (long long)io.order_offsets[e];
+  const int n_orders = io.order_counts ? io.order_counts[e] : io.order_offsets[e + 1] - (int)o_begin;
 
   // stock in: the environment's [W,S] block, row stride SP; bit w of a SKU's availability mask says warehouse w has it
   {
+    constexpr int kRows = SPL <= 4 ? 5 : 2;
     uint32_t av[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) av[k] = 0u;
-    for (int w0 = 0; w0 < W; w0 += 2) {
-      int v[2][SPL];
+    for (int w0 = 0; w0 < W; w0 += kRows) {              // kRows x SPL loads in flight per lane
+      int v[kRows][SPL];
 #pragma unroll
-      for (int d = 0; d < 2; ++d)
+      for (int d = 0; d < kRows; ++d)
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
           const int s = lane + 32 * k;
           v[d][k] = (w0 + d < W && s < S) ? p.inv[(w0 + d) * S + s] : 0;
         }
 #pragma unroll
-      for (int d = 0; d < 2; ++d)
+      for (int d = 0; d < kRows; ++d)
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
           const int s = lane + 32 * k;
@@ -150,9 +155,6 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
     s_lostP[i] = 0.0;
   }
 
-  // CSR (offsets) or padded layout (row e * stride, count[e]); the latter is what the device sampler writes
-  const long long o_begin = io.order_counts ? e * (long long)io.order_stride : (long long)io.order_offsets[e];
-  const int n_orders = io.order_counts ? io.order_counts[e] : io.order_offsets[e + 1] - (int)o_begin;
   const uint8_t* const qty = reinterpret_cast<const uint8_t*>(io.order_qty) + o_begin * S;
   const int16_t* const reg = io.order_region + o_begin;
   int32_t* const dh_acc = sp.dh_mode == 1 ? p.hist + (t % kWindow) * WS : nullptr;
