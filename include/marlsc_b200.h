@@ -254,6 +254,10 @@ int marlsc_lead_sample(int64_t num_envs, int32_t n_warehouses, int32_t n_skus, c
  * level: device float32 [W,S]; actions: device float32 [E,W,S]. Direct action space only. */
 int marlsc_policy_base_stock(marlsc_env_t* env, const marlsc_env_state_t* state, const float* level, int32_t t,
                              float* actions, void* stream);
+/* The same with one level per environment, level [E,W,S] (the rolling-mean "BS-Adaptive" heuristic,
+ * src/experiments/run_baselines.py:209-293, derives its levels from each environment's own demand history). */
+int marlsc_policy_base_stock_per_env(marlsc_env_t* env, const marlsc_env_state_t* state, const float* level, int32_t t,
+                                     float* actions, void* stream);
 
 /* Reverse-time GAE(lambda) / value-target scan over a rollout segment, one column per
  * (environment, agent). Replaces RLlib's GeneralAdvantageEstimation connector that the reference

@@ -119,6 +119,8 @@ def lib() -> C.CDLL:
     L.marlsc_lead_sample.restype = C.c_int
     L.marlsc_policy_base_stock.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
     L.marlsc_policy_base_stock.restype = C.c_int
+    L.marlsc_policy_base_stock_per_env.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
+    L.marlsc_policy_base_stock_per_env.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.marlsc_gae.restype = C.c_int
     L.marlsc_ppo_loss.argtypes = [vp, vp, vp, C.c_float, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,

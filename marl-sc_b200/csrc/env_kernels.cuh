@@ -152,8 +152,8 @@ int launch_reset_t(const LaunchArgs& a, const int32_t* init, int per_env, float*
 }
 
 // K5 launcher (samplers.cu)
-int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int t, float* actions,
-                      cudaStream_t s);
+int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int level_per_env, int t,
+                      float* actions, cudaStream_t s);
 
 // One pair of entry points per team width, defined in env_inst_g*.cu; spl selects the instantiation.
 #define MARLSC_DECLARE_G(G)                                                                                   \

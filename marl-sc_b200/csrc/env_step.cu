@@ -448,7 +448,18 @@ int marlsc_policy_base_stock(marlsc_env_t* env, const marlsc_env_state_t* state,
   if (env->ds.action_type != MARLSC_ACTION_DIRECT) return set_error(MARLSC_EINVAL, "the base-stock heuristic assumes the direct action space");
   if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
   MARLSC_CUDA(cudaSetDevice(env->device));
-  return launch_base_stock(env->ds, *state, level, t, actions, static_cast<cudaStream_t>(stream));
+  return launch_base_stock(env->ds, *state, level, 0, t, actions, static_cast<cudaStream_t>(stream));
+}
+
+int marlsc_policy_base_stock_per_env(marlsc_env_t* env, const marlsc_env_state_t* state, const float* level, int32_t t,
+                                     float* actions, void* stream) {
+  int rc = check_state(env, state);
+  if (rc) return rc;
+  if (!level || !actions) return set_error(MARLSC_EINVAL, "level and actions must not be NULL");
+  if (env->ds.action_type != MARLSC_ACTION_DIRECT) return set_error(MARLSC_EINVAL, "the base-stock heuristic assumes the direct action space");
+  if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
+  MARLSC_CUDA(cudaSetDevice(env->device));
+  return launch_base_stock(env->ds, *state, level, 1, t, actions, static_cast<cudaStream_t>(stream));
 }
 
 const char* marlsc_last_error(void) { return g_last_error.c_str(); }

@@ -217,7 +217,7 @@ sample_lead_kernel(const int32_t* __restrict__ expected, const int32_t* __restri
 template <typename IDX>
 __global__ void __launch_bounds__(256)
 base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
-                         const float* __restrict__ level, int t, float* __restrict__ actions) {
+                         const float* __restrict__ level, int level_per_env, int t, float* __restrict__ actions) {
   const IDX WS = (IDX)(sp.W * sp.S);
   const IDX idx = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;
   if (idx >= (IDX)st.num_envs * WS) return;
@@ -252,17 +252,17 @@ base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_consta
     }
   }
   const double mx = sp.action_max[i % sp.S];
-  double q = (double)level[i] - (double)st.inventory[idx] - (double)pending;
+  double q = (double)(level_per_env ? level[idx] : level[i]) - (double)st.inventory[idx] - (double)pending;
   q = q < 0.0 ? 0.0 : (q > mx ? mx : q);
   actions[idx] = (float)(2.0 * q / mx - 1.0);
 }
 
-int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int t, float* actions,
-                      cudaStream_t s) {
+int launch_base_stock(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int level_per_env, int t,
+                      float* actions, cudaStream_t s) {
   const long long n = st.num_envs * (long long)ds.W * ds.S;
   const unsigned grid = (unsigned)((n + 255) / 256);
-  if (n < (1LL << 32)) base_stock_policy_kernel<unsigned><<<grid, 256, 0, s>>>(ds, st, level, t, actions);
-  else base_stock_policy_kernel<long long><<<grid, 256, 0, s>>>(ds, st, level, t, actions);
+  if (n < (1LL << 32)) base_stock_policy_kernel<unsigned><<<grid, 256, 0, s>>>(ds, st, level, level_per_env, t, actions);
+  else base_stock_policy_kernel<long long><<<grid, 256, 0, s>>>(ds, st, level, level_per_env, t, actions);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;

@@ -224,11 +224,11 @@ class BatchedInventoryEnv:
         order up to ``level[w,s]`` given on-hand stock and units in transit, clipped to the order maximum."""
         E, W, S = self.num_envs, self.n_warehouses, self.n_skus
         lvl = level.to(device=self.device, dtype=torch.float32).contiguous()
-        if lvl.shape != (W, S):
-            raise ValueError(f"level must have shape {(W, S)}")
+        if lvl.shape not in ((W, S), (E, W, S)):
+            raise ValueError(f"level must have shape {(W, S)} (shared) or {(E, W, S)} (one per environment)")
         act = torch.empty((E, W, S), device=self.device) if out is None else out
-        _capi.check(_capi.lib().marlsc_policy_base_stock(self._h, C.byref(self._state), lvl.data_ptr(), self.timestep,
-                                                         act.data_ptr(), self._stream()))
+        fn = _capi.lib().marlsc_policy_base_stock if lvl.dim() == 2 else _capi.lib().marlsc_policy_base_stock_per_env
+        _capi.check(fn(self._h, C.byref(self._state), lvl.data_ptr(), self.timestep, act.data_ptr(), self._stream()))
         self._keep_level = lvl
         return act
 

@@ -766,3 +766,48 @@ def test_fused_ppo_loss_matches_pytorch(S, beta):
     assert float((pol.log_std.grad != 0).sum()) > 0
     for (name, _), a, b in zip(pol.named_parameters(), g_f, g_r):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-6, err_msg=name)
+
+
+def test_adaptive_constant_and_random_baselines_match_reference_formulas():
+    """BS-Adaptive / constant / random baselines (reference: src/experiments/run_baselines.py:73-293) for a batch of
+    environments against the reference formulas evaluated in NumPy on the same states."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from marlsc_b200.rollout import AdaptiveBaseStock, constant_actions, random_actions
+    cfg = environment_config_from_dict(small_default())
+    E, z, H = 37, 1.5, 4
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False)
+    env.enable_device_demand(seed=9)
+    env.reset()
+    pol = AdaptiveBaseStock(env, z, H)
+    lead = np.asarray(env.expected_lead_times, dtype=float)
+    mx = np.asarray(cfg.action_space.params.max_order_quantities, dtype=float)
+    hist = []
+    for t in range(12):
+        a = pol.actions().cpu().numpy()
+        if t > 0:
+            hist.append(env.demand_hist[:, (t - 1) % 5].cpu().numpy().astype(float))
+        if not hist:
+            assert np.all(a == -1.0)
+        else:
+            win = np.array(hist[-H:])
+            mean = win.mean(0)
+            var = win.var(0) if len(win) > 1 else mean.copy()
+            level = lead * mean + z * np.sqrt(lead * var)
+            ring = env.ring_qty.cpu().numpy()
+            pend = np.zeros_like(mean)
+            for k in range(1, int(lead.max()) + 1):          # orders placed at t - k still in transit when lead > k - 1 ... >= k
+                if t - k >= 0:
+                    pend += ring[:, (t - k) % env.ring_depth] * (lead >= k)[None]
+            qty = np.clip(level - env.inventory.cpu().numpy() - pend, 0.0, mx)
+            np.testing.assert_allclose(a, (2.0 * qty / mx - 1.0).astype(np.float32), rtol=1e-5, atol=2e-6, err_msg=f"t={t}")
+        env.step(torch.from_numpy(a).cuda())
+    c = constant_actions(env, np.array([[3.0, 500.0], [0.0, 7.0], [-2.0, 1.0]]))
+    exp = (2.0 * np.clip(np.array([[3.0, 500.0], [0.0, 7.0], [-2.0, 1.0]]), 0.0, mx) / mx - 1.0).astype(np.float32)
+    assert c.shape == (E, 3, 2) and np.array_equal(c[5].cpu().numpy(), exp)
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(1)
+    r = random_actions(env, g)
+    assert r.shape == (E, 3, 2) and float(r.min()) >= -1.0 and float(r.max()) < 1.0 and abs(float(r.mean())) < 0.2
+    env.close()
