@@ -228,11 +228,12 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
         rp += S >> 2;
       }
       uint32_t packed = 0u;
+      const uint32_t home_w = (uint32_t)(home_orders >> (wi * OPW)) & (OPW >= 32 ? 0xffffffffu : ((1u << (OPW & 31)) - 1u));   // this word's orders
 #pragma unroll
       for (int oo = 0; oo < OPW; ++oo) {
         const int j = wi * OPW + oo;
         packed |= nonzero_nibble(x[oo]) << (oo * 4);
-        if ((home_orders >> j) & 1ull) {              // uniform: the region belongs to the order
+        if (home_w & (1u << oo)) {                    // uniform: the region belongs to the order
           uint32_t hm = t_hmask[s_reg[j]];
           while (hm) {
             const int w = lowest_bit(hm);
@@ -334,7 +335,7 @@ env_alloc_warp_kernel(const __grid_constant__ DevSpec sp, const __grid_constant_
           rem = 0;
         }
       }
-      if (!__any_sync(FULL, rem > 0 || n_ok || a_mask != a_mask_end)) break;
+      if (!__any_sync(FULL, ((uint32_t)rem | (uint32_t)n_ok | (a_mask ^ a_mask_end)) != 0u)) break;
     }
     __syncwarp();
   }
