@@ -241,6 +241,11 @@ void marlsc_demand_destroy(marlsc_demand_t* d);
 int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t max_orders_per_env,
                          int32_t* order_counts, int16_t* order_region, uint8_t* order_qty, int32_t* overflow_flag, void* stream);
 
+/* Test hook: the Poisson inversion K4 uses, evaluated for n given (lambda, u) pairs (device float32 arrays):
+ * k_out[i] = the order count drawn from uniform u[i] at rate lambda[i] (tabulated == 0), or the quantity drawn through
+ * the tabulated-CDF search the per-SKU quantities use (tabulated != 0; synchronises the stream). */
+int marlsc_poisson_inverse(const float* lambda, const float* u, int64_t n, int32_t tabulated, int32_t* k_out, void* stream);
+
 /* Device lead-time sampler: the distribution of the reference's StochasticLeadTimeSampler.sample
  * (src/environment/components/lead_time_sampler.py:169-197): actual = max(1, expected[w,s] + U{-d[s]..+d[s]}),
  * independently per environment, warehouse, SKU and step (the reference also draws every step). expected_lead
@@ -277,16 +282,20 @@ int marlsc_standardize(float* x, int64_t n, void* workspace, void* stream);
 
 /* K6 - PPO objective of one minibatch, forward and backward (RLlib PPOTorchLearner as the reference configures it,
  * src/algorithms/ippo.py:145-160; hysteretic_beta < 0 disables the weighting of learners/hysteretic_learner.py:39-42):
- *   L = -mean(min(ratio adv, clip(ratio, 1-c, 1+c) adv)) + vf_loss_coeff mean(min((value - target)^2, vf_clip_param))
- * with ratio = exp(logp(actions | mean, max(log_std, logstd_floor)) - logp_old) of a diagonal Gaussian. All arrays on the
- * device: mean, actions, grad_mean [n_samples, action_dim]; logp_old, adv, value, targets, grad_value [n_samples];
- * log_std [action_dim]. Writes dL/dmean and dL/dvalue; sums (float64 [2 + action_dim], zeroed by the call) receives
- * sum of the surrogate, sum of the clipped value loss, and dL/dlog_std. The entropy bonus only depends on log_std and is
- * left to the caller. */
-int marlsc_ppo_loss(const float* mean, const float* actions, const float* log_std, float logstd_floor, const float* logp_old,
-                    const float* adv, const float* value, const float* targets, int64_t n_samples, int32_t action_dim,
-                    float clip_param, float vf_clip_param, float vf_loss_coeff, float hysteretic_beta, float* grad_mean,
-                    float* grad_value, double* sums, void* stream);
+ *   L_p = -mean_p(min(ratio adv, clip(ratio, 1-c, 1+c) adv)) + vf_loss_coeff mean_p(min((value - target)^2, vf_clip_param))
+ *         + kl_coeff mean_p(KL(old || new))                 (use_kl_loss, ippo.py:146; skipped when mean_old is NULL)
+ * with ratio = exp(logp(actions | mean, max(log_std_p, logstd_floor)) - logp_old) of a diagonal Gaussian, summed over the
+ * n_policies policies: 1 with parameter sharing (ippo.py:106-110), else one per warehouse (ippo.py:111-115) with sample i
+ * belonging to policy i % n_policies, each policy averaging over its own samples. All arrays on the device: mean, actions,
+ * mean_old, grad_mean [n_samples, action_dim]; logp_old, adv, value, targets, grad_value [n_samples]; log_std,
+ * log_std_old (already floored) [n_policies, action_dim]. Writes dL/dmean and dL/dvalue; sums (float64
+ * [n_policies, 3 + action_dim], zeroed by the call) receives per policy the sum of the surrogate, of the clipped value
+ * loss, of the KL term, and dL/dlog_std. The entropy bonus only depends on log_std and is left to the caller. */
+int marlsc_ppo_loss(const float* mean, const float* actions, const float* log_std, int32_t n_policies, float logstd_floor,
+                    const float* logp_old, const float* adv, const float* value, const float* targets, const float* mean_old,
+                    const float* log_std_old, float kl_coeff, int64_t n_samples, int32_t action_dim, float clip_param,
+                    float vf_clip_param, float vf_loss_coeff, float hysteretic_beta, float* grad_mean, float* grad_value,
+                    double* sums, void* stream);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char* marlsc_last_error(void);

@@ -115,6 +115,8 @@ def lib() -> C.CDLL:
     L.marlsc_demand_destroy.restype = None
     L.marlsc_demand_sample.argtypes = [vp, i64, C.c_uint64, i64, i32, vp, vp, vp, vp, vp]
     L.marlsc_demand_sample.restype = C.c_int
+    L.marlsc_poisson_inverse.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.marlsc_poisson_inverse.restype = C.c_int
     L.marlsc_lead_sample.argtypes = [i64, i32, i32, vp, vp, C.c_uint64, i64, vp, vp]
     L.marlsc_lead_sample.restype = C.c_int
     L.marlsc_policy_base_stock.argtypes = [vp, C.POINTER(EnvStateC), vp, i32, vp, vp]
@@ -123,8 +125,8 @@ def lib() -> C.CDLL:
     L.marlsc_policy_base_stock_per_env.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.marlsc_gae.restype = C.c_int
-    L.marlsc_ppo_loss.argtypes = [vp, vp, vp, C.c_float, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
-                                  vp, vp, vp, vp]
+    L.marlsc_ppo_loss.argtypes = [vp, vp, vp, i32, C.c_float, vp, vp, vp, vp, vp, vp, C.c_float, i64, i32, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, vp, vp, vp, vp]
     L.marlsc_ppo_loss.restype = C.c_int
     L.marlsc_standardize_workspace_bytes.argtypes = []
     L.marlsc_standardize_workspace_bytes.restype = C.c_size_t

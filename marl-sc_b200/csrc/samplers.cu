@@ -12,6 +12,7 @@
 // K5 evaluates the reference's base-stock heuristic (src/experiments/run_baselines.py:133-207) for every
 // environment: qty = clip(S[w,k] - on_hand - in_transit, 0, max_qty), action = 2 qty / max_qty - 1 (float32).
 #include <cmath>
+#include <vector>
 
 #include "env_kernels.cuh"
 
@@ -42,12 +43,17 @@ __device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 167
 __device__ __forceinline__ int poisson_from(float lambda, float u, float u2) {
   if (lambda <= 0.f) return 0;
   if (lambda < 30.f) {
+    // float32 running sum: in the far tail the terms drop below half an ulp of F and the sum plateaus a few ulp
+    // short of 1 (2-3 x 2^-24 for lambda = 1, 3, 5), below the largest uniform 1 - 2^-24 - the search then has to stop
+    // where the sum stops growing instead of running on to the cap.
     float p = __expf(-lambda), F = p;
     int k = 0;
     while (u > F && k < 200) {
       ++k;
       p *= lambda / (float)k;
-      F += p;
+      const float Fn = F + p;
+      if (Fn == F && (float)k > lambda) break;
+      F = Fn;
     }
     return k;
   }
@@ -78,10 +84,20 @@ __device__ __forceinline__ int quantity_from(const float* __restrict__ cdf, floa
     while (u > F && k < 200) {
       ++k;
       p *= lambda / (float)k;
-      F += p;
+      const float Fn = F + p;
+      if (Fn == F) break;                               // the float32 sum has stopped growing (see poisson_from)
+      F = Fn;
     }
   }
   return k;
+}
+
+// test hook: the inversions K4 uses, for given (lambda, u) pairs
+__global__ void poisson_inverse_kernel(const float* __restrict__ lambda, const float* __restrict__ u, long long n,
+                                       const float* __restrict__ cdf, int32_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = cdf ? quantity_from(cdf + i * kCdf, lambda[i], u[i], 0.5f) : poisson_from(lambda[i], u[i], 0.5f);
 }
 
 // one warp per environment
@@ -349,6 +365,38 @@ int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, in
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+int marlsc_poisson_inverse(const float* lambda, const float* u, int64_t n, int32_t tabulated, int32_t* k_out, void* stream) {
+  if (!lambda || !u || !k_out || n < 1) return set_error(MARLSC_EINVAL, "null argument or n < 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* cdf = nullptr;
+  if (tabulated) {   // the table marlsc_demand_create builds, for these rates
+    std::vector<float> hl((size_t)n), hc((size_t)n * kCdf);
+    MARLSC_CUDA(cudaMemcpyAsync(hl.data(), lambda, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    MARLSC_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; ++i) {
+      const double lam = (double)hl[i];
+      double pk = std::exp(-lam), F = pk;
+      for (int k = 0; k < kCdf; ++k) {
+        if (k > 0) {
+          pk *= lam / k;
+          F += pk;
+        }
+        hc[i * kCdf + k] = (float)F;
+      }
+    }
+    MARLSC_CUDA(cudaMalloc(&cdf, hc.size() * sizeof(float)));
+    MARLSC_CUDA(cudaMemcpyAsync(cdf, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  poisson_inverse_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(lambda, u, n, cdf, k_out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  if (cdf) {
+    MARLSC_CUDA(cudaStreamSynchronize(s));
+    MARLSC_CUDA(cudaFree(cdf));
+  }
   return MARLSC_OK;
 }
 

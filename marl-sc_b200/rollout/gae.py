@@ -64,3 +64,15 @@ def standardize_(x: torch.Tensor) -> torch.Tensor:
         ws = _ws[x.device] = torch.zeros(max(16, int(L.marlsc_standardize_workspace_bytes())), dtype=torch.uint8, device=x.device)
     _capi.check(L.marlsc_standardize(x.data_ptr(), x.numel(), ws.data_ptr(), _stream(x)))
     return x
+
+
+def standardize_columns_(x: torch.Tensor, n_columns: int) -> torch.Tensor:
+    """In place ``(x - mean_c) / max(1e-4, std_c)`` per last-axis column c (one column per independent policy:
+    RLlib standardises the advantages of every module's batch on their own)."""
+    if x.shape[-1] != n_columns:
+        raise ValueError("the last axis must be the policy axis")
+    flat = x.view(-1, n_columns)
+    mean = flat.mean(0)
+    std = flat.std(0, unbiased=False).clamp_min(1e-4)
+    flat.sub_(mean).div_(std)
+    return x

@@ -6,12 +6,18 @@ Mirrors what the reference's ``ActorCriticRLModule`` does for its shipped IPPO /
 action means, a state-independent ``log_std`` parameter clamped from below, and an MLP critic on the
 local observation (IPPO) or on ``[local_i | global]`` (MAPPO, ``critic_obs_type: global``).
 
+``parameter_sharing`` follows src/algorithms/ippo.py:106-115: with sharing every warehouse runs the same
+module (and the env prepends a one-hot warehouse id, ippo.py:70); without it every warehouse owns an
+independent module - here one set of stacked weights ``[W, in, out]`` evaluated with a batched GEMM, so the
+W policies still run as one kernel per layer.
+
 The centralised critic never materialises the W-times duplicated ``[local_i | global]`` vector: its first
 layer is split into a local and a global block, ``W1 [local|global]^T = Wl local_i^T + Wg global^T``,
 and the global term is computed once per environment.
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -34,6 +40,42 @@ def mlp(in_dim: int, hidden: Sequence[int], out_dim: int, activation: str = "rel
     return nn.Sequential(*layers)
 
 
+class StackedLinear(nn.Module):
+    """P independent ``nn.Linear(in, out)`` layers evaluated together: x ``[..., P, in]`` -> ``[..., P, out]``.
+    Initialised like P separate ``nn.Linear`` modules."""
+
+    def __init__(self, n: int, in_dim: int, out_dim: int):
+        super().__init__()
+        self.n, self.in_features, self.out_features = n, in_dim, out_dim
+        self.weight = nn.Parameter(torch.empty(n, in_dim, out_dim))
+        self.bias = nn.Parameter(torch.empty(n, 1, out_dim))
+        bound = 1.0 / math.sqrt(in_dim)
+        for p in range(n):
+            w = torch.empty(out_dim, in_dim)
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+            self.weight.data[p] = w.t()
+            nn.init.uniform_(self.bias.data[p], -bound, bound)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-2]
+        h = x.reshape(-1, self.n, self.in_features).transpose(0, 1)          # [P, B, in]
+        out = torch.baddbmm(self.bias, h, self.weight).transpose(0, 1)       # [B, P, out]
+        return out.reshape(*lead, self.n, self.out_features)
+
+
+def stacked_mlp(n: int, in_dim: int, hidden: Sequence[int], out_dim: int, activation: str = "relu",
+                output_activation: Optional[str] = None) -> nn.Sequential:
+    layers: List[nn.Module] = []
+    d = in_dim
+    for h in hidden:
+        layers += [StackedLinear(n, d, h), _ACT[activation]()]
+        d = h
+    layers.append(StackedLinear(n, d, out_dim))
+    if output_activation:
+        layers.append(_ACT[output_activation]())
+    return nn.Sequential(*layers)
+
+
 def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """``seq(x)`` for an :func:`mlp`; without autograd on a CUDA tensor a Linear followed by ReLU runs as one
     cuBLASLt GEMM with the bias and the ReLU in its epilogue, so the hidden activations (800 MB per MLP at
@@ -43,6 +85,8 @@ def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     lead = x.shape[:-1]
     h = x.reshape(-1, x.shape[-1])
     mods = list(seq)
+    if any(isinstance(m, StackedLinear) for m in mods):
+        return seq(x)
     i = 0
     while i < len(mods):
         m = mods[i]
@@ -58,45 +102,66 @@ def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
 class ActorCritic(nn.Module):
     def __init__(self, local_obs_dim: int, n_warehouses: int, action_dim: int, actor_hidden: Sequence[int] = (256,),
                  critic_hidden: Sequence[int] = (256,), activation: str = "relu", critic_obs_type: str = "local",
-                 logstd_init: float = 0.0, logstd_floor: float = -2.0):
+                 logstd_init: float = 0.0, logstd_floor: float = -2.0, parameter_sharing: bool = True):
         super().__init__()
         self.local_obs_dim, self.n_warehouses, self.action_dim = local_obs_dim, n_warehouses, action_dim
         self.critic_obs_type = critic_obs_type
         self.logstd_floor = float(logstd_floor)
-        self.actor = mlp(local_obs_dim, actor_hidden, action_dim, activation)
-        self.log_std = nn.Parameter(torch.full((action_dim,), float(logstd_init)))
+        self.parameter_sharing = bool(parameter_sharing)
+        self.n_policies = 1 if self.parameter_sharing else n_warehouses
         crit_in = local_obs_dim * (1 + n_warehouses) if critic_obs_type == "global" else local_obs_dim
-        self.critic = mlp(crit_in, critic_hidden, 1, activation)
+        if self.parameter_sharing:
+            self.actor = mlp(local_obs_dim, actor_hidden, action_dim, activation)
+            self.log_std = nn.Parameter(torch.full((action_dim,), float(logstd_init)))
+            self.critic = mlp(crit_in, critic_hidden, 1, activation)
+        else:
+            W = n_warehouses
+            self.actor = stacked_mlp(W, local_obs_dim, actor_hidden, action_dim, activation)
+            self.log_std = nn.Parameter(torch.full((W, action_dim), float(logstd_init)))
+            self.critic = stacked_mlp(W, crit_in, critic_hidden, 1, activation)
 
     @classmethod
     def from_algorithm_config(cls, algo_config, local_obs_dim: int, n_warehouses: int, action_dim: int) -> "ActorCritic":
+        """``local_obs_dim`` must include the one-hot warehouse id when ``parameter_sharing`` is on: the reference
+        turns ``include_warehouse_id`` on with it (ippo.py:70, mappo.py:67) - build the env with
+        ``env_meta_from_algorithm_config(algo_config)``."""
         sp = algo_config.algorithm_specific
         net = sp.networks
         return cls(local_obs_dim, n_warehouses, action_dim, actor_hidden=net.actor.config.hidden_sizes,
                    critic_hidden=net.critic.config.hidden_sizes, activation=net.actor.config.activation,
                    critic_obs_type=getattr(sp, "critic_obs_type", "local"), logstd_init=sp.logstd_init,
-                   logstd_floor=sp.logstd_floor)
+                   logstd_floor=sp.logstd_floor, parameter_sharing=bool(getattr(sp, "parameter_sharing", False)))
 
     # obs: [E, W, D] local observations (flattened over W this is the global state)
     def action_mean(self, obs: torch.Tensor) -> torch.Tensor:
         return forward_mlp(self.actor, obs)
 
+    def clamped_log_std(self) -> torch.Tensor:
+        return torch.clamp(self.log_std, min=self.logstd_floor)
+
     def std(self) -> torch.Tensor:
-        return torch.clamp(self.log_std, min=self.logstd_floor).exp()
+        return self.clamped_log_std().exp()
 
     def value(self, obs: torch.Tensor) -> torch.Tensor:
         if self.critic_obs_type != "global":
             return forward_mlp(self.critic, obs).squeeze(-1)
         E, W, D = obs.shape
-        first: nn.Linear = self.critic[0]
-        wl, wg = first.weight[:, :D], first.weight[:, D:]
-        h = obs @ wl.t() + (obs.reshape(E, W * D) @ wg.t()).unsqueeze(1) + first.bias
+        first = self.critic[0]
+        if self.parameter_sharing:
+            wl, wg = first.weight[:, :D], first.weight[:, D:]
+            h = obs @ wl.t() + (obs.reshape(E, W * D) @ wg.t()).unsqueeze(1) + first.bias
+        else:
+            wl, wg = first.weight[:, :D], first.weight[:, D:]                      # [W, D, H], [W, W*D, H]
+            h = torch.baddbmm(first.bias, obs.transpose(0, 1), wl)                   # [W, E, H]
+            h = (h + torch.einsum("eg,wgh->weh", obs.reshape(E, W * D), wg)).transpose(0, 1)
         return forward_mlp(self.critic[1:], h).squeeze(-1)
 
-    def act(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None, deterministic: bool = False
-            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """(clipped action in [-1,1], log-prob of the unclipped sample, value) - RLlib samples the diagonal
-        Gaussian, stores its log-prob and clips the action it sends to the env (ippo.py:183-188)."""
+    def act(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None, deterministic: bool = False,
+            return_raw: bool = False):
+        """``(clipped action in [-1,1], log-prob of the unclipped sample, value)`` - RLlib samples the diagonal
+        Gaussian, stores the RAW sample and its log-prob in the batch and clips only the copy it sends to the env
+        (``clip_actions=True``, ippo.py:183-188). ``return_raw=True`` returns
+        ``(clipped, raw, logp, value, mean)`` so that a collector can store what the log-prob refers to."""
         mean = self.action_mean(obs)
         std = self.std()
         if deterministic:
@@ -104,12 +169,26 @@ class ActorCritic(nn.Module):
         else:
             raw = mean + std * torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
         logp = self.log_prob(mean, raw)
-        return raw.clamp(-1.0, 1.0), logp, self.value(obs)
+        clipped = raw.clamp(-1.0, 1.0)
+        if return_raw:
+            return clipped, raw, logp, self.value(obs), mean
+        return clipped, logp, self.value(obs)
 
     def log_prob(self, mean: torch.Tensor, raw_action: torch.Tensor) -> torch.Tensor:
-        log_std = torch.clamp(self.log_std, min=self.logstd_floor)
+        log_std = self.clamped_log_std()
         z = (raw_action - mean) / log_std.exp()
         return (-0.5 * z * z - log_std - 0.9189385332046727).sum(-1)
 
     def entropy(self) -> torch.Tensor:
-        return (torch.clamp(self.log_std, min=self.logstd_floor) + 1.4189385332046727).sum()
+        """Sum over policies of the per-policy Gaussian entropy (state independent)."""
+        return (self.clamped_log_std() + 1.4189385332046727).sum()
+
+
+def env_meta_from_algorithm_config(algo_config) -> dict:
+    """The ``env_meta`` keys the reference's algorithm wrappers derive from the algorithm config
+    (ippo.py:68-73, 121-142): parameter sharing switches the one-hot warehouse id on."""
+    sp = algo_config.algorithm_specific
+    meta = {"obs_normalization": getattr(sp, "obs_normalization", "off")}
+    if getattr(sp, "parameter_sharing", False):
+        meta["include_warehouse_id"] = True
+    return meta

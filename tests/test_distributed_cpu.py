@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the multi-GPU host logic: env sharding by rank and the learner's
-single flat gradient all-reduce (the only collective of the path)."""
+bucketed gradient all-reduce issued from the backward hooks (the only collective of the path)."""
 import os
 import socket
 
@@ -22,15 +22,27 @@ def _worker(rank, world, port, out):
     from marlsc_b200.rollout import ActorCritic, PPOLearner, shard_envs
     torch.manual_seed(0)                      # identical initial weights on every rank
     pol = ActorCritic(6, 3, 2, actor_hidden=(16,), critic_hidden=(16,))
-    learner = PPOLearner(pol, lr=1e-2)
+    # two buckets (bucket_bytes below the model size) so that the per-bucket path is exercised
+    learner = PPOLearner(pol, lr=1e-2, bucket_bytes=300)
+    assert len(learner.buckets.buckets) >= 2
     shard = shard_envs(10, rank, world)
     g = torch.Generator().manual_seed(100 + rank)            # different data per rank
     obs = torch.randn(len(shard), 3, 6, generator=g)
     act = torch.randn(len(shard), 3, 2, generator=g)
-    loss = learner.loss(obs, act, torch.zeros(len(shard), 3), torch.randn(len(shard), 3, generator=g),
-                        torch.randn(len(shard), 3, generator=g))["total"]
+    batch = (obs, act, torch.zeros(len(shard), 3), torch.randn(len(shard), 3, generator=g), torch.randn(len(shard), 3, generator=g))
+    # local gradient without any collective (a twin module with the same weights, no hooks)
+    twin = ActorCritic(6, 3, 2, actor_hidden=(16,), critic_hidden=(16,))
+    twin.load_state_dict(pol.state_dict())
+    ref = PPOLearner.__new__(PPOLearner)
+    ref.__dict__.update(policy=twin, fused=False, clip=learner.clip, vf_clip=learner.vf_clip, vf_coeff=learner.vf_coeff,
+                        ent_coeff=learner.ent_coeff, beta=None, use_kl=False, kl_coeff=0.0)
+    ref.loss(*batch)["total"].backward()
+    local = torch.cat([p.grad.reshape(-1) for p in twin.parameters()])
+    # the learner's own path: zero the buckets, backward (hooks launch one all-reduce per bucket), finish
+    learner.buckets.zero()
+    loss = learner.loss(*batch)["total"]
     loss.backward()
-    local = torch.cat([p.grad.reshape(-1) for p in learner.params]).clone()
+    learner.buckets.finish()
     nbytes = learner.all_reduce_grads()
     reduced = torch.cat([p.grad.reshape(-1) for p in learner.params])
     gathered = [torch.zeros_like(local) for _ in range(world)]

@@ -811,3 +811,96 @@ def test_adaptive_constant_and_random_baselines_match_reference_formulas():
     r = random_actions(env, g)
     assert r.shape == (E, 3, 2) and float(r.min()) >= -1.0 and float(r.max()) < 1.0 and abs(float(r.mean())) < 0.2
     env.close()
+
+
+@pytest.mark.gpu
+def test_fresh_rollout_has_ratio_one_and_zero_kl():
+    """The collector stores the RAW Gaussian sample the log-prob refers to and sends only its clipped copy to the env
+    (RLlib clip_actions=True, reference ippo.py:183-188): on the first minibatch of a fresh rollout the probability
+    ratio is exactly 1, so the surrogate equals -mean(advantages) and the KL term vanishes."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from marlsc_b200.rollout import ActorCritic, PPOLearner, RolloutCollector
+    cfg = environment_config_from_dict(small_default())
+    torch.manual_seed(0)
+    E, T = 64, 20
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", seed=3, env_meta=dict(include_warehouse_id=True))
+    pol = ActorCritic(env.obs_dim, 3, 2, actor_hidden=(32,), critic_hidden=(32,), logstd_init=0.0).cuda()   # std 1: ~32 % clipped
+    col = RolloutCollector(env, pol, T, seed=1, keep_dist_inputs=True)
+    ro = col.collect()
+    assert float((ro.actions.abs() > 1).float().mean()) > 0.1          # raw samples are kept
+    learner = PPOLearner(pol, use_kl_loss=True, fused_loss=True)
+    sl = (slice(0, 10), slice(0, 32))
+    out = learner.loss(ro.obs[sl].flatten(0, 1), ro.actions[sl].flatten(0, 1), ro.logp[sl].flatten(0, 1),
+                       ro.advantages[sl].flatten(0, 1), ro.targets[sl].flatten(0, 1), ro.mean_old[sl].flatten(0, 1), ro.log_std_old)
+    np.testing.assert_allclose(float(out["policy"]), -float(ro.advantages[sl].mean()), rtol=1e-4, atol=1e-5)
+    assert abs(float(out["kl"])) < 1e-5
+    stats = learner.update(ro, num_epochs=2, num_minibatches=4)
+    assert stats["minibatches"] == 8 and np.isfinite(stats["total"])
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sharing", [True, False])
+def test_fused_ppo_loss_with_kl_and_independent_policies(sharing):
+    """K6 with the KL penalty (use_kl_loss, reference mappo.yaml:21) and with one policy per warehouse
+    (parameter_sharing=False, ippo.py:111-115) against the same objective in plain PyTorch with autograd."""
+    from marlsc_b200.rollout import ActorCritic, PPOLearner
+    torch.manual_seed(5)
+    W, D, S, B = 3, 9, 4, 500
+    pol = ActorCritic(D, W, S, actor_hidden=(16,), critic_hidden=(16,), critic_obs_type="global", logstd_floor=-1.0,
+                      parameter_sharing=sharing).cuda()
+    with torch.no_grad():
+        pol.log_std.copy_(torch.linspace(-1.5, 0.5, pol.log_std.numel()).reshape(pol.log_std.shape))
+    obs = torch.randn(B, W, D, device="cuda")
+    with torch.no_grad():
+        mean = pol.action_mean(obs)
+        actions = mean + torch.randn_like(mean) * 0.8
+        logp_old = pol.log_prob(mean, actions) + torch.randn(B, W, device="cuda") * 0.3
+        adv = torch.randn(B, W, device="cuda")
+        targets = pol.value(obs) + torch.randn(B, W, device="cuda") * 4.0
+        mean_old = mean + 0.2 * torch.randn_like(mean)
+        ls_old = (pol.clamped_log_std() + 0.1 * torch.randn_like(pol.log_std)).reshape(pol.n_policies, S)
+    fused = PPOLearner(pol, fused_loss=True, use_kl_loss=True, kl_coeff=0.3)
+    ref = PPOLearner(pol, fused_loss=False, use_kl_loss=True, kl_coeff=0.3)
+    grads = []
+    outs = []
+    for lr_ in (fused, ref):
+        out = lr_.loss(obs, actions, logp_old, adv, targets, mean_old, ls_old)
+        pol.zero_grad()
+        out["total"].backward()
+        grads.append([p.grad.clone() for p in pol.parameters()])
+        outs.append(out)
+    for k in ("total", "policy", "vf", "entropy", "kl"):
+        np.testing.assert_allclose(float(outs[0][k].detach()), float(outs[1][k].detach()), rtol=1e-4, atol=1e-6, err_msg=k)
+    for (name, _), a, b in zip(pol.named_parameters(), grads[0], grads[1]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=name)
+
+
+@pytest.mark.gpu
+def test_poisson_inversion_survives_the_largest_uniform():
+    """The float32 CDF sum of the device Poisson inversion plateaus a few ulp below 1; with the largest 24-bit uniform
+    (1 - 2^-24) the search must stop where the sum stops growing, not run to its 200 cap (which used to hand a region
+    200 orders about once per 10^7 draws)."""
+    from marlsc_b200 import _capi
+    lam = torch.tensor([0.25, 1.0, 3.0, 5.0, 12.0, 29.0], device="cuda")
+    u = torch.full_like(lam, 1.0 - 2.0 ** -24)
+    for tab in (0, 1):
+        out = torch.zeros(lam.numel(), dtype=torch.int32, device="cuda")
+        _capi.check(_capi.lib().marlsc_poisson_inverse(lam.data_ptr(), u.data_ptr(), lam.numel(), tab, out.data_ptr(),
+                                                       torch.cuda.current_stream().cuda_stream))
+        k = out.cpu().numpy()
+        # far in the tail, but nowhere near the cap: P(X >= k) at these k is ~1e-7
+        bound = np.array([8, 12, 20, 25, 40, 70])
+        assert (k <= bound).all() and (k >= np.array([3, 6, 10, 14, 25, 50])).all(), (tab, k)
+    # and ordinary uniforms still invert exactly like the float64 CDF
+    from scipy.stats import poisson
+    g = torch.Generator(device="cuda").manual_seed(1)
+    lam2 = torch.tensor([1.0, 3.0, 5.0], device="cuda").repeat_interleave(4000)
+    u2 = torch.rand(lam2.numel(), device="cuda", generator=g) * 0.999
+    out = torch.zeros(lam2.numel(), dtype=torch.int32, device="cuda")
+    _capi.check(_capi.lib().marlsc_poisson_inverse(lam2.data_ptr(), u2.data_ptr(), lam2.numel(), 0, out.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
+    ref = poisson.ppf(u2.cpu().numpy().astype(np.float64), lam2.cpu().numpy().astype(np.float64))
+    assert (out.cpu().numpy() != ref).mean() < 2e-3        # only draws within float32 rounding of a CDF step differ

@@ -267,3 +267,87 @@ def test_shard_envs():
     parts = [shard_envs(10, r, 4) for r in range(4)]
     assert [len(p) for p in parts] == [3, 3, 2, 2]
     assert sorted(i for p in parts for i in p) == list(range(10))
+
+
+def test_independent_policies_equal_separate_modules():
+    """parameter_sharing=False (reference ippo.py:111-115): the stacked-weight module must equal W separate MLPs with
+    the same weights, the loss must be the sum of the per-policy mean losses, and grad_clip must act per policy."""
+    from marlsc_b200.rollout import ActorCritic, PPOLearner, mlp
+    torch.manual_seed(1)
+    W, D, S, B = 3, 7, 2, 41
+    pol = ActorCritic(D, W, S, actor_hidden=(8,), critic_hidden=(8,), critic_obs_type="global", parameter_sharing=False,
+                      logstd_floor=-3.0)
+    assert pol.n_policies == W and pol.log_std.shape == (W, S)
+    obs = torch.randn(B, W, D)
+    mean = pol.action_mean(obs)
+    val = pol.value(obs)
+    full = torch.cat([obs, obs.reshape(B, 1, W * D).expand(B, W, W * D)], dim=2)
+    for w in range(W):
+        a = mlp(D, (8,), S)
+        a[0].weight.data, a[0].bias.data = pol.actor[0].weight.data[w].t(), pol.actor[0].bias.data[w, 0]
+        a[2].weight.data, a[2].bias.data = pol.actor[2].weight.data[w].t(), pol.actor[2].bias.data[w, 0]
+        assert torch.allclose(a(obs[:, w]), mean[:, w], atol=1e-5)
+        c = mlp(D * (1 + W), (8,), 1)
+        c[0].weight.data, c[0].bias.data = pol.critic[0].weight.data[w].t(), pol.critic[0].bias.data[w, 0]
+        c[2].weight.data, c[2].bias.data = pol.critic[2].weight.data[w].t(), pol.critic[2].bias.data[w, 0]
+        assert torch.allclose(c(full[:, w]).squeeze(-1), val[:, w], atol=1e-5)
+    learner = PPOLearner(pol, fused_loss=False, grad_clip=0.05, use_kl_loss=True)
+    with torch.no_grad():
+        actions = mean + 0.5 * torch.randn_like(mean)
+        logp_old = pol.log_prob(mean, actions) + 0.2 * torch.randn(B, W)
+        mean_old = mean + 0.1 * torch.randn_like(mean)
+        ls_old = pol.clamped_log_std() - 0.1
+    adv, tgt = torch.randn(B, W), torch.randn(B, W)
+    out = learner.loss(obs, actions, logp_old, adv, tgt, mean_old, ls_old)
+    # per-policy pieces by hand
+    ratio = (pol.log_prob(mean, actions) - logp_old).exp()
+    surr = torch.minimum(ratio * adv, ratio.clamp(0.8, 1.2) * adv)
+    assert torch.allclose(out["policy"], -sum(surr[:, w].mean() for w in range(W)), atol=1e-6)
+    learner.buckets.zero()
+    out["total"].backward()
+    learner._clip()
+    for w in range(W):                                  # every policy's own gradient norm is clipped to 0.05
+        sq = sum(float(p.grad[w].pow(2).sum()) for p in learner.params)
+        assert sq ** 0.5 <= 0.05 * (1 + 1e-4)
+
+
+def test_learner_update_loop_and_kl_adaptation():
+    """num_epochs x num_minibatches with a fresh on-device permutation per epoch (reference ippo.py:149-152) on a
+    synthetic rollout; at the behaviour parameters the first minibatch has ratio 1 and KL 0."""
+    from marlsc_b200.rollout import ActorCritic, PPOLearner
+    from marlsc_b200.rollout.collector import Rollout
+    torch.manual_seed(2)
+    T, E, W, D, S = 6, 10, 3, 5, 2
+    pol = ActorCritic(D, W, S, actor_hidden=(8,), critic_hidden=(8,))
+    obs = torch.randn(T + 1, E, W, D)
+    with torch.no_grad():
+        act, raw, logp, val, mean = pol.act(obs[:T], return_raw=True)
+    assert float((raw - act).abs().max()) > 0          # some samples were clipped; the batch keeps the raw ones
+    ro = Rollout(obs, raw, logp, torch.randn(T, E, W), torch.randn(T + 1, E, W), torch.randn(T, E, W), torch.randn(T, E, W),
+                 torch.zeros(T, dtype=torch.uint8), mean, pol.clamped_log_std().detach().reshape(1, S).clone())
+    learner = PPOLearner(pol, lr=1e-3, fused_loss=False, use_kl_loss=True, num_epochs=3, num_minibatches=4, seed=1)
+    first = learner.loss(obs[:T].reshape(T * E, W, D), raw.reshape(T * E, W, S), logp.reshape(T * E, W),
+                         ro.advantages.reshape(T * E, W), ro.targets.reshape(T * E, W), mean.reshape(T * E, W, S), ro.log_std_old)
+    assert abs(float(first["kl"])) < 1e-6
+    assert torch.allclose(first["policy"], -ro.advantages.mean(), atol=1e-5)     # ratio == 1 everywhere
+    before = [p.detach().clone() for p in pol.parameters()]
+    stats = learner.update(ro)
+    assert stats["minibatches"] == 12 and np.isfinite(stats["total"])
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, pol.parameters()))
+    assert stats["kl_coeff"] in (0.1, 0.2, 0.30000000000000004)
+
+
+def test_running_meanstd_filter_and_column_standardisation():
+    from marlsc_b200.rollout import MeanStdFilter, standardize_columns_
+    torch.manual_seed(0)
+    flt = MeanStdFilter(4, "cpu")
+    chunks = [torch.randn(5, 3, 4) * 3 + 7 for _ in range(6)]
+    for c in chunks:
+        flt(c.clone())
+    allx = torch.cat(chunks).reshape(-1, 4).double()
+    assert torch.allclose(flt.mean, allx.mean(0), atol=1e-9)
+    assert torch.allclose(torch.sqrt(flt.m2 / (flt.count - 1)), allx.std(0), atol=1e-9)
+    x = torch.randn(7, 5, 3) * torch.tensor([1.0, 5.0, 0.0]) + torch.tensor([0.0, 2.0, 1.0])
+    standardize_columns_(x, 3)
+    assert torch.allclose(x.reshape(-1, 3).mean(0), torch.zeros(3), atol=1e-5)
+    assert torch.allclose(x.reshape(-1, 3).std(0, unbiased=False)[:2], torch.ones(2), atol=1e-4)
