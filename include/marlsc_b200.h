@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MARLSC_ABI_VERSION 1
+#define MARLSC_ABI_VERSION 2
 
 enum {
   MARLSC_OK = 0,
@@ -112,18 +112,40 @@ typedef struct marlsc_env_spec {
 typedef struct marlsc_env marlsc_env_t; /* opaque handle */
 
 /*
+ * State layouts. WIDE is the general one (every configuration). COMPACT stores the same state in the width the
+ * values need and indexes the in-transit ring by arrival time; it exists for the common configurations
+ * (marlsc_env_layout() tells which one a handle uses; marlsc_env_set_layout() can force WIDE before the first reset):
+ * fixed lead times, direct action space with order maxima <= 255, unit SKU weights, no outbound fixed costs, static
+ * warehouse priority, non-binding split limit, inventory / pipeline / home-demand / rolling-mean feature blocks,
+ * normalisation off or fixed mean-std, 32 < S <= 128 (even), W <= 16, R <= 64, L <= 16. The caller guarantees
+ * on-hand stock stays below 65536 (initial stock + episode_length * max order quantity bounds it).
+ */
+enum { MARLSC_LAYOUT_WIDE = 0, MARLSC_LAYOUT_COMPACT = 1 };
+
+/*
  * Struct-of-arrays state of E environments, all DEVICE pointers owned by the caller
  * (reference state: multi_env.py:175-186). Layout is env-major so one environment's slice of
  * every array is contiguous.
+ *                 WIDE                                              COMPACT
+ *   inventory    int32 [E,W,S]                                      uint16 [E,W,S]
+ *   ring_qty     int32 [E,D,W,S], order placed at step tau lives    uint8 [E,W,L,S], order ARRIVING at step a lives in
+ *                in plane tau % D (D = ring_depth)                  plane a % L of its warehouse row (L = max_expected_lead)
+ *   ring_lead    uint8 [E,D,W,S] actual lead of that order;         unused (NULL)
+ *                NULL when lead_mode is FIXED
+ *   demand_hist  int32 [E,5,W,S] home-region demand of the last     uint16 [E,5,W,S]
+ *                5 steps, plane t % 5; may be NULL when
+ *                marlsc_env_needs_history() == 0
+ *   forecast     float [E,W,S] EMA demand forecast; may be NULL     unused (NULL)
+ *                when marlsc_env_needs_forecast() == 0
  */
 typedef struct marlsc_env_state {
   int64_t num_envs;
-  int32_t* inventory;    /* [E,W,S] on-hand stock (integer valued float64 in the reference) */
-  int32_t* ring_qty;     /* [E,D,W,S] order placed at step tau lives in plane tau % D */
-  uint8_t* ring_lead;    /* [E,D,W,S] actual lead of that order; NULL when lead_mode is FIXED */
-  int32_t* demand_hist;  /* [E,5,W,S] home-region demand of the last 5 steps, plane t % 5; may be NULL
-                            when marlsc_env_needs_history() == 0 */
-  float* forecast;       /* [E,W,S] EMA demand forecast; may be NULL when marlsc_env_needs_forecast() == 0 */
+  void* inventory;
+  void* ring_qty;
+  uint8_t* ring_lead;
+  void* demand_hist;
+  float* forecast;
+  int32_t layout;        /* MARLSC_LAYOUT_*: must equal marlsc_env_layout() of the handle the state is used with */
 } marlsc_env_state_t;
 
 /*
@@ -155,6 +177,23 @@ typedef struct marlsc_step_io {
    * [e*order_stride, e*order_stride + order_counts[e]) of order_region / order_qty and order_offsets is ignored */
   const int32_t* order_counts;   /* [E] or NULL */
   int32_t order_stride;
+  /* Sparse demand ("lines"), the native input of the COMPACT layout: the non-zero (order, SKU) cells of the step's orders
+   * (region ids already mapped through region_map), regrouped into 32 streams per environment. Stream l holds the cells
+   * of SKUs s with s % 32 == l in the order the reference allocator meets them (order index ascending, then SKU); entry =
+   * quantity (1..255) | region << 8 | (s / 32) << 14, 0 = padding. Streams are stored round-major, lines[round][l], and an
+   * environment owns rounds [line_offsets[e], line_offsets[e+1]) - or, in the padded layout (line_counts != NULL),
+   * rounds [e*line_stride, e*line_stride + line_counts[e]). Streams shorter than the environment's round count are padded
+   * with 0 at their end. When lines != NULL the order_* fields are ignored; a COMPACT handle given dense orders converts
+   * them with marlsc_lines_from_orders into a library-owned buffer first. WIDE handles take dense orders only.
+   * Build lines on the host with marlsc_b200.demand.pack_lines, on the device with marlsc_lines_from_orders or
+   * marlsc_demand_sample_lines. */
+  const uint16_t* lines;         /* [n_rounds, 32] or NULL */
+  const int32_t* line_offsets;   /* [E+1] */
+  const int32_t* line_counts;    /* [E] or NULL */
+  int32_t line_stride;
+  /* Integer order quantities instead of float actions (direct action space, COMPACT layout): uint8 [E,W,S], the quantity
+   * itself (clipped to the SKU's maximum), a quarter of the bytes of `actions` for callers that decide in units. */
+  const uint8_t* action_qty;     /* [E,W,S] or NULL; replaces actions when set */
 } marlsc_step_io_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -178,6 +217,15 @@ int marlsc_env_set_generic(marlsc_env_t* env, int32_t on);
 /* Lean launches of teams of 8+ lanes run the step as four kernels (place / allocate / features / rewards, see
  * csrc/env_split.cuh); on != 0 keeps them in the single fused kernel (used for comparisons and by the tests). */
 int marlsc_env_set_fused(marlsc_env_t* env, int32_t on);
+/* State layout of this handle (MARLSC_LAYOUT_*): COMPACT when the configuration qualifies, else WIDE. */
+int32_t marlsc_env_layout(const marlsc_env_t* env);
+/* Force a layout before the state is allocated / first reset: MARLSC_LAYOUT_WIDE is always possible (needed for the
+ * diagnostic outputs, explicit team sizes and the generic / fused test switches); MARLSC_LAYOUT_COMPACT fails with
+ * MARLSC_EUNSUPPORTED when the configuration does not qualify. */
+int marlsc_env_set_layout(marlsc_env_t* env, int32_t layout);
+/* Rounds per environment of the library-owned line buffer a COMPACT handle converts dense orders into (default 128;
+ * a stream that needs more sets an overflow flag that fails the NEXT call on the handle). */
+int marlsc_env_set_line_stride(marlsc_env_t* env, int32_t rounds);
 /* Measurement aid: with on != 0 every marlsc_env_step records CUDA events on its stream around each kernel it
  * launches. marlsc_env_last_timing waits for the last timed step and writes the per-launch durations in
  * milliseconds (split step: place, allocate, features, rewards; fused step: one entry); returns how many, or a
@@ -240,6 +288,19 @@ void marlsc_demand_destroy(marlsc_demand_t* d);
  * max_orders_per_env are dropped and *overflow_flag (device int32, caller-zeroed) is set to 1. */
 int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t max_orders_per_env,
                          int32_t* order_counts, int16_t* order_region, uint8_t* order_qty, int32_t* overflow_flag, void* stream);
+
+/* The same draw written as lines (padded layout): lines [E*line_stride, 32], line_counts [E]; region ids are mapped
+ * through region_map (device int32 [n_regions], or NULL). Identical orders to marlsc_demand_sample for the same
+ * (seed, step). A stream longer than line_stride is cut and *overflow_flag set. S <= 128, n_regions (mapped) <= 64. */
+int marlsc_demand_sample_lines(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t line_stride,
+                               const int32_t* region_map, uint16_t* lines, int32_t* line_counts, int32_t* overflow_flag,
+                               void* stream);
+
+/* Dense orders (CSR or padded, as in marlsc_step_io) -> lines in the padded layout for a COMPACT handle: lines
+ * [E*line_stride, 32], line_counts [E] (device). Applies the handle's region_map. overflow_flag (device int32,
+ * caller-zeroed) is set when a stream needs more than line_stride rounds (the surplus is dropped). */
+int marlsc_lines_from_orders(marlsc_env_t* env, int64_t num_envs, const marlsc_step_io_t* orders, int32_t line_stride,
+                             uint16_t* lines, int32_t* line_counts, int32_t* overflow_flag, void* stream);
 
 /* Test hook: the Poisson inversion K4 uses, evaluated for n given (lambda, u) pairs (device float32 arrays):
  * k_out[i] = the order count drawn from uniform u[i] at rate lambda[i] (tabulated == 0), or the quantity drawn through

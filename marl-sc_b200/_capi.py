@@ -11,7 +11,8 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmarlsc_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
+LAYOUT_WIDE, LAYOUT_COMPACT = 0, 1
 
 # enums (include/marlsc_b200.h)
 ACTION = {"direct": 0, "demand_centered": 1, "base_stock": 2}
@@ -47,7 +48,7 @@ class EnvSpecC(C.Structure):
 
 class EnvStateC(C.Structure):
     _fields_ = [("num_envs", C.c_int64), ("inventory", C.c_void_p), ("ring_qty", C.c_void_p),
-                ("ring_lead", C.c_void_p), ("demand_hist", C.c_void_p), ("forecast", C.c_void_p)]
+                ("ring_lead", C.c_void_p), ("demand_hist", C.c_void_p), ("forecast", C.c_void_p), ("layout", C.c_int32)]
 
 
 class StepIOC(C.Structure):
@@ -56,7 +57,9 @@ class StepIOC(C.Structure):
                 ("rewards", C.c_void_p), ("obs", C.c_void_p), ("truncated", C.c_void_p),
                 ("cost_breakdown", C.c_void_p), ("d_ordered", C.c_void_p), ("d_ship", C.c_void_p),
                 ("d_ship_count", C.c_void_p), ("d_unfulfilled", C.c_void_p), ("d_lost_orders", C.c_void_p),
-                ("d_lost_sales", C.c_void_p), ("order_counts", C.c_void_p), ("order_stride", C.c_int32)]
+                ("d_lost_sales", C.c_void_p), ("order_counts", C.c_void_p), ("order_stride", C.c_int32),
+                ("lines", C.c_void_p), ("line_offsets", C.c_void_p), ("line_counts", C.c_void_p), ("line_stride", C.c_int32),
+                ("action_qty", C.c_void_p)]
 
 
 class HostStepC(C.Structure):
@@ -91,6 +94,16 @@ def lib() -> C.CDLL:
     for fn in ("marlsc_env_obs_dim", "marlsc_env_needs_history", "marlsc_env_needs_forecast", "marlsc_env_team_size"):
         getattr(L, fn).argtypes = [vp]
         getattr(L, fn).restype = i32
+    L.marlsc_env_layout.argtypes = [vp]
+    L.marlsc_env_layout.restype = i32
+    L.marlsc_env_set_layout.argtypes = [vp, i32]
+    L.marlsc_env_set_layout.restype = C.c_int
+    L.marlsc_env_set_line_stride.argtypes = [vp, i32]
+    L.marlsc_env_set_line_stride.restype = C.c_int
+    L.marlsc_lines_from_orders.argtypes = [vp, i64, C.POINTER(StepIOC), i32, vp, vp, vp, vp]
+    L.marlsc_lines_from_orders.restype = C.c_int
+    L.marlsc_demand_sample_lines.argtypes = [vp, i64, C.c_uint64, i64, i32, vp, vp, vp, vp, vp]
+    L.marlsc_demand_sample_lines.restype = C.c_int
     L.marlsc_env_set_team_size.argtypes = [vp, i32]
     L.marlsc_env_set_team_size.restype = C.c_int
     L.marlsc_env_set_generic.argtypes = [vp, i32]

@@ -115,6 +115,12 @@ struct DevSpec {
   const uint16_t* prio_perm;   // [R,perm_chunks,16] availability bits -> priority-order bits (W <= 16), else null
   int perm_chunks;
   int pen_uniform;             // every SKU has the same lost-sales penalty rate
+  // compact layout (env_compact.cu): five warehouse bits per lookup, priority rows padded to 16, home warehouse per region
+  const uint16_t* perm5;       // [R,perm5_chunks,32] availability bits -> priority-order bits (W <= 16), else null
+  const uint8_t* prio16;       // [R,16] warehouses in priority order
+  const uint8_t* home_wh;      // [R] the warehouse whose home region r is; 255 none, 254 several (see home_mask)
+  int perm5_chunks;
+  int compact_ok;              // the configuration fits the compact state layout and its fused kernel
   int row_rates_uniform;       // holding / weight / inbound rates do not vary over the SKUs of a warehouse
   const float* obs_mean;
   const float* obs_std;        // holds 1/std (precomputed on the host in float32)
@@ -289,10 +295,10 @@ struct EnvPtrs {
 MDEV EnvPtrs env_ptrs(const DevSpec& sp, const marlsc_env_state_t& st, int64_t e) {
   const int64_t ws = (int64_t)sp.W * sp.S;
   EnvPtrs p;
-  p.inv = pinned(st.inventory + e * ws);
-  p.ring_q = pinned(st.ring_qty + e * ws * sp.D);
+  p.inv = pinned(static_cast<int32_t*>(st.inventory) + e * ws);
+  p.ring_q = pinned(static_cast<int32_t*>(st.ring_qty) + e * ws * sp.D);
   p.ring_l = st.ring_lead ? pinned(st.ring_lead + e * ws * sp.D) : nullptr;
-  p.hist = st.demand_hist ? pinned(st.demand_hist + e * ws * kWindow) : nullptr;
+  p.hist = st.demand_hist ? pinned(static_cast<int32_t*>(st.demand_hist) + e * ws * kWindow) : nullptr;
   p.fcst = st.forecast ? pinned(st.forecast + e * ws) : nullptr;
   return p;
 }

@@ -7,6 +7,7 @@
 #include <new>
 #include <string>
 
+#include "env_compact.cuh"
 #include "env_split.cuh"
 
 namespace marlsc {
@@ -56,6 +57,13 @@ struct marlsc_env {
   int timing = 0;              // marlsc_env_set_timing: events around the launches of a step
   int timed_launches = 0;      // launches the last timed step made (4 split, 1 fused)
   cudaEvent_t marks[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int layout = MARLSC_LAYOUT_WIDE;     // state layout this handle works on (marlsc_env_layout)
+  int line_stride = 128;               // rounds per environment of the library-owned line buffer (dense orders on a compact handle)
+  uint16_t* d_lines = nullptr;         // [line_envs * line_stride, 32]
+  int32_t* d_line_counts = nullptr;    // [line_envs]
+  int64_t line_envs = 0;
+  int32_t* h_overflow = nullptr;       // mapped host flag the conversion kernel sets when a stream does not fit
+  int32_t* d_overflow = nullptr;       // its device alias
   cudaStream_t copy_stream = nullptr;        // marlsc_env_rollout_host: H2D copies of the next step
   cudaEvent_t ready[2] = {nullptr, nullptr};  // staging set filled
   cudaEvent_t done[2] = {nullptr, nullptr};   // staging set consumed by its step kernel
@@ -151,8 +159,47 @@ bool split_ok(const marlsc_env* env) {
   return ((g == 8 || g == 16) && (k == 1 || k == 4)) || (g == 32 && (k == 1 || k == 4 || k == 8 || k == 16)) || g == 64;
 }
 
+// Configurations the compact layout and its fused kernel cover (include/marlsc_b200.h, MARLSC_LAYOUT_COMPACT).
+bool compact_eligible(const DevSpec& ds, const HostTables& tb) {
+  const uint32_t caps = required_caps(ds, tb, nullptr) & ~C_REGMAP;    // the region map is applied when lines are built
+  if (caps & ~kCapsLean) return false;
+  if (ds.dh_mode == 2) return false;                                    // home-demand block without a history plane
+  if (ds.S <= 32 || ds.S > kCompactMaxS || (ds.S & 1)) return false;
+  if (ds.W > kCompactMaxW || ds.R > kCompactMaxR || ds.L > kCompactMaxL || !ds.perm5) return false;
+  for (double v : tb.action_max) if (!(v >= 0.0 && v <= 255.0)) return false;
+  return true;
+}
+
+// Line buffer for dense orders given to a compact handle, grown on demand (growing synchronises the device).
+int ensure_lines(marlsc_env* env, int64_t num_envs) {
+  if (!env->h_overflow) {
+    MARLSC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&env->h_overflow), sizeof(int32_t), cudaHostAllocMapped));
+    *env->h_overflow = 0;
+    MARLSC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&env->d_overflow), env->h_overflow, 0));
+  }
+  if (env->line_envs >= num_envs) return MARLSC_OK;
+  if (env->d_lines) {
+    MARLSC_CUDA(cudaDeviceSynchronize());
+    MARLSC_CUDA(cudaFree(env->d_lines));
+    MARLSC_CUDA(cudaFree(env->d_line_counts));
+    env->d_lines = nullptr;
+    env->d_line_counts = nullptr;
+    env->line_envs = 0;
+  }
+  MARLSC_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->d_lines), sizeof(uint16_t) * 32 * (size_t)num_envs * env->line_stride));
+  MARLSC_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->d_line_counts), sizeof(int32_t) * (size_t)num_envs));
+  env->line_envs = num_envs;
+  return MARLSC_OK;
+}
+
 int check_state(const marlsc_env* env, const marlsc_env_state_t* st) {
   if (!env || !st) return set_error(MARLSC_EINVAL, "null handle or state");
+  if (st->layout != env->layout)
+    return set_error(MARLSC_EINVAL, std::string("state.layout does not match the handle's layout (") +
+                                        (env->layout == MARLSC_LAYOUT_COMPACT ? "COMPACT" : "WIDE") + ", see marlsc_env_layout)");
+  if (env->h_overflow && *env->h_overflow)
+    return set_error(MARLSC_EINVAL, "an earlier step's orders did not fit the line buffer (a stream needed more than line_stride "
+                                    "rounds): raise it with marlsc_env_set_line_stride");
   if (st->num_envs < 1) return set_error(MARLSC_EINVAL, "num_envs must be positive");
   if (st->num_envs > (int64_t)0x7fffffff) return set_error(MARLSC_EINVAL, "num_envs too large");
   if (!st->inventory || !st->ring_qty) return set_error(MARLSC_EINVAL, "state.inventory / state.ring_qty are NULL");
@@ -206,7 +253,8 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
                o_hm = blob_add(off, t.home), o_cl = blob_add(off, t.closest), o_rm = blob_add(off, t.region_map),
                o_pp = blob_add(off, t.prio), o_ps = blob_add(off, t.prio_static), o_om = blob_add(off, t.obs_mean),
                o_os = blob_add(off, t.obs_std), o_hk = blob_add(off, t.home_mask), o_l8 = blob_add(off, t.lead_u8),
-               o_pm = blob_add(off, t.prio_perm);
+               o_pm = blob_add(off, t.prio_perm), o_p5 = blob_add(off, t.perm5), o_p16 = blob_add(off, t.prio16),
+               o_hw = blob_add(off, t.home_wh);
   std::vector<unsigned char> host(off + 16, 0);
   auto put = [&](size_t at, const void* src, size_t n) { if (n) std::memcpy(host.data() + at, src, n); };
   put(o_amax, t.action_max.data(), t.action_max.size() * 8); put(o_of, t.out_fixed.data(), t.out_fixed.size() * 8);
@@ -219,6 +267,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   put(o_om, t.obs_mean.data(), t.obs_mean.size() * 4); put(o_os, t.obs_std.data(), t.obs_std.size() * 4);
   put(o_hk, t.home_mask.data(), t.home_mask.size() * 4); put(o_l8, t.lead_u8.data(), t.lead_u8.size());
   put(o_pm, t.prio_perm.data(), t.prio_perm.size() * 2);
+  put(o_p5, t.perm5.data(), t.perm5.size() * 2); put(o_p16, t.prio16.data(), t.prio16.size()); put(o_hw, t.home_wh.data(), t.home_wh.size());
   ce = cudaMalloc(&env->d_blob, host.size());
   if (ce == cudaSuccess) ce = cudaMemcpy(env->d_blob, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) {
@@ -235,6 +284,11 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
               t.obs_mean.empty() ? nullptr : reinterpret_cast<const float*>(b + o_om),
               t.obs_std.empty() ? nullptr : reinterpret_cast<const float*>(b + o_os));
   env->ds.prio_perm = t.prio_perm.empty() ? nullptr : reinterpret_cast<const uint16_t*>(b + o_pm);
+  env->ds.perm5 = t.perm5.empty() ? nullptr : reinterpret_cast<const uint16_t*>(b + o_p5);
+  env->ds.prio16 = t.prio16.empty() ? nullptr : b + o_p16;
+  env->ds.home_wh = b + o_hw;
+  env->ds.compact_ok = compact_eligible(env->ds, env->tb) ? 1 : 0;
+  env->layout = env->ds.compact_ok ? MARLSC_LAYOUT_COMPACT : MARLSC_LAYOUT_WIDE;
   *out = env;
   return MARLSC_OK;
 }
@@ -248,6 +302,9 @@ void marlsc_env_destroy(marlsc_env_t* env) {
   }
   if (env->d_blob) cudaFree(env->d_blob);
   if (env->d_work) cudaFree(env->d_work);
+  if (env->d_lines) cudaFree(env->d_lines);
+  if (env->d_line_counts) cudaFree(env->d_line_counts);
+  if (env->h_overflow) cudaFreeHost(env->h_overflow);
   for (cudaEvent_t ev : env->marks)
     if (ev) cudaEventDestroy(ev);
   delete env;
@@ -257,9 +314,38 @@ int32_t marlsc_env_obs_dim(const marlsc_env_t* env) { return env ? env->ds.obs_d
 int32_t marlsc_env_needs_history(const marlsc_env_t* env) { return env ? env->ds.need_hist : 0; }
 int32_t marlsc_env_needs_forecast(const marlsc_env_t* env) { return env ? env->ds.need_fcst : 0; }
 int32_t marlsc_env_team_size(const marlsc_env_t* env) { return env ? env->team : 0; }
+int32_t marlsc_env_layout(const marlsc_env_t* env) { return env ? env->layout : 0; }
+
+int marlsc_env_set_layout(marlsc_env_t* env, int32_t layout) {
+  if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  if (layout != MARLSC_LAYOUT_WIDE && layout != MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "unknown layout");
+  if (layout == MARLSC_LAYOUT_COMPACT && !env->ds.compact_ok)
+    return set_error(MARLSC_EUNSUPPORTED, "this configuration does not qualify for the compact layout (see MARLSC_LAYOUT_COMPACT in marlsc_b200.h)");
+  env->layout = layout;
+  return MARLSC_OK;
+}
+
+int marlsc_env_set_line_stride(marlsc_env_t* env, int32_t rounds) {
+  if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  if (rounds < 1 || rounds > 4096) return set_error(MARLSC_EINVAL, "line stride must be in [1, 4096]");
+  if (env->d_lines) {
+    MARLSC_CUDA(cudaSetDevice(env->device));
+    MARLSC_CUDA(cudaDeviceSynchronize());
+    MARLSC_CUDA(cudaFree(env->d_lines));
+    MARLSC_CUDA(cudaFree(env->d_line_counts));
+    env->d_lines = nullptr;
+    env->d_line_counts = nullptr;
+    env->line_envs = 0;
+  }
+  if (env->h_overflow) *env->h_overflow = 0;
+  env->line_stride = rounds;
+  return MARLSC_OK;
+}
 
 int marlsc_env_set_team_size(marlsc_env_t* env, int32_t tpe) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  if (env->layout == MARLSC_LAYOUT_COMPACT && tpe != 0)
+    return set_error(MARLSC_EINVAL, "the compact layout runs one warp per environment; force MARLSC_LAYOUT_WIDE to choose a team size");
   if (tpe == 0) return set_team(env, env->team_auto);
   if (tpe < 1 || tpe > 64 || (tpe & (tpe - 1))) return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,64]");
   return set_team(env, tpe);
@@ -267,12 +353,14 @@ int marlsc_env_set_team_size(marlsc_env_t* env, int32_t tpe) {
 
 int marlsc_env_set_generic(marlsc_env_t* env, int32_t on) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  if (on && env->layout == MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "force MARLSC_LAYOUT_WIDE first: the compact layout has one kernel");
   env->force_generic = on ? 1 : 0;
   return MARLSC_OK;
 }
 
 int marlsc_env_set_fused(marlsc_env_t* env, int32_t on) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
+  if (on && env->layout == MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "force MARLSC_LAYOUT_WIDE first: the compact layout has one kernel");
   env->force_fused = on ? 1 : 0;
   return MARLSC_OK;
 }
@@ -305,6 +393,10 @@ int marlsc_env_reset(marlsc_env_t* env, const marlsc_env_state_t* state, const i
   if (!init_inventory || !obs) return set_error(MARLSC_EINVAL, "init_inventory and obs must not be NULL");
   MARLSC_CUDA(cudaSetDevice(env->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (env->layout == MARLSC_LAYOUT_COMPACT) {
+    const LaunchArgs lc{env->ds, *state, env->max_smem_optin, true};
+    return launch_reset_compact(lc, init_inventory, per_env, obs, s);
+  }
   if (split_ok(env)) {
     rc = ensure_work(env, state->num_envs);
     if (rc) return rc;
@@ -320,8 +412,16 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   int rc = check_state(env, state);
   if (rc) return rc;
   if (!io) return set_error(MARLSC_EINVAL, "null io");
-  if (!io->actions || !io->rewards || !io->obs || (!io->order_offsets && !io->order_counts))
-    return set_error(MARLSC_EINVAL, "io.actions, io.rewards, io.obs and one of io.order_offsets / io.order_counts must not be NULL");
+  if ((!io->actions && !io->action_qty) || !io->rewards || !io->obs)
+    return set_error(MARLSC_EINVAL, "io.actions (or io.action_qty), io.rewards and io.obs must not be NULL");
+  if (io->lines) {
+    if (env->layout != MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "io.lines needs a handle with the COMPACT layout");
+    if (!io->line_offsets && !io->line_counts) return set_error(MARLSC_EINVAL, "io.lines needs io.line_offsets or io.line_counts");
+    if (io->line_counts && io->line_stride < 1) return set_error(MARLSC_EINVAL, "line_stride must be positive with line_counts");
+  } else if (!io->order_offsets && !io->order_counts) {
+    return set_error(MARLSC_EINVAL, "one of io.lines / io.order_offsets / io.order_counts must not be NULL");
+  }
+  if (io->action_qty && env->layout != MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "io.action_qty needs a handle with the COMPACT layout");
   if (io->order_counts && io->order_stride < 1) return set_error(MARLSC_EINVAL, "order_stride must be positive with order_counts");
   if (io->order_qty_bytes != 1 && io->order_qty_bytes != 2) return set_error(MARLSC_EINVAL, "order_qty_bytes must be 1 or 2");
   if (env->ds.lead_mode == MARLSC_LEAD_STOCHASTIC && !io->actual_lead)
@@ -330,6 +430,32 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
   MARLSC_CUDA(cudaSetDevice(env->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (env->layout == MARLSC_LAYOUT_COMPACT) {
+    if (io->order_qty_bytes == 2 && !io->lines) return set_error(MARLSC_EUNSUPPORTED, "two-byte order quantities need MARLSC_LAYOUT_WIDE");
+    if (io->cost_breakdown || io->d_ordered || io->d_ship || io->d_ship_count || io->d_unfulfilled || io->d_lost_orders || io->d_lost_sales)
+      return set_error(MARLSC_EUNSUPPORTED, "the diagnostic outputs need MARLSC_LAYOUT_WIDE (marlsc_env_set_layout before the first reset)");
+    const LaunchArgs lc{env->ds, *state, env->max_smem_optin, true};
+    marlsc_step_io_t ioc = *io;
+    if (env->timing) MARLSC_CUDA(cudaEventRecord(env->marks[0], s));
+    int n_marks = 1;
+    if (!io->lines) {                                  // dense orders: build the lines in the library's buffer first
+      rc = ensure_lines(env, state->num_envs);
+      if (rc) return rc;
+      rc = launch_lines_from_orders(env->ds, state->num_envs, *io, env->line_stride, env->d_lines, env->d_line_counts, env->d_overflow, s);
+      if (rc) return rc;
+      ioc.lines = env->d_lines;
+      ioc.line_offsets = nullptr;
+      ioc.line_counts = env->d_line_counts;
+      ioc.line_stride = env->line_stride;
+      if (env->timing) MARLSC_CUDA(cudaEventRecord(env->marks[n_marks], s));
+      ++n_marks;
+    }
+    rc = launch_step_compact(lc, ioc, t, s);
+    if (rc) return rc;
+    if (env->timing) MARLSC_CUDA(cudaEventRecord(env->marks[n_marks], s));
+    env->timed_launches = env->timing ? n_marks : 0;
+    return MARLSC_OK;
+  }
   const bool lean = !env->force_generic && (required_caps(env->ds, env->tb, io) & ~kCapsLean) == 0;
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
   // the row kernels of the split step index (environment, warehouse) rows with 32 bits
@@ -448,6 +574,7 @@ int marlsc_policy_base_stock(marlsc_env_t* env, const marlsc_env_state_t* state,
   if (env->ds.action_type != MARLSC_ACTION_DIRECT) return set_error(MARLSC_EINVAL, "the base-stock heuristic assumes the direct action space");
   if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
   MARLSC_CUDA(cudaSetDevice(env->device));
+  if (env->layout == MARLSC_LAYOUT_COMPACT) return launch_base_stock_compact(env->ds, *state, level, 0, t, actions, static_cast<cudaStream_t>(stream));
   return launch_base_stock(env->ds, *state, level, 0, t, actions, static_cast<cudaStream_t>(stream));
 }
 
@@ -459,7 +586,19 @@ int marlsc_policy_base_stock_per_env(marlsc_env_t* env, const marlsc_env_state_t
   if (env->ds.action_type != MARLSC_ACTION_DIRECT) return set_error(MARLSC_EINVAL, "the base-stock heuristic assumes the direct action space");
   if (t < 0) return set_error(MARLSC_EINVAL, "timestep must be >= 0");
   MARLSC_CUDA(cudaSetDevice(env->device));
+  if (env->layout == MARLSC_LAYOUT_COMPACT) return launch_base_stock_compact(env->ds, *state, level, 1, t, actions, static_cast<cudaStream_t>(stream));
   return launch_base_stock(env->ds, *state, level, 1, t, actions, static_cast<cudaStream_t>(stream));
+}
+
+int marlsc_lines_from_orders(marlsc_env_t* env, int64_t num_envs, const marlsc_step_io_t* orders, int32_t line_stride,
+                             uint16_t* lines, int32_t* line_counts, int32_t* overflow_flag, void* stream) {
+  if (!env || !orders || !lines || !line_counts || !overflow_flag) return set_error(MARLSC_EINVAL, "null argument");
+  if (!env->ds.compact_ok) return set_error(MARLSC_EUNSUPPORTED, "lines exist for configurations that qualify for the compact layout");
+  if (num_envs < 1 || line_stride < 1) return set_error(MARLSC_EINVAL, "num_envs and line_stride must be positive");
+  if (!orders->order_offsets && !orders->order_counts) return set_error(MARLSC_EINVAL, "orders need order_offsets or order_counts");
+  if (orders->order_qty_bytes != 1) return set_error(MARLSC_EUNSUPPORTED, "lines carry one-byte quantities");
+  MARLSC_CUDA(cudaSetDevice(env->device));
+  return launch_lines_from_orders(env->ds, num_envs, *orders, line_stride, lines, line_counts, overflow_flag, static_cast<cudaStream_t>(stream));
 }
 
 const char* marlsc_last_error(void) { return g_last_error.c_str(); }

@@ -156,6 +156,63 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
   if (lane == 0) counts[e] = row;
 }
 
+// K4 writing lines (the compact layout's demand format, include/marlsc_b200.h): the same draws as sample_demand_kernel
+// (same Philox counters), but every lane appends the non-zero cells of its SKUs to its own stream instead of filling
+// dense rows - the allocation kernel then walks the streams without ever scanning the 80 % zero cells.
+__global__ void __launch_bounds__(128)
+sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, long long step, int stride,
+                           const int32_t* __restrict__ region_map, uint16_t* __restrict__ lines, int32_t* __restrict__ counts,
+                           int32_t* __restrict__ overflow) {
+  const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  uint16_t* out = lines + e * (long long)stride * 32 + lane;
+  int row = 0, cnt = 0;
+  bool over = false;
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    const int r = r0 + lane;
+    int n = 0;
+    if (r < R) {
+      uint32_t c[4] = {(uint32_t)e, (uint32_t)(e >> 32) ^ 0x5bd1e995u, (uint32_t)step, (uint32_t)r};
+      philox4x32(c, seed);
+      n = poisson_from(dp.lam_orders[r], u01(c[0]), u01(c[1]));
+    }
+    for (int l = 0; l < 32 && r0 + l < R; ++l) {      // regions in ascending order, like the reference
+      const int nr = __shfl_sync(0xffffffffu, n, l);
+      const int rr = r0 + l;
+      const float p = dp.prob[rr];
+      const int rm = region_map ? region_map[rr] : rr;
+      for (int i = 0; i < nr; ++i) {
+        if (lane < S) {
+          uint32_t c[4] = {(uint32_t)e, (uint32_t)row | 0x80000000u, (uint32_t)step, (uint32_t)lane};
+          philox4x32(c, seed);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int s = lane + 32 * j;
+            if (s < S) {
+              const float ub = (float)(c[j] & 0xfffu) * (1.0f / 4096.0f);
+              const float uq = (float)(c[j] >> 12) * (1.0f / 1048576.0f);
+              if (ub < p) {
+                int q = quantity_from(dp.cdf_qty + (size_t)(rr * S + s) * kCdf, dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
+                q = q < 1 ? 1 : (q > 255 ? 255 : q);
+                if (cnt < stride) out[(long long)cnt * 32] = (uint16_t)(q | (rm << 8) | (j << 14));
+                else over = true;
+                ++cnt;
+              }
+            }
+          }
+        }
+        ++row;
+      }
+    }
+  }
+  cnt = cnt < stride ? cnt : stride;
+  const int rounds = __reduce_max_sync(0xffffffffu, cnt);
+  for (int c = cnt; c < rounds; ++c) out[(long long)c * 32] = 0;     // pad this stream to the environment's round count
+  if (lane == 0) counts[e] = rounds;
+  if (over) atomicExch(overflow, 1);
+}
+
 // K4 for small SKU counts: one thread per environment (a warp per environment leaves 30 of 32 lanes idle at two
 // SKUs). Same Philox counters and words as sample_demand_kernel, so both kernels draw identical orders.
 __global__ void __launch_bounds__(128)
@@ -240,7 +297,7 @@ base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_consta
   const IDX e = idx / WS;
   const int i = (int)(idx - e * WS);
   const int D = sp.D;
-  const int32_t* ring = st.ring_qty + (long long)e * (long long)WS * D + i;
+  const int32_t* ring = static_cast<const int32_t*>(st.ring_qty) + (long long)e * (long long)WS * D + i;
   const int le = sp.lead_exp[i];
   int pending = 0;                                     // units ordered and not yet arrived before step t
   if (sp.lead_mode == MARLSC_LEAD_FIXED) {
@@ -268,7 +325,7 @@ base_stock_policy_kernel(const __grid_constant__ DevSpec sp, const __grid_consta
     }
   }
   const double mx = sp.action_max[i % sp.S];
-  double q = (double)(level_per_env ? level[idx] : level[i]) - (double)st.inventory[idx] - (double)pending;
+  double q = (double)(level_per_env ? level[idx] : level[i]) - (double)static_cast<const int32_t*>(st.inventory)[idx] - (double)pending;
   q = q < 0.0 ? 0.0 : (q > mx ? mx : q);
   actions[idx] = (float)(2.0 * q / mx - 1.0);
 }
@@ -363,6 +420,22 @@ int marlsc_demand_sample(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, in
     sample_demand_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         d->dp, d->R, d->S, num_envs, seed, step_index, max_orders_per_env, order_counts, order_region, order_qty, overflow_flag);
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+int marlsc_demand_sample_lines(marlsc_demand_t* d, int64_t num_envs, uint64_t seed, int64_t step_index, int32_t line_stride,
+                               const int32_t* region_map, uint16_t* lines, int32_t* line_counts, int32_t* overflow_flag,
+                               void* stream) {
+  if (!d || !lines || !line_counts || !overflow_flag) return set_error(MARLSC_EINVAL, "null argument");
+  if (num_envs < 1 || line_stride < 1) return set_error(MARLSC_EINVAL, "num_envs and line_stride must be positive");
+  if (d->S > 128) return set_error(MARLSC_EUNSUPPORTED, "lines address at most 128 SKUs");
+  if (!region_map && d->R > 64) return set_error(MARLSC_EUNSUPPORTED, "lines address at most 64 regions");
+  MARLSC_CUDA(cudaSetDevice(d->device));
+  const int wpb = 4;
+  sample_demand_lines_kernel<<<(unsigned)((num_envs + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      d->dp, d->R, d->S, num_envs, seed, step_index, line_stride, region_map, lines, line_counts, overflow_flag);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;

@@ -21,6 +21,10 @@ struct HostTables {
   // W <= 16: warehouse-availability bits (bit w) -> the same bits in region r's priority order (bit v = the v-th
   // cheapest warehouse), four warehouse bits per lookup: [R][perm_chunks][16] (env_alloc.cuh)
   std::vector<uint16_t> prio_perm;
+  // compact layout (env_compact.cu): [R][ceil(W/5)][32] availability -> priority-order bits, [R][16] priority rows,
+  // [R] home warehouse of a region (255 none, 254 several)
+  std::vector<uint16_t> perm5;
+  std::vector<uint8_t> prio16, home_wh;
 };
 
 inline int pow2ceil(int v) {
@@ -125,6 +129,27 @@ inline std::string build_devspec(const marlsc_env_spec_t& sp, DevSpec& ds, HostT
         for (int m = 0; m < 16; ++m)
           if ((m >> (w % 4)) & 1) tb.prio_perm[((size_t)r * nc + w / 4) * 16 + m] |= (uint16_t)(1u << v);
       }
+  }
+  tb.perm5.clear();
+  tb.prio16.clear();
+  ds.perm5_chunks = 0;
+  if (W <= 16) {
+    const int nc = (W + 4) / 5;
+    ds.perm5_chunks = nc;
+    tb.perm5.assign((size_t)R * nc * 32, 0);
+    tb.prio16.assign((size_t)R * 16, 0);
+    for (int r = 0; r < R; ++r)
+      for (int v = 0; v < W; ++v) {
+        const int w = tb.prio[(size_t)r * Wp + v];
+        tb.prio16[(size_t)r * 16 + v] = (uint8_t)w;
+        for (int m = 0; m < 32; ++m)
+          if ((m >> (w % 5)) & 1) tb.perm5[((size_t)r * nc + w / 5) * 32 + m] |= (uint16_t)(1u << v);
+      }
+  }
+  tb.home_wh.assign(R, 255);
+  for (int w = 0; w < W; ++w) {
+    uint8_t& h = tb.home_wh[tb.home[w]];
+    h = h == 255 ? (uint8_t)w : (uint8_t)254;
   }
   ds.pen_uniform = 1;
   for (int s = 1; s < S; ++s) ds.pen_uniform = ds.pen_uniform && tb.pen_rate[s] == tb.pen_rate[0];

@@ -7,7 +7,7 @@ order the reference sampler emits them (region-major for Poisson, reference dema
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -58,3 +58,55 @@ def pack_orders(per_env: Sequence[Sequence], n_skus: int, qty_dtype=None) -> Ord
     qty = np.zeros((_pad_rows(n, n_skus, np.dtype(qty_dtype).itemsize), n_skus), dtype=qty_dtype)
     qty[:n] = q
     return OrderBatch(offsets=offsets, region=np.asarray(regions, dtype=np.int16), qty=qty)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sparse demand ("lines", include/marlsc_b200.h ``marlsc_step_io.lines``): the native input of the compact layout.
+# ---------------------------------------------------------------------------------------------------------
+LINE_LANES = 32
+
+
+@dataclass
+class LineBatch:
+    offsets: np.ndarray   # [E+1] int32, in rounds
+    lines: np.ndarray     # [n_rounds_pad, 32] uint16: qty | region << 8 | (sku // 32) << 14, 0 = padding
+    n_lines: int          # non-zero (order, SKU) cells
+
+    @property
+    def n_rounds(self) -> int:
+        return int(self.offsets[-1])
+
+
+def pack_lines(batch: OrderBatch, region_map: Optional[Sequence[int]] = None) -> LineBatch:
+    """Regroup one step of orders into 32 line streams per environment (stream l = SKUs with ``s % 32 == l``, cells in
+    the order the reference allocator meets them: order index, then SKU; demand_allocator.py:150-208). Region ids are
+    mapped through ``region_map`` (raw -> included, reference preprocessor.py:382-441) when given."""
+    if batch.qty_bytes != 1:
+        raise ValueError("lines carry one-byte quantities")
+    E = batch.offsets.shape[0] - 1
+    n = batch.n_orders
+    S = batch.qty.shape[1]
+    if S > 4 * LINE_LANES:
+        raise ValueError("lines address at most 128 SKUs")
+    region = batch.region[:n].astype(np.int64)
+    if region_map is not None:
+        region = np.asarray(region_map, dtype=np.int64)[region]
+    if n and (region.min() < 0 or region.max() >= 64):
+        raise ValueError("lines address at most 64 regions")
+    oj, s = np.nonzero(batch.qty[:n])                      # row-major: order index ascending, then SKU
+    q = batch.qty[:n][oj, s].astype(np.int64)
+    env = np.searchsorted(batch.offsets, oj, side="right") - 1
+    stream = env * LINE_LANES + (s % LINE_LANES)
+    order = np.argsort(stream, kind="stable")             # keeps (order, SKU) sequence inside a stream
+    stream_sorted = stream[order]
+    counts = np.bincount(stream, minlength=E * LINE_LANES)
+    starts = np.cumsum(counts) - counts
+    pos = np.arange(stream_sorted.shape[0]) - starts[stream_sorted]      # position inside the stream
+    rounds = counts.reshape(E, LINE_LANES).max(axis=1) if E else np.zeros(0, np.int64)
+    offsets = np.zeros(E + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(rounds)
+    total = int(offsets[-1])
+    lines = np.zeros((max(total, 1), LINE_LANES), dtype=np.uint16)
+    entry = q[order] | (region[oj[order]] << 8) | ((s[order] // LINE_LANES) << 14)
+    lines[offsets[env[order]] + pos, s[order] % LINE_LANES] = entry.astype(np.uint16)
+    return LineBatch(offsets=offsets, lines=lines, n_lines=int(q.shape[0]))

@@ -1,5 +1,5 @@
-from .batched_env import BatchedInventoryEnv, DeviceOrders, HostRollout
+from .batched_env import BatchedInventoryEnv, DeviceLines, DeviceOrders, HostRollout
 from .multi_env import InventoryEnvironment
 from .single_env import CentralizedEnvWrapper
 
-__all__ = ["BatchedInventoryEnv", "CentralizedEnvWrapper", "DeviceOrders", "HostRollout", "InventoryEnvironment"]
+__all__ = ["BatchedInventoryEnv", "CentralizedEnvWrapper", "DeviceLines", "DeviceOrders", "HostRollout", "InventoryEnvironment"]

@@ -21,7 +21,7 @@ import torch
 from .. import _capi
 from ..config.schema import (EnvironmentConfig, InitialInventoryCustom, InitialInventoryUniform,
                              InitialInventoryZero)
-from ..demand import OrderBatch, pack_orders
+from ..demand import LineBatch, OrderBatch, pack_lines, pack_orders
 from ..seeds import ENVIRONMENT_SEEDS, SeedManager
 from ..spec import EnvSpec, build_env_spec
 
@@ -50,6 +50,20 @@ class DeviceOrders:
                             qty, batch.n_orders)
 
 
+class DeviceLines:
+    """One step of demand as sparse lines on the device (CSR over environments, see marlsc_b200.demand.pack_lines and
+    ``marlsc_step_io.lines`` in include/marlsc_b200.h): the native input of the compact layout."""
+
+    def __init__(self, offsets: torch.Tensor, lines: torch.Tensor, n_lines: int, n_rounds: int):
+        self.offsets, self.lines, self.n_lines, self.n_rounds = offsets, lines, int(n_lines), int(n_rounds)
+
+    @staticmethod
+    def from_host(batch: LineBatch, device) -> "DeviceLines":
+        # uint16 entries travel as int16 storage (same bytes)
+        return DeviceLines(torch.from_numpy(batch.offsets).to(device), torch.from_numpy(batch.lines.view(np.int16)).to(device),
+                           batch.n_lines, batch.n_rounds)
+
+
 class BatchedInventoryEnv:
     metadata = {"render_modes": ["human"], "name": "multi_env"}
 
@@ -58,7 +72,7 @@ class BatchedInventoryEnv:
                  region_map: Optional[Sequence[int]] = None, env_seeds: Optional[Sequence[int]] = None,
                  host_samplers: bool = True, diagnostics: bool = False, team_size: int = 0,
                  generic_kernel: bool = False, fused_kernel: bool = False, device_demand: bool = False, demand_seed: int = 0,
-                 max_orders_per_env: Optional[int] = None):
+                 max_orders_per_env: Optional[int] = None, layout: Optional[str] = None):
         if num_envs < 1:
             raise ValueError("num_envs must be positive")
         if not torch.cuda.is_available():
@@ -98,6 +112,20 @@ class BatchedInventoryEnv:
         with torch.cuda.device(self.device):
             _capi.check(L.marlsc_env_create(C.byref(self._spec_c), self.device.index, C.byref(handle)))
         self._h = handle
+        # State layout (include/marlsc_b200.h): "compact" (narrow state, one fused kernel, sparse demand lines) when the
+        # configuration qualifies and nothing asks for the general kernels; "wide" otherwise.
+        if layout not in (None, "wide", "compact"):
+            raise ValueError("layout must be None, 'wide' or 'compact'")
+        compact = L.marlsc_env_layout(self._h) == _capi.LAYOUT_COMPACT
+        wants_wide = bool(diagnostics or team_size or generic_kernel or fused_kernel) or self._stock_bound() >= 32768
+        if layout == "compact":
+            if wants_wide:
+                raise ValueError("layout='compact' excludes diagnostics / team_size / generic_kernel / fused_kernel and needs "
+                                 "initial stock + episode_length * max order quantity < 32768")
+            _capi.check(L.marlsc_env_set_layout(self._h, _capi.LAYOUT_COMPACT))
+        elif compact and (layout == "wide" or wants_wide):
+            _capi.check(L.marlsc_env_set_layout(self._h, _capi.LAYOUT_WIDE))
+        self.layout = "compact" if L.marlsc_env_layout(self._h) == _capi.LAYOUT_COMPACT else "wide"
         if team_size:
             _capi.check(L.marlsc_env_set_team_size(self._h, team_size))
         if generic_kernel:      # tests: bypass the lean instantiation of the step kernel
@@ -108,14 +136,26 @@ class BatchedInventoryEnv:
         self.global_obs_dim = self.n_warehouses * self.obs_dim
 
         E, W, S, D, dev = self.num_envs, self.n_warehouses, self.n_skus, self.ring_depth, self.device
-        self.inventory = torch.zeros((E, W, S), dtype=torch.int32, device=dev)
-        self.ring_qty = torch.zeros((E, D, W, S), dtype=torch.int32, device=dev)
-        self.ring_lead = torch.zeros((E, D, W, S), dtype=torch.uint8, device=dev) if self.stochastic_lead else None
-        self.demand_hist = (torch.zeros((E, 5, W, S), dtype=torch.int32, device=dev)
-                            if L.marlsc_env_needs_history(self._h) else None)
-        self.forecast = torch.zeros((E, W, S), dtype=torch.float32, device=dev) if L.marlsc_env_needs_forecast(self._h) else None
+        if self.layout == "compact":
+            # uint16 stock / history (int16 storage: values stay below 32768, see _stock_bound), uint8 ring indexed by
+            # arrival time: ring_qty[e, w, a % L, s] holds the order arriving at step a
+            Lm = self.max_expected_lead_time
+            self.inventory = torch.zeros((E, W, S), dtype=torch.int16, device=dev)
+            self.ring_qty = torch.zeros((E, W, Lm, S), dtype=torch.uint8, device=dev)
+            self.ring_lead = None
+            self.demand_hist = (torch.zeros((E, 5, W, S), dtype=torch.int16, device=dev)
+                                if L.marlsc_env_needs_history(self._h) else None)
+            self.forecast = None
+        else:
+            self.inventory = torch.zeros((E, W, S), dtype=torch.int32, device=dev)
+            self.ring_qty = torch.zeros((E, D, W, S), dtype=torch.int32, device=dev)
+            self.ring_lead = torch.zeros((E, D, W, S), dtype=torch.uint8, device=dev) if self.stochastic_lead else None
+            self.demand_hist = (torch.zeros((E, 5, W, S), dtype=torch.int32, device=dev)
+                                if L.marlsc_env_needs_history(self._h) else None)
+            self.forecast = torch.zeros((E, W, S), dtype=torch.float32, device=dev) if L.marlsc_env_needs_forecast(self._h) else None
         self._state = _capi.EnvStateC(E, _ptr(self.inventory), _ptr(self.ring_qty), _ptr(self.ring_lead),
-                                      _ptr(self.demand_hist), _ptr(self.forecast))
+                                      _ptr(self.demand_hist), _ptr(self.forecast),
+                                      _capi.LAYOUT_COMPACT if self.layout == "compact" else _capi.LAYOUT_WIDE)
         self.obs = torch.zeros((E, W, self.obs_dim), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((E, W), dtype=torch.float32, device=dev)
         self.truncated = torch.zeros((E,), dtype=torch.uint8, device=dev)
@@ -134,6 +174,7 @@ class BatchedInventoryEnv:
                 lost_orders=torch.zeros((E, R), dtype=torch.int32, device=dev),
                 lost_sales=torch.zeros((E, W, S), dtype=torch.float32, device=dev))
         self.timestep = 0
+        self._seed, self._episode = seed, 0  # reproducible device-side initial stock (see _initial_inventory)
         self._dd = None                      # device demand sampler state (enable_device_demand)
         self._dl = None                      # device lead-time sampler state (enable_device_leads)
         self._demand_step = 0
@@ -233,6 +274,21 @@ class BatchedInventoryEnv:
         return act
 
     # ------------------------------------------------------------------ helpers
+    def _stock_bound(self) -> int:
+        """Upper bound of on-hand stock over an episode: initial stock + one maximal order per step (nothing else adds
+        stock, multi_env.py:903-919); the compact layout keeps stock in 16 bits."""
+        ic = self.env_config.initial_inventory
+        if isinstance(ic, InitialInventoryUniform):
+            init = int(ic.params["max"])
+        elif isinstance(ic, InitialInventoryCustom):
+            init = int(np.max(np.asarray(ic.params["values"])))
+        else:
+            init = 0
+        a = self.env_config.action_space
+        if a.type != "direct":
+            return 1 << 30
+        return init + self.episode_length * int(np.max(np.asarray(a.params.max_order_quantities)))
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -283,6 +339,8 @@ class BatchedInventoryEnv:
 
     def pending_matrix(self) -> torch.Tensor:
         """Units in transit per (env, warehouse, SKU) (reference ``_compute_pending_matrix``)."""
+        if self.layout == "compact":      # every plane of the arrival-indexed ring is an order still on its way
+            return self.ring_qty.sum(dim=2, dtype=torch.int32).to(torch.float32)
         t = self.timestep
         D = self.ring_depth
         tau = torch.tensor([t - 1 - ((t - 1 - d) % D) for d in range(D)], device=self.device).view(1, D, 1, 1)
@@ -303,7 +361,11 @@ class BatchedInventoryEnv:
             if self._host_samplers:
                 vals = np.stack([sm.get_rng("inventory").integers(lo, hi + 1, size=(W, S)) for sm in self.seed_managers])
                 return torch.from_numpy(vals.astype(np.int32)).to(self.device), 1
-            return torch.randint(lo, hi + 1, (self.num_envs, W, S), dtype=torch.int32, device=self.device), 1
+            # no host samplers: a device generator keyed by (env seed, episode) so that resets are reproducible
+            # (the reference draws from the seeded "inventory" stream on every reset, multi_env.py:504-520)
+            g = torch.Generator(device=self.device)
+            g.manual_seed((int(self._seed or 0) * 1000003 + self._episode) & 0x7fffffffffffffff)
+            return torch.randint(lo, hi + 1, (self.num_envs, W, S), dtype=torch.int32, device=self.device, generator=g), 1
         if isinstance(ic, InitialInventoryCustom):
             v = ic.params["values"]
             arr = np.full((W, S), v, dtype=np.int32) if isinstance(v, int) else np.array(v, dtype=np.int32)
@@ -325,6 +387,7 @@ class BatchedInventoryEnv:
                     sm.advance_episode()
                 for name, comp in (("demand_sampler", self.demand_samplers[i]), ("lead_time_sampler", self.lead_time_samplers[i])):
                     comp.reset(rng=sm.get_rng(name))
+        self._episode += 1
         if init_inventory is None:
             init, per_env = self._initial_inventory()
         else:
@@ -335,6 +398,8 @@ class BatchedInventoryEnv:
                 per_env = 0
             else:
                 raise ValueError(f"init_inventory must be [E,W,S] or [W,S], got {tuple(init.shape)}")
+            if self.layout == "compact" and int(init.max()) + self._stock_bound() >= 32768:
+                raise ValueError("init_inventory too large for the compact layout (16-bit stock); construct with layout='wide'")
         out = self._check_obs_out(obs_out)
         _capi.check(_capi.lib().marlsc_env_reset(self._h, C.byref(self._state), init.data_ptr(), per_env, out.data_ptr(), self._stream()))
         self._keep = init
@@ -361,7 +426,7 @@ class BatchedInventoryEnv:
         per_env = [ds.sample(self.timestep) for ds in self.demand_samplers]
         return pack_orders(per_env, self.n_skus), leads
 
-    def step(self, actions: torch.Tensor, orders: Union[DeviceOrders, OrderBatch, None] = None,
+    def step(self, actions: torch.Tensor, orders: Union[DeviceOrders, OrderBatch, DeviceLines, LineBatch, None] = None,
              actual_lead: Union[torch.Tensor, np.ndarray, None] = None, obs_out: Optional[torch.Tensor] = None,
              rewards_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, bool]:
         """Advance every environment by one timestep.
@@ -373,8 +438,11 @@ class BatchedInventoryEnv:
         The returned tensors are reused by the next call unless ``obs_out`` / ``rewards_out`` are given.
         """
         E, W, S = self.num_envs, self.n_warehouses, self.n_skus
-        if actions.shape != (E, W, S) or actions.dtype != torch.float32 or actions.device != self.device:
-            raise ValueError(f"actions must be a float32 tensor of shape {(E, W, S)} on {self.device}")
+        qty_actions = actions.dtype == torch.uint8
+        if qty_actions and self.layout != "compact":
+            raise ValueError("uint8 quantity actions need the compact layout")
+        if actions.shape != (E, W, S) or (actions.dtype != torch.float32 and not qty_actions) or actions.device != self.device:
+            raise ValueError(f"actions must be a float32 (or, compact layout, uint8 quantity) tensor of shape {(E, W, S)} on {self.device}")
         actions = actions.contiguous()
         use_dd = orders is None and self._dd is not None
         if use_dd:
@@ -388,7 +456,21 @@ class BatchedInventoryEnv:
             if actual_lead is None:
                 actual_lead = host_leads
         if isinstance(orders, OrderBatch):
-            orders = DeviceOrders.from_host(orders, self.device)
+            if self.layout == "compact" and orders.qty_bytes == 1:
+                orders = pack_lines(orders, self.spec.tables["region_map"])
+            else:
+                orders = DeviceOrders.from_host(orders, self.device)
+        if isinstance(orders, LineBatch):
+            orders = DeviceLines.from_host(orders, self.device)
+        lines = orders if isinstance(orders, DeviceLines) else None
+        if lines is not None:
+            if self.layout != "compact":
+                raise ValueError("demand lines need the compact layout")
+            if lines.offsets.shape != (E + 1,) or lines.offsets.dtype != torch.int32 or lines.offsets.device != self.device:
+                raise ValueError(f"lines.offsets must be int32 [E+1] on {self.device}")
+            if lines.lines.device != self.device or lines.lines.numel() < 32 * max(1, lines.n_rounds):
+                raise ValueError("lines.lines is smaller than offsets[E] rounds of 32 entries")
+            orders = self._empty_orders
         lead_t = None
         if self.stochastic_lead:
             if actual_lead is None:
@@ -397,27 +479,38 @@ class BatchedInventoryEnv:
                       if isinstance(actual_lead, np.ndarray) else actual_lead.to(device=self.device, dtype=torch.uint8).contiguous())
             if lead_t.shape != (E, W, S):
                 raise ValueError(f"actual_lead must have shape {(E, W, S)}")
-        if orders.offsets.shape != (E + 1,) or orders.offsets.dtype != torch.int32:
-            raise ValueError("orders.offsets must be int32 [E+1]")
+        if orders.offsets.shape != (E + 1,) or orders.offsets.dtype != torch.int32 or orders.offsets.device != self.device:
+            raise ValueError(f"orders.offsets must be int32 [E+1] on {self.device}")
+        if lines is None and not use_dd:
+            # cheap host-side consistency checks of user-supplied device orders (n_orders is host knowledge)
+            if orders.region.device != self.device or orders.qty.device != self.device:
+                raise ValueError(f"orders must live on {self.device}")
+            need = (orders.n_orders * S * orders.qty_bytes + 3) & ~3      # the kernels read the rows as aligned 32-bit words
+            if orders.region.numel() < max(1, orders.n_orders) or orders.qty.numel() * orders.qty.element_size() < need:
+                raise ValueError("orders.region / orders.qty are smaller than offsets[E] rows (qty padded to whole 32-bit words)")
         out = self._check_obs_out(obs_out)
         rew = self.rewards if rewards_out is None else rewards_out
-        if rew.shape != (E, W) or rew.dtype != torch.float32 or not rew.is_contiguous():
-            raise ValueError("rewards_out must be a contiguous float32 [E,W] tensor")
+        if rew.shape != (E, W) or rew.dtype != torch.float32 or not rew.is_contiguous() or rew.device != self.device:
+            raise ValueError(f"rewards_out must be a contiguous float32 [E,W] tensor on {self.device}")
         d = self.diag
         if d:
             for k in ("ship_by_sku", "ship_counts", "unfulfilled", "lost_orders"):
                 d[k].zero_()
         io = _capi.StepIOC(
-            actions.data_ptr(), orders.offsets.data_ptr(), orders.region.data_ptr(), orders.qty.data_ptr(),
+            None if qty_actions else actions.data_ptr(), orders.offsets.data_ptr(), orders.region.data_ptr(), orders.qty.data_ptr(),
             orders.qty_bytes, _ptr(lead_t), rew.data_ptr(), out.data_ptr(), self.truncated.data_ptr(),
             _ptr(d.get("cost_breakdown")), _ptr(d.get("ordered")), _ptr(d.get("ship_by_sku")), _ptr(d.get("ship_counts")),
             _ptr(d.get("unfulfilled")), _ptr(d.get("lost_orders")), _ptr(d.get("lost_sales")))
+        if qty_actions:
+            io.action_qty = actions.data_ptr()
+        if lines is not None:
+            io.lines, io.line_offsets = lines.lines.data_ptr(), lines.offsets.data_ptr()
         if use_dd:
             dd = self._dd
             io.order_offsets, io.order_region, io.order_qty, io.order_qty_bytes = None, dd["region"].data_ptr(), dd["qty"].data_ptr(), 1
             io.order_counts, io.order_stride = dd["counts"].data_ptr(), dd["omax"]
         _capi.check(_capi.lib().marlsc_env_step(self._h, C.byref(self._state), C.byref(io), self.timestep, self._stream()))
-        self._keep = (actions, orders, lead_t)   # keep inputs alive until the stream has consumed them
+        self._keep = (actions, orders, lines, lead_t)   # keep inputs alive until the stream has consumed them
         self.timestep += 1
         return out, rew, self.timestep >= self.episode_length
 

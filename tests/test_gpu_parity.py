@@ -11,15 +11,15 @@ from parity_common import compare_step, spec_for, step_orders
 pytestmark = pytest.mark.gpu
 
 
-def _run(g, team_size=0, region_map=None, region_shift=None, steps=None, diagnostics=True, generic=False, fused=False):
+def _run(g, team_size=0, region_map=None, region_shift=None, steps=None, diagnostics=True, generic=False, fused=False, layout=None):
     from marlsc_b200.envs import BatchedInventoryEnv
     cfg, _ = spec_for(g)
     meta = dict(obs_normalization=g.meta["obs_normalization"], obs_stats=g.obs_stats,
                 include_warehouse_id=g.meta["include_warehouse_id"])
     env = BatchedInventoryEnv(cfg, g.N, device="cuda:0", env_meta=meta, host_samplers=False, diagnostics=diagnostics,
-                              team_size=team_size, region_map=region_map, generic_kernel=generic, fused_kernel=fused)
+                              team_size=team_size, region_map=region_map, generic_kernel=generic, fused_kernel=fused, layout=layout)
     # poison the state so reset has to clear it
-    env.ring_qty.fill_(-5)
+    env.ring_qty.fill_(5)
     env.inventory.fill_(123)
     obs0 = env.reset(init_inventory=torch.from_numpy(g["init_inventory"]))
     np.testing.assert_allclose(obs0.cpu().numpy(), g["obs0_local"], rtol=1e-5, atol=1e-6)
@@ -32,8 +32,10 @@ def _run(g, team_size=0, region_map=None, region_shift=None, steps=None, diagnos
         out.update(inventory=env.inventory.cpu().numpy(), rewards=rew.cpu().numpy(), obs=obs.cpu().numpy(),
                    trunc=env.truncated.cpu().numpy())
         assert bool(trunc) == bool(g["trunc"][0, t])
-        compare_step(g, t, out, what=f"cuda team={env.team_size} ")
+        compare_step(g, t, out, what=f"cuda team={env.team_size} layout={env.layout} ")
+    layout_used = env.layout
     env.close()
+    return layout_used
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -41,14 +43,17 @@ def test_cuda_matches_reference_auto_team(name):
     _run(Golden(name))
 
 
-@pytest.mark.parametrize("mode", ["auto", "fused", "generic"])
+@pytest.mark.parametrize("mode", ["auto", "split", "fused", "generic"])
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_without_diagnostics(name, mode):
-    """No diagnostic outputs: configurations the lean capability set covers (small_default,
-    regions_ne_warehouses, large_network) run the lean path - the four-kernel split step for teams of 8+
-    lanes, else the lean fused kernel; ``fused`` keeps them in the fused kernel, ``generic`` forces the generic
-    instantiation."""
-    _run(Golden(name), diagnostics=False, generic=mode == "generic", fused=mode == "fused")
+    """No diagnostic outputs. ``auto``: the compact layout and its fused kernel where the configuration qualifies (the
+    large networks), else the wide lean path; ``split``: the wide layout's lean path - the four-kernel split step for
+    teams of 8+ lanes, else the lean fused kernel; ``fused`` keeps lean launches in the wide fused kernel; ``generic``
+    forces the generic instantiation."""
+    used = _run(Golden(name), diagnostics=False, generic=mode == "generic", fused=mode == "fused",
+                layout="wide" if mode == "split" else None)
+    if name.startswith("large_network"):
+        assert used == ("compact" if mode == "auto" else "wide")
 
 
 @pytest.mark.parametrize("team", [1, 2, 4, 8, 16, 32])
@@ -904,3 +909,117 @@ def test_poisson_inversion_survives_the_largest_uniform():
                                                    torch.cuda.current_stream().cuda_stream))
     ref = poisson.ppf(u2.cpu().numpy().astype(np.float64), lam2.cpu().numpy().astype(np.float64))
     assert (out.cpu().numpy() != ref).mean() < 2e-3        # only draws within float32 rounding of a CDF step differ
+
+
+def _lean_env_dict(rng, W, S, R, lost, pen_uniform, lead_hi, scope="agent", demand_home=False, qmax_hi=30):
+    out_var = np.stack([rng.permutation(W) for _ in range(R)], 1) * 0.05 + 0.05          # tie-free -> static priority
+    pen = 4.0 if pen_uniform else [float(x) for x in rng.integers(1, 9, S)]
+    lead = rng.integers(1, lead_hi + 1, (W, S))
+    lead[0, 0] = lead_hi                                                                  # some cell has the longest lead
+    return dict(
+        action_space=dict(type="direct", params=dict(max_order_quantities=[int(x) for x in rng.integers(5, qmax_hi, S)])),
+        n_warehouses=W, n_skus=S, n_regions=R, episode_length=9, max_wh_capacities=[1e7] * W,
+        initial_inventory=dict(type="custom", params=dict(values=6)),
+        cost_structure=dict(
+            holding_cost=0.5, penalty_cost=pen,
+            shipment_cost=dict(outbound_fixed=np.zeros((W, R)).tolist(), outbound_variable=out_var.tolist(),
+                               inbound_fixed=np.full((W, S), 0.5).tolist(), inbound_variable=np.full((W, S), 0.25).tolist()),
+            sku_weights=[1.0] * S, distances=(rng.integers(10, 500, (W, R)) * 1.0).tolist()),
+        components=dict(
+            demand_sampler=dict(type="poisson", params=dict(lambda_orders=1.0, probability_skus=0.3, lambda_quantity=5.0)),
+            demand_allocator=dict(type="greedy", params=dict(max_splits=W - 1)),
+            lead_time_sampler=dict(type="fixed", params=dict(expected_lead_times=lead.tolist())),
+            lost_sales_handler=dict(type=lost, params=None),
+            reward_calculator=dict(type="cost", params=dict(scope=scope, scale_factor=0.1, cost_weights=[0.25] * 4))),
+        data_source=dict(type="custom"),
+        features=dict(inventory=True, pipeline=True, incoming_demand_home=demand_home, units_shipped_home=False, units_shipped_away=False,
+                      stockout=False, rolling_demand_mean=True, demand_forecast=False, days_of_supply=False,
+                      net_inventory_position=False, demand_variability=False, demand_history=False, inventory_aggregate=True,
+                      pipeline_aggregate=False, incoming_demand_home_aggregate=False, units_shipped_away_aggregate=False,
+                      rolling_demand_mean_aggregate=False, demand_forecast_aggregate=False))
+
+
+@pytest.mark.parametrize("W,S,R,lost,pen_uniform,max_orders,lead_hi,variant", [
+    (7, 70, 9, "closest", False, 9, 3, "lines"),            # ragged last slot, per-SKU penalties (float64 lost sums), W in two chunks
+    (10, 100, 50, "shipment", False, 80, 10, "lines"),      # the large shape, leads up to 10 (ring wraps), > 64 orders per step
+    (16, 128, 64, "shipment", True, 40, 16, "lines"),       # every limit of the layout at once: W 16, S 128, R 64, L 16
+    (5, 34, 3, "shipment", True, 12, 1, "lines"),           # a single ring plane (L = 1), one warehouse chunk
+    (10, 100, 50, "shipment", True, 30, 6, "dense"),        # dense order rows converted on the device (marlsc_lines_from_orders)
+    (10, 100, 50, "closest", True, 30, 6, "qty_actions"),   # integer order quantities instead of float actions
+    (6, 64, 12, "shipment", True, 20, 4, "norm_id_team"),   # fixed mean/std normalisation, one-hot id, team reward, home-demand block
+    (10, 100, 50, "shipment", True, 30, 6, "region_map"),   # 50 raw regions mapped onto 10 included ones (preprocessor.py:382-441)
+])
+def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi, variant):
+    """The compact layout's fused kernel (csrc/env_compact.cu) against the oracle: scarce stock (most lines are split or
+    lost), environments without orders, all-zero orders, a batch that does not fill the last CTA, a mid-run reset, ring
+    wrap-around, and every way of feeding it (lines packed on the host, dense rows converted on the device, integer
+    quantity actions, a region map)."""
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.demand import pack_orders
+    from marlsc_b200.envs import BatchedInventoryEnv, DeviceOrders
+    from oracle.inventory_oracle import OracleEnv
+    rng = np.random.default_rng(W * 1000 + S + len(variant))
+    norm = variant == "norm_id_team"
+    R_cost = 10 if variant == "region_map" else R                 # regions the cost tables are defined on
+    env_dict = _lean_env_dict(rng, W, S, R_cost, lost, pen_uniform, lead_hi, scope="team" if norm else "agent", demand_home=norm)
+    env_dict["episode_length"] = 2 * lead_hi + 5
+    cfg = environment_config_from_dict(dict(env_dict, allow_region_mismatch=True))
+    region_map = [int(x) for x in rng.integers(0, R_cost, R)] if variant == "region_map" else None
+    meta, okw = {}, {}
+    if norm:
+        dim = S + 1 + lead_hi * S + S + S
+        stats = (rng.uniform(0, 5, dim).astype(np.float32), rng.uniform(0.5, 3, dim).astype(np.float32))
+        meta = dict(obs_normalization="meanstd_custom", obs_stats=stats, include_warehouse_id=True)
+        okw = dict(obs_normalization="meanstd_custom", obs_stats=stats, include_warehouse_id=True)
+    E, T = 11, 2 * lead_hi + 7
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, env_meta=meta, region_map=region_map)
+    assert env.layout == "compact"
+    oracles = [OracleEnv(env_dict, **okw) for _ in range(E)]
+    maxq = np.asarray(env_dict["action_space"]["params"]["max_order_quantities"])
+
+    def reset_all():
+        obs = env.reset().cpu().numpy()
+        for i, o in enumerate(oracles):
+            np.testing.assert_allclose(obs[i], o.reset(np.full((W, S), 6)), rtol=1e-5, atol=1e-6)
+    env.ring_qty.fill_(7)                                          # reset has to clear the state
+    env.inventory.fill_(99)
+    reset_all()
+    lost_any = False
+    for t in range(T):
+        if env.timestep >= env.episode_length or t == lead_hi + 3:
+            reset_all()
+        per_env = []
+        for i in range(E):
+            if i == 1 or (i == 3 and t % 2):
+                per_env.append([])
+                continue
+            orders = []
+            for _ in range(int(rng.integers(max_orders // 2, max_orders + 1))):
+                q = np.where(rng.random(S) < 0.3, rng.integers(1, 12, S), 0)
+                if rng.random() < 0.1:
+                    q[:] = 0
+                orders.append((int(rng.integers(0, R)), q.astype(float)))
+            per_env.append(orders)
+        batch = pack_orders(per_env, S)
+        if variant == "qty_actions":
+            qa = rng.integers(0, 40, (E, W, S)).astype(np.uint8)                   # some above the SKU's maximum: clipped
+            act_dev = torch.from_numpy(qa).cuda()
+            act = (2.0 * np.minimum(qa, maxq) / maxq - 1.0).astype(np.float32)      # the float action with the same quantity
+        else:
+            act = rng.uniform(-1, 1, (E, W, S)).astype(np.float32)
+            act_dev = torch.from_numpy(act).cuda()
+        feed = DeviceOrders.from_host(batch, "cuda:0") if variant == "dense" else batch
+        obs, rew, trunc = env.step(act_dev, orders=feed)
+        inv, r, ob = env.inventory.cpu().numpy(), rew.cpu().numpy(), obs.cpu().numpy()
+        pend = env.pending_matrix().cpu().numpy()
+        for i, o in enumerate(oracles):
+            mapped = [(region_map[rg], q) for rg, q in per_env[i]] if region_map else per_env[i]
+            out = o.step(act[i], mapped)
+            assert np.array_equal(inv[i], out["inventory"]), (t, i)
+            assert np.array_equal(pend[i], out["pending"]), (t, i)
+            np.testing.assert_allclose(r[i], out["rewards"], rtol=1e-5, atol=1e-5, err_msg=f"rewards t={t} env={i}")
+            np.testing.assert_allclose(ob[i], out["obs_local"], rtol=1e-5, atol=2e-5, err_msg=f"obs t={t} env={i}")
+            assert bool(trunc) == bool(out["trunc"])
+            lost_any = lost_any or out["lost_orders"].sum() > 0
+    assert lost_any, "workload was meant to lose sales"
+    env.close()
