@@ -91,11 +91,16 @@ def record_base_stock_actions(env, env_dict, demand, z):
     return actions
 
 
-def algorithmic_bytes_per_env_step(W, S, L, obs_dim, mean_orders, qty_bytes=1):
-    """int32 state, fp32 actions/obs/rewards, dense demand rows + region id.
-    reads: actions 4WS + inventory 4WS + pipeline 4WSL + history (sum + oldest) 8WS + demand
-    writes: inventory 4WS + new pipeline slot 4WS + history 8WS + obs 4*W*obs_dim + rewards 4W + trunc 1"""
-    return 4 * W * S * (L + 8) + mean_orders * (S * qty_bytes + 2) + 4 * W * obs_dim + 4 * W + 1
+def algorithmic_bytes_per_env_step(W, S, L, obs_dim, mean_orders, qty_bytes=1, layout="wide", mean_lines=0.0):
+    """SURVEY.md section 8d, evaluated with the actual dtype sizes of the layout in use (as 8d requires for narrower state).
+    reads: actions + inventory + pipeline (L planes) + history (sum + oldest) + demand
+    writes: inventory + new pipeline slot + history (2) + obs 4*W*obs_dim + rewards 4W + trunc 1
+    wide:    int32 state, dense demand rows + region id            -> 4WS(L+8) + orders (S+2) + ...
+    compact: uint16 stock/history, uint8 ring, 2-byte demand lines -> WS(4 + 2*2 + L + 1 + 4*2) + 2 lines + 4 + ..."""
+    tail = 4 * W * obs_dim + 4 * W + 1
+    if layout == "compact":
+        return W * S * (4 + 4 + L + 1 + 8) + 2 * mean_lines + 4 + tail
+    return 4 * W * S * (L + 8) + mean_orders * (S * qty_bytes + 2) + tail
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -278,14 +283,27 @@ def run_ours(args):
     cfg = environment_config_from_dict(d)
     E = args.envs or cfg_desc["envs_per_gpu"]
     W, S = cfg.n_warehouses, cfg.n_skus
-    env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False, team_size=args.team, fused_kernel=args.fused)
+    env = BatchedInventoryEnv(cfg, E, device=dev, host_samplers=False, team_size=args.team, fused_kernel=args.fused,
+                              layout=args.layout)
     L = _capi.lib()
+    compact = env.layout == "compact"
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     n_in = args.distinct_steps if args.policy == "uniform" else cfg.episode_length
     demand = synth_demand(env_dict, E, n_in, dev, 99 + rank)
     mean_orders = float(np.mean([dm.n_orders for dm in demand])) / E
+    dense_demand = demand
+    mean_lines = 0.0
+    if compact:
+        # the compact layout's native demand format: sparse lines, converted once on the device (outside every timed region)
+        demand = []
+        for dm in dense_demand:
+            demand.append(env.lines_from_orders(dm))
+        mean_lines = float(np.mean([dm.n_lines for dm in demand])) / E
+        if args.policy != "base_stock" or args.no_e2e:
+            dense_demand = dense_demand[:4]
+        torch.cuda.empty_cache()
     if args.policy == "uniform":
         lo, hi = ACTION_RANGE
         actions = [(torch.rand((E, W, S), device=dev, generator=gen) * (hi - lo) + lo) for _ in range(n_in)]
@@ -368,54 +386,90 @@ def run_ours(args):
     agent_steps = E * W * SEG * args.steps * world
     value = agent_steps / (elapsed_ms * 1e-3)
 
-    # ---- end to end through the host-buffer C-ABI call (marlsc_env_step_host) --------------------
+    # ---- end to end through the host-buffer C-ABI call (marlsc_env_rollout_host) -----------------
     e2e = None
+    e2e_obs = None
     if not args.no_e2e:
         from marlsc_b200.envs import HostRollout
         n_host = min(n_in, 4)
-        h_act = [a.cpu().pin_memory() for a in actions[:n_host]]
-        h_off = [dm.offsets.cpu().pin_memory() for dm in demand[:n_host]]
-        h_reg = [dm.region.cpu().pin_memory() for dm in demand[:n_host]]
-        h_qty = [dm.qty.cpu().pin_memory() for dm in demand[:n_host]]
-        h_n = [dm.n_orders for dm in demand[:n_host]]
         h_rew = torch.empty((SEG, E, W)).pin_memory()
         h_val = values.cpu().pin_memory()
         h_adv, h_tgt = torch.empty((SEG, E, W)).pin_memory(), torch.empty((SEG, E, W)).pin_memory()
-        hr = HostRollout(env, max(h_n))
         idx = [i % n_host for i in range(SEG)]
-        seg_in = ([h_act[i] for i in idx], [h_off[i] for i in idx], [h_reg[i] for i in idx], [h_qty[i] for i in idx],
-                  [h_n[i] for i in idx])
-        h2d_seg = sum(h_act[i].numel() * 4 + h_off[i].numel() * 4 + h_n[i] * (2 + S) for i in idx) + h_val.numel() * 4
+        if compact:
+            # the compact layout's host-facing inputs: integer order quantities (uint8, the rescaled action) and sparse
+            # demand lines - 2.3x fewer bytes over PCIe than float actions + dense order rows
+            maxq = torch.tensor(env_dict["action_space"]["params"]["max_order_quantities"], dtype=torch.float64, device=dev)
+            h_act = [torch.round((a.to(torch.float64) + 1.0) * 0.5 * maxq).clamp_(0, 255).to(torch.uint8).cpu().pin_memory()
+                     for a in actions[:n_host]]
+            h_off = [dm.offsets.cpu().pin_memory() for dm in demand[:n_host]]
+            h_lines = [dm.lines.cpu().pin_memory() for dm in demand[:n_host]]
+            h_n = [dm.n_rounds for dm in demand[:n_host]]
+            hr = HostRollout(env, max_rounds_per_step=max(h_n))
+            seg_in = ([h_act[i] for i in idx], [h_off[i] for i in idx], [h_lines[i] for i in idx], [h_n[i] for i in idx])
+            run = hr.run_lines
+            h2d_seg = sum(h_act[i].numel() + h_off[i].numel() * 4 + h_n[i] * 64 for i in idx) + h_val.numel() * 4
+            api = ("marlsc_env_rollout_host (pinned host uint8 order quantities + sparse demand lines in per env step, copies "
+                   "overlapped with the step kernels, rewards out) + marlsc_gae (host values in, advantages/targets out)")
+        else:
+            h_act = [a.cpu().pin_memory() for a in actions[:n_host]]
+            h_off = [dm.offsets.cpu().pin_memory() for dm in dense_demand[:n_host]]
+            h_reg = [dm.region.cpu().pin_memory() for dm in dense_demand[:n_host]]
+            h_qty = [dm.qty.cpu().pin_memory() for dm in dense_demand[:n_host]]
+            h_n = [dm.n_orders for dm in dense_demand[:n_host]]
+            hr = HostRollout(env, max(h_n))
+            seg_in = ([h_act[i] for i in idx], [h_off[i] for i in idx], [h_reg[i] for i in idx], [h_qty[i] for i in idx],
+                      [h_n[i] for i in idx])
+            run = hr.run
+            h2d_seg = sum(h_act[i].numel() * 4 + h_off[i].numel() * 4 + h_n[i] * (2 + S) for i in idx) + h_val.numel() * 4
+            api = ("marlsc_env_rollout_host (pinned host actions+orders in per env step, copies overlapped with the "
+                   "step kernels, rewards out) + marlsc_gae (host values in, advantages/targets out)")
         d2h_seg = SEG * E * W * 4 + 2 * h_adv.numel() * 4
 
-        def host_segment():
+        def host_segment(obs_host=None):
             if env.timestep + SEG > env.episode_length:
                 env.reset(obs_out=obs_buf[0])
-            hr.run(*seg_in, h_rew, rewards)                       # SEG steps: host actions+orders in, rewards out
+            run(*seg_in, h_rew, rewards, obs_host=obs_host)          # SEG steps: host actions+demand in, rewards out
             values.copy_(h_val, non_blocking=True)
             compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
             h_adv.copy_(adv, non_blocking=True)
             h_tgt.copy_(tgt, non_blocking=True)
             torch.cuda.synchronize()
 
+        def timed(fn, n):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tm = torch.tensor([dt], device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dt = float(tm.item())
+            return dt
+
         e2e_steps = max(1, min(args.steps, 3))
         host_segment()
         launches_e2e0 = L.marlsc_launch_count()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            host_segment()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tm = torch.tensor([dt], device=dev)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
+        dt = timed(host_segment, e2e_steps)
         e2e = dict(value=E * W * SEG * e2e_steps * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d_seg),
                    d2h_bytes_per_step=int(d2h_seg), ms_per_step=1e3 * dt / e2e_steps,
-                   api="marlsc_env_rollout_host (pinned host actions+orders in per env step, copies overlapped with the "
-                       "step kernels, rewards out) + marlsc_gae (host values in, advantages/targets out)",
+                   h2d_gbs_per_gpu=h2d_seg * e2e_steps / dt / 1e9, api=api,
                    segments=e2e_steps, gpu_launches=int(L.marlsc_launch_count() - launches_e2e0))
+        # the same with every step's observations copied back to the host (what a host-side policy would need):
+        # 4*W*obs_dim bytes per env step device->host, PCIe-bound by construction
+        try:
+            h_obs = [torch.empty((E, W, env.obs_dim)).pin_memory() for _ in range(2)]
+            obs_list = [h_obs[i & 1] for i in range(SEG)]
+            dt = timed(lambda: host_segment(obs_list), 1)
+            e2e_obs = dict(value=E * W * SEG * world / dt, unit=UNIT, ms_per_step=1e3 * dt,
+                           d2h_bytes_per_step=int(d2h_seg + SEG * E * W * env.obs_dim * 4),
+                           d2h_gbs_per_gpu=(d2h_seg + SEG * E * W * env.obs_dim * 4) / dt / 1e9,
+                           note="rewards AND observations [E,W,obs_dim] float32 copied to pinned host memory every env step")
+            del h_obs
+        except RuntimeError as ex:                                   # pinned allocation of 2 x 3.1 GB refused
+            e2e_obs = dict(unavailable=str(ex)[:120])
 
     # ---- everything on the device: base-stock policy kernel (K5) -> Poisson demand kernel (K4) -> K1 ------
     on_device = None
@@ -463,7 +517,8 @@ def run_ours(args):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-    b_env = algorithmic_bytes_per_env_step(W, S, env.max_expected_lead_time, env.obs_dim, mean_orders)
+    b_env = algorithmic_bytes_per_env_step(W, S, env.max_expected_lead_time, env.obs_dim, mean_orders,
+                                           layout=env.layout, mean_lines=mean_lines)
     k1_avg_ms = statistics.mean(k1_ms)
     achieved = b_env * E / (k1_avg_ms * 1e-3) / 1e9
     traffic = None
@@ -471,7 +526,7 @@ def run_ours(args):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if tj.get("envs") == E and tj.get("workload") == args.workload:
+            if tj.get("envs") == E and tj.get("workload") == args.workload and tj.get("layout", "wide") == env.layout:
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -488,6 +543,8 @@ def run_ours(args):
                      ("env_alloc_warp_kernel (K1b)", 8 * WS + mean_orders * (S + 2) + 8 * W, "issue"),
                      ("env_feature_kernel (K1c)", 4 * WS * 7 + 4 * W * (od - Lmax * S) + 8 * W, "hbm"),
                      ("env_reward_kernel (K1d)", 20 * W + 1, "latency")]
+        elif compact:
+            parts = [("env_step_compact_kernel (fused K1, csrc/env_compact.cu)", b_env, "hbm")]
         else:
             parts = [("env_step_kernel (fused K1)", b_env, "hbm")]
         for (name, b, bound), t_ms in zip(parts, ms):
@@ -495,6 +552,7 @@ def run_ours(args):
                                 achieved=b * E / (t_ms * 1e-3) / 1e9, frac=b * E / (t_ms * 1e-3) / 1e9 / peak))
     roofline = dict(bound="hbm",
                     kernel=("env step K1 = place + allocate + features + rewards launches (csrc/env_split.cuh)" if split
+                            else "env_step_compact_kernel (K1, one fused launch per env step, csrc/env_compact.cu)" if compact
                             else "env_step_kernel (K1)"),
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_env_step=b_env, k1_ms_per_launch=k1_avg_ms,
@@ -521,15 +579,19 @@ def run_ours(args):
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="int32 state / fp32 obs+GAE / fp64 cost sums", data="synthetic",
+                dtype=("uint16 stock+history, uint8 ring / fp32 obs+GAE / fp64 cost sums" if compact
+                       else "int32 state / fp32 obs+GAE / fp64 cost sums"), data="synthetic",
                 config=dict(cfg_desc, envs_per_gpu=E, segment_env_steps=SEG, gamma=GAMMA, lam=LAM, team_size=env.team_size,
-                            mean_orders_per_env_step=mean_orders,
+                            mean_orders_per_env_step=mean_orders, layout=env.layout,
+                            demand_format=(f"sparse lines, {mean_lines:.0f} per env step (2 bytes each)" if compact
+                                           else "dense order rows (S + 2 bytes per order)"),
                             actions=(f"pre-sampled base-stock heuristic z={args.z} (recorded once, replayed)" if args.policy == "base_stock"
                                      else f"uniform{ACTION_RANGE}"),
                             l2="inputs larger than L2 (per-step state+obs far exceeds 126 MB)" if args.workload == "large"
                             else "small working set; L2 resident (launch-latency bound)",
                             distinct_input_steps=n_in),
-                roofline=roofline, roofline_gae=roofline_gae, cpu_baseline=cpu, e2e=e2e, on_device_pipeline=on_device, gpu_launches=int(launches), clocks=clk)
+                roofline=roofline, roofline_gae=roofline_gae, cpu_baseline=cpu, e2e=e2e, e2e_with_observations=e2e_obs,
+                on_device_pipeline=on_device, gpu_launches=int(launches), clocks=clk)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -623,6 +685,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--team", type=int, default=0, help="threads per env (0 = auto)")
     ap.add_argument("--fused", action="store_true", help="keep the step in the single fused kernel (comparison)")
+    ap.add_argument("--layout", default=None, choices=["wide", "compact"], help="state layout (default: compact where the config qualifies)")
     ap.add_argument("--distinct-steps", type=int, default=8, help="uniform policy: distinct pre-sampled input steps cycled through")
     ap.add_argument("--policy", default="base_stock", choices=["base_stock", "uniform"],
                     help="pre-sampled actions: recorded base-stock heuristic (default) or uniform noise")

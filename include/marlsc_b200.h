@@ -117,7 +117,7 @@ typedef struct marlsc_env marlsc_env_t; /* opaque handle */
  * (marlsc_env_layout() tells which one a handle uses; marlsc_env_set_layout() can force WIDE before the first reset):
  * fixed lead times, direct action space with order maxima <= 255, unit SKU weights, no outbound fixed costs, static
  * warehouse priority, non-binding split limit, inventory / pipeline / home-demand / rolling-mean feature blocks,
- * normalisation off or fixed mean-std, 32 < S <= 128 (even), W <= 16, R <= 64, L <= 16. The caller guarantees
+ * normalisation off or fixed mean-std, 32 < S <= 128 (a multiple of 4), W <= 16, R <= 64, L <= 16. The caller guarantees
  * on-hand stock stays below 65536 (initial stock + episode_length * max order quantity bounds it).
  */
 enum { MARLSC_LAYOUT_WIDE = 0, MARLSC_LAYOUT_COMPACT = 1 };
@@ -180,10 +180,12 @@ typedef struct marlsc_step_io {
   /* Sparse demand ("lines"), the native input of the COMPACT layout: the non-zero (order, SKU) cells of the step's orders
    * (region ids already mapped through region_map), regrouped into 32 streams per environment. Stream l holds the cells
    * of SKUs s with s % 32 == l in the order the reference allocator meets them (order index ascending, then SKU); entry =
-   * quantity (1..255) | region << 8 | (s / 32) << 14, 0 = padding. Streams are stored round-major, lines[round][l], and an
-   * environment owns rounds [line_offsets[e], line_offsets[e+1]) - or, in the padded layout (line_counts != NULL),
-   * rounds [e*line_stride, e*line_stride + line_counts[e]). Streams shorter than the environment's round count are padded
-   * with 0 at their end. When lines != NULL the order_* fields are ignored; a COMPACT handle given dense orders converts
+   * quantity (1..255) | region << 8 | (s / 32) << 14, 0 = padding. A "round" is one entry of each of the 32 streams
+   * (64 bytes); rounds come in pairs: entries 2i and 2i+1 of stream l are the low and high half of 32-bit word l of pair
+   * i, i.e. entry p of stream l is uint16 lines[(r0 + (p & ~1)) * 32 + 2 l + (p & 1)] for an environment whose rounds
+   * start at r0. An environment owns the (even number of) rounds [line_offsets[e], line_offsets[e+1]) - or, in the
+   * padded layout (line_counts != NULL, line_stride even), rounds [e*line_stride, e*line_stride + line_counts[e]).
+   * Streams shorter than the environment's round count are padded with 0 at their end. When lines != NULL the order_* fields are ignored; a COMPACT handle given dense orders converts
    * them with marlsc_lines_from_orders into a library-owned buffer first. WIDE handles take dense orders only.
    * Build lines on the host with marlsc_b200.demand.pack_lines, on the device with marlsc_lines_from_orders or
    * marlsc_demand_sample_lines. */
@@ -259,6 +261,12 @@ typedef struct marlsc_host_step {
   const uint8_t* actual_lead;    /* host [E,W,S] or NULL */
   float* rewards;                /* host [E,W] */
   float* obs;                    /* host [E,W,obs_dim] or NULL */
+  /* COMPACT layout: sparse demand lines instead of dense orders, integer quantities instead of float actions
+   * (see marlsc_step_io); the staging sets then need lines / line_offsets / action_qty device buffers */
+  const uint16_t* lines;         /* host [n_rounds,32] or NULL */
+  const int32_t* line_offsets;   /* host [E+1] */
+  int64_t n_rounds;
+  const uint8_t* action_qty;     /* host [E,W,S] or NULL */
 } marlsc_host_step_t;
 int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* dev_staging,
                          const marlsc_host_step_t* host, int32_t t, void* stream);

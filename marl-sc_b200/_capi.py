@@ -65,7 +65,8 @@ class StepIOC(C.Structure):
 class HostStepC(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("order_offsets", C.c_void_p), ("order_region", C.c_void_p),
                 ("order_qty", C.c_void_p), ("n_orders", C.c_int64), ("actual_lead", C.c_void_p),
-                ("rewards", C.c_void_p), ("obs", C.c_void_p)]
+                ("rewards", C.c_void_p), ("obs", C.c_void_p), ("lines", C.c_void_p), ("line_offsets", C.c_void_p),
+                ("n_rounds", C.c_int64), ("action_qty", C.c_void_p)]
 
 
 class MarlscError(RuntimeError):

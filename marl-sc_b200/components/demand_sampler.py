@@ -77,14 +77,56 @@ class PoissonDemandSampler(BaseDemandSampler):
 
 
 class EmpiricalDemandSampler(BaseDemandSampler):
-    """Replays a preprocessed demand frame (reference :166-271). The raw data set is not shipped with
-    the reference, so construction fails the same way the reference does without preprocessed data."""
+    """Replays a random contiguous window of a preprocessed demand frame (reference :166-271): the window start is one
+    ``rng.integers(0, n_timesteps - episode_length + 1)`` draw per episode (:226-229), the orders of a step are the frame's
+    rows of that timestep grouped by ``(region_id, order_id)`` (:247-258). The frame is grouped once at construction
+    (``marlsc_b200.data.pack_demand_frame``); ``sample`` only slices. The reference's raw data set is not shipped, so the
+    frame comes from the caller (``env_meta["preprocessed_data"]``); without one construction fails like the reference's."""
 
     def __init__(self, context: EnvironmentContext, component_config: DemandSamplerConfig):
         super().__init__(context, component_config)
-        if context.preprocessed_data is None:
+        self.episode_length = context.episode_length
+        pre = context.preprocessed_data
+        if pre is None:
             raise ValueError("EmpiricalDemandSampler requires preprocessed_data. "
                              "Ensure real_world data source is configured and preprocessing is enabled.")
+        from ..data import pack_demand_frame
+        use_val = context.data_mode == "val" and getattr(pre, "val_demand_data", None) is not None
+        self.data = pre.val_demand_data if use_val else pre.demand_data
+        cache = getattr(pre, "_packed", None)                      # E samplers of a batch share one packed frame
+        if cache is None:
+            cache = {}
+            try:
+                pre._packed = cache
+            except AttributeError:
+                pass
+        key = ("val" if use_val else "train", self.n_skus)
+        if key not in cache:
+            cache[key] = pack_demand_frame(self.data, self.n_skus)
+        self.frame = cache[key]
+        self.available_timesteps = [int(t) for t in self.frame.timesteps]
+        self.max_timestep = max(self.available_timesteps) if self.available_timesteps else 0
+        if len(self.available_timesteps) < self.episode_length:
+            raise ValueError(f"EmpiricalDemandSampler: episode_length ({self.episode_length}) > "
+                             f"available timesteps ({len(self.available_timesteps)}). "
+                             "Episode length must be <= number of available timesteps.")
+        self._start_index: Optional[int] = None
+
+    def start_index(self) -> int:
+        """Index (into ``available_timesteps``) of this episode's window start; drawn on first use like the reference."""
+        if self._start_index is None:
+            max_start_idx = len(self.available_timesteps) - self.episode_length
+            self._start_index = int(self._rng.integers(0, max_start_idx + 1))
+        return self._start_index
+
+    def sample(self, timestep: int) -> List[Order]:
+        k = self.start_index() + timestep % self.episode_length
+        region, qty = self.frame.orders(k)
+        return [Order(region_id=int(r), sku_demands=q.astype(float)) for r, q in zip(region, qty)]
+
+    def reset(self, rng: Optional[np.random.Generator] = None):
+        super().reset(rng)
+        self._start_index = None
 
 
 class ReplayDemandSampler(BaseDemandSampler):

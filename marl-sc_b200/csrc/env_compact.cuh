@@ -35,7 +35,7 @@ constexpr int kCompactMaxL = 16;
 // shared memory of the step kernel: [perm5 | prio16 | home_wh | warp 0 | warp 1 | ...], byte offsets
 struct CompactSmem {
   int t_perm, t_prio, t_home, t_bytes;          // per CTA
-  int inv, shipq, lostU, lostP, warp_bytes;     // per warp, from the warp's base
+  int inv, shipq, lostU, lostP, avail, ring, warp_bytes;     // per warp, from the warp's base
 };
 __host__ __device__ inline CompactSmem compact_smem(int W, int S, int R, int nch, int pen_uniform) {
   CompactSmem l;
@@ -49,6 +49,8 @@ __host__ __device__ inline CompactSmem compact_smem(int W, int S, int R, int nch
   l.inv = o; o += (W * S * 2 + 15) & ~15;
   l.shipq = o; o += W * R * 4;
   l.lostU = o; o += R * 4;
+  l.avail = o;                                      // (unused: availability masks live in registers)
+  l.ring = o;                                       // (unused: the line words in flight live in registers)
   l.warp_bytes = (o + 15) & ~15;
   return l;
 }
@@ -57,6 +59,8 @@ __host__ __device__ inline CompactSmem compact_smem(int W, int S, int R, int nch
 __host__ __device__ inline uint16_t line_entry(int qty, int region, int slot) { return (uint16_t)(qty | (region << 8) | (slot << 14)); }
 
 int launch_step_compact(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s);
+struct SplitWork;
+int launch_split_compact(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitWork& wk, int t, cudaStream_t s);
 int launch_reset_compact(const LaunchArgs& a, const int32_t* init, int per_env, float* obs, cudaStream_t s);
 int launch_base_stock_compact(const DevSpec& ds, const marlsc_env_state_t& st, const float* level, int level_per_env, int t,
                               float* actions, cudaStream_t s);

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -164,9 +165,9 @@ bool compact_eligible(const DevSpec& ds, const HostTables& tb) {
   const uint32_t caps = required_caps(ds, tb, nullptr) & ~C_REGMAP;    // the region map is applied when lines are built
   if (caps & ~kCapsLean) return false;
   if (ds.dh_mode == 2) return false;                                    // home-demand block without a history plane
-  if (ds.S <= 32 || ds.S > kCompactMaxS || (ds.S & 1)) return false;
+  if (ds.S <= 32 || ds.S > kCompactMaxS || (ds.S & 3)) return false;      // rows are read as 32-bit words of four cells
   if (ds.W > kCompactMaxW || ds.R > kCompactMaxR || ds.L > kCompactMaxL || !ds.perm5) return false;
-  for (double v : tb.action_max) if (!(v >= 0.0 && v <= 255.0)) return false;
+  for (double v : tb.action_max) if (!(v >= 0.0 && v <= 255.0) || v != (double)(int)v) return false;
   return true;
 }
 
@@ -288,6 +289,9 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   env->ds.prio16 = t.prio16.empty() ? nullptr : b + o_p16;
   env->ds.home_wh = b + o_hw;
   env->ds.compact_ok = compact_eligible(env->ds, env->tb) ? 1 : 0;
+  // cp.async.bulk.prefetch.L2 wants 16-byte aligned addresses and sizes: true for every environment's block when the
+  // smallest one (W*S bytes of uint8 quantities) is a multiple of 16 (MARLSC_NO_PREFETCH=1 switches them off for A/B runs)
+  env->ds.compact_prefetch = ((env->ds.W * env->ds.S) % 16 == 0 && !std::getenv("MARLSC_NO_PREFETCH")) ? 1 : 0;
   env->layout = env->ds.compact_ok ? MARLSC_LAYOUT_COMPACT : MARLSC_LAYOUT_WIDE;
   *out = env;
   return MARLSC_OK;
@@ -327,7 +331,7 @@ int marlsc_env_set_layout(marlsc_env_t* env, int32_t layout) {
 
 int marlsc_env_set_line_stride(marlsc_env_t* env, int32_t rounds) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
-  if (rounds < 1 || rounds > 4096) return set_error(MARLSC_EINVAL, "line stride must be in [1, 4096]");
+  if (rounds < 2 || rounds > 4096 || (rounds & 1)) return set_error(MARLSC_EINVAL, "line stride must be even and in [2, 4096]");
   if (env->d_lines) {
     MARLSC_CUDA(cudaSetDevice(env->device));
     MARLSC_CUDA(cudaDeviceSynchronize());
@@ -360,8 +364,7 @@ int marlsc_env_set_generic(marlsc_env_t* env, int32_t on) {
 
 int marlsc_env_set_fused(marlsc_env_t* env, int32_t on) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
-  if (on && env->layout == MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "force MARLSC_LAYOUT_WIDE first: the compact layout has one kernel");
-  env->force_fused = on ? 1 : 0;
+  env->force_fused = on ? 1 : 0;                       // compact layout: the single fused kernel instead of the split step
   return MARLSC_OK;
 }
 
@@ -417,7 +420,7 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   if (io->lines) {
     if (env->layout != MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "io.lines needs a handle with the COMPACT layout");
     if (!io->line_offsets && !io->line_counts) return set_error(MARLSC_EINVAL, "io.lines needs io.line_offsets or io.line_counts");
-    if (io->line_counts && io->line_stride < 1) return set_error(MARLSC_EINVAL, "line_stride must be positive with line_counts");
+    if (io->line_counts && (io->line_stride < 2 || (io->line_stride & 1))) return set_error(MARLSC_EINVAL, "line_stride must be positive and even with line_counts");
   } else if (!io->order_offsets && !io->order_counts) {
     return set_error(MARLSC_EINVAL, "one of io.lines / io.order_offsets / io.order_counts must not be NULL");
   }
@@ -449,6 +452,15 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
       ioc.line_stride = env->line_stride;
       if (env->timing) MARLSC_CUDA(cudaEventRecord(env->marks[n_marks], s));
       ++n_marks;
+    }
+    if (!env->force_fused && state->num_envs * (int64_t)env->ds.W < (int64_t)0xffffffffLL) {
+      // the step as row / environment kernels (K1a' place, K1b' allocate, K1c' features, K1d rewards)
+      rc = ensure_work(env, state->num_envs);
+      if (rc) return rc;
+      const SplitWork wk{env->d_work, env->d_work + (size_t)env->work_envs * env->ds.W,
+                         (env->timing && io->lines) ? env->marks : nullptr};
+      env->timed_launches = (env->timing && io->lines) ? 4 : 0;
+      return launch_split_compact(lc, ioc, wk, t, s);
     }
     rc = launch_step_compact(lc, ioc, t, s);
     if (rc) return rc;
@@ -487,31 +499,69 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   MARLSC_DISPATCH_G(team, launch_step_g, spl, la, *io, t, s)
 }
 
+}  // extern "C" (host-buffer entry points follow their staging helper)
+
+namespace {
+
+// Host -> device copies of one step's inputs into a staging set (on stream cp); returns the io the step should use.
+int stage_host_step(marlsc_env* env, const marlsc_env_state_t* state, const marlsc_step_io_t& dv, const marlsc_host_step_t& h,
+                    cudaStream_t cp, marlsc_step_io_t* io_out) {
+  const int64_t E = state->num_envs, WS = (int64_t)env->ds.W * env->ds.S;
+  if (!h.rewards || (!h.actions && !h.action_qty)) return set_error(MARLSC_EINVAL, "host step with NULL rewards or without actions");
+  marlsc_step_io_t io = dv;
+  if (h.action_qty) {
+    if (!dv.action_qty) return set_error(MARLSC_EINVAL, "host.action_qty needs a staging set with an action_qty buffer");
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(dv.action_qty), h.action_qty, (size_t)E * WS, cudaMemcpyHostToDevice, cp));
+    io.actions = nullptr;
+  } else {
+    if (!dv.actions) return set_error(MARLSC_EINVAL, "host.actions needs a staging set with an actions buffer");
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<float*>(dv.actions), h.actions, sizeof(float) * E * WS, cudaMemcpyHostToDevice, cp));
+    io.action_qty = nullptr;
+  }
+  if (h.lines) {
+    if (!dv.lines || !dv.line_offsets || !h.line_offsets) return set_error(MARLSC_EINVAL, "host.lines needs host.line_offsets and staging lines / line_offsets buffers");
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(dv.line_offsets), h.line_offsets, sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice, cp));
+    if (h.n_rounds > 0)
+      MARLSC_CUDA(cudaMemcpyAsync(const_cast<uint16_t*>(dv.lines), h.lines, (size_t)h.n_rounds * 64, cudaMemcpyHostToDevice, cp));
+    io.line_counts = nullptr;
+  } else {
+    if (!h.order_offsets) return set_error(MARLSC_EINVAL, "host step without order_offsets or lines");
+    if (h.n_orders > 0 && (!h.order_region || !h.order_qty)) return set_error(MARLSC_EINVAL, "host order arrays are NULL");
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(dv.order_offsets), h.order_offsets, sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice, cp));
+    if (h.n_orders > 0) {
+      MARLSC_CUDA(cudaMemcpyAsync(const_cast<int16_t*>(dv.order_region), h.order_region, sizeof(int16_t) * h.n_orders, cudaMemcpyHostToDevice, cp));
+      MARLSC_CUDA(cudaMemcpyAsync(const_cast<void*>(dv.order_qty), h.order_qty, (size_t)h.n_orders * env->ds.S * dv.order_qty_bytes, cudaMemcpyHostToDevice, cp));
+    }
+    io.lines = nullptr;
+    io.order_counts = nullptr;
+  }
+  if (env->ds.lead_mode == MARLSC_LEAD_STOCHASTIC) {
+    if (!h.actual_lead) return set_error(MARLSC_EINVAL, "host.actual_lead is required with a stochastic lead-time sampler");
+    MARLSC_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(dv.actual_lead), h.actual_lead, (size_t)E * WS, cudaMemcpyHostToDevice, cp));
+  }
+  *io_out = io;
+  return MARLSC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int marlsc_env_step_host(marlsc_env_t* env, const marlsc_env_state_t* state, const marlsc_step_io_t* dev,
                          const marlsc_host_step_t* host, int32_t t, void* stream) {
   int rc = check_state(env, state);
   if (rc) return rc;
   if (!dev || !host) return set_error(MARLSC_EINVAL, "null staging or host descriptor");
-  if (!host->actions || !host->order_offsets || !host->rewards) return set_error(MARLSC_EINVAL, "host.actions / order_offsets / rewards are NULL");
-  if (host->n_orders > 0 && (!host->order_region || !host->order_qty)) return set_error(MARLSC_EINVAL, "host order arrays are NULL");
   MARLSC_CUDA(cudaSetDevice(env->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t E = state->num_envs, WS = (int64_t)env->ds.W * env->ds.S;
-  MARLSC_CUDA(cudaMemcpyAsync(const_cast<float*>(dev->actions), host->actions, sizeof(float) * E * WS, cudaMemcpyHostToDevice, s));
-  MARLSC_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(dev->order_offsets), host->order_offsets, sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice, s));
-  if (host->n_orders > 0) {
-    MARLSC_CUDA(cudaMemcpyAsync(const_cast<int16_t*>(dev->order_region), host->order_region, sizeof(int16_t) * host->n_orders, cudaMemcpyHostToDevice, s));
-    MARLSC_CUDA(cudaMemcpyAsync(const_cast<void*>(dev->order_qty), host->order_qty,
-                                (size_t)host->n_orders * env->ds.S * dev->order_qty_bytes, cudaMemcpyHostToDevice, s));
-  }
-  if (env->ds.lead_mode == MARLSC_LEAD_STOCHASTIC) {
-    if (!host->actual_lead) return set_error(MARLSC_EINVAL, "host.actual_lead is required with a stochastic lead-time sampler");
-    MARLSC_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(dev->actual_lead), host->actual_lead, (size_t)E * WS, cudaMemcpyHostToDevice, s));
-  }
-  rc = marlsc_env_step(env, state, dev, t, stream);
+  const int64_t E = state->num_envs;
+  marlsc_step_io_t io;
+  rc = stage_host_step(env, state, *dev, *host, s, &io);
   if (rc) return rc;
-  MARLSC_CUDA(cudaMemcpyAsync(host->rewards, dev->rewards, sizeof(float) * E * env->ds.W, cudaMemcpyDeviceToHost, s));
-  if (host->obs) MARLSC_CUDA(cudaMemcpyAsync(host->obs, dev->obs, sizeof(float) * E * env->ds.W * env->ds.obs_dim, cudaMemcpyDeviceToHost, s));
+  rc = marlsc_env_step(env, state, &io, t, stream);
+  if (rc) return rc;
+  MARLSC_CUDA(cudaMemcpyAsync(host->rewards, io.rewards, sizeof(float) * E * env->ds.W, cudaMemcpyDeviceToHost, s));
+  if (host->obs) MARLSC_CUDA(cudaMemcpyAsync(host->obs, io.obs, sizeof(float) * E * env->ds.W * env->ds.obs_dim, cudaMemcpyDeviceToHost, s));
   MARLSC_CUDA(cudaStreamSynchronize(s));
   return MARLSC_OK;
 }
@@ -531,30 +581,19 @@ int marlsc_env_rollout_host(marlsc_env_t* env, const marlsc_env_state_t* state, 
     }
   }
   cudaStream_t cs = static_cast<cudaStream_t>(stream), cp = env->copy_stream;
-  const int64_t E = state->num_envs, WS = (int64_t)env->ds.W * env->ds.S, W = env->ds.W;
-  const bool stoch = env->ds.lead_mode == MARLSC_LEAD_STOCHASTIC;
+  const int64_t E = state->num_envs, W = env->ds.W;
   // the copy stream must not run ahead of work already queued on the caller's stream
   MARLSC_CUDA(cudaEventRecord(env->done[0], cs));
   MARLSC_CUDA(cudaEventRecord(env->done[1], cs));
   for (int i = 0; i < n_steps; ++i) {
     const int b = i & 1;
-    const marlsc_step_io_t& dv = staging[b];
     const marlsc_host_step_t& h = host[i];
-    if (!h.actions || !h.order_offsets || !h.rewards) return set_error(MARLSC_EINVAL, "host step with NULL actions / offsets / rewards");
     MARLSC_CUDA(cudaStreamWaitEvent(cp, env->done[b], 0));      // staging set b is free again
-    MARLSC_CUDA(cudaMemcpyAsync(const_cast<float*>(dv.actions), h.actions, sizeof(float) * E * WS, cudaMemcpyHostToDevice, cp));
-    MARLSC_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(dv.order_offsets), h.order_offsets, sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice, cp));
-    if (h.n_orders > 0) {
-      MARLSC_CUDA(cudaMemcpyAsync(const_cast<int16_t*>(dv.order_region), h.order_region, sizeof(int16_t) * h.n_orders, cudaMemcpyHostToDevice, cp));
-      MARLSC_CUDA(cudaMemcpyAsync(const_cast<void*>(dv.order_qty), h.order_qty, (size_t)h.n_orders * env->ds.S * dv.order_qty_bytes, cudaMemcpyHostToDevice, cp));
-    }
-    if (stoch) {
-      if (!h.actual_lead) return set_error(MARLSC_EINVAL, "host.actual_lead is required with a stochastic lead-time sampler");
-      MARLSC_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(dv.actual_lead), h.actual_lead, (size_t)E * WS, cudaMemcpyHostToDevice, cp));
-    }
+    marlsc_step_io_t io;
+    rc = stage_host_step(env, state, staging[b], h, cp, &io);
+    if (rc) return rc;
     MARLSC_CUDA(cudaEventRecord(env->ready[b], cp));
     MARLSC_CUDA(cudaStreamWaitEvent(cs, env->ready[b], 0));
-    marlsc_step_io_t io = dv;
     io.rewards = rewards_dev + (int64_t)i * E * W;
     rc = marlsc_env_step(env, state, &io, t0 + i, stream);
     if (rc) return rc;
@@ -565,6 +604,10 @@ int marlsc_env_rollout_host(marlsc_env_t* env, const marlsc_env_state_t* state, 
   MARLSC_CUDA(cudaStreamSynchronize(cs));
   return MARLSC_OK;
 }
+
+}  // extern "C"
+
+extern "C" {
 
 int marlsc_policy_base_stock(marlsc_env_t* env, const marlsc_env_state_t* state, const float* level, int32_t t,
                              float* actions, void* stream) {
@@ -594,7 +637,7 @@ int marlsc_lines_from_orders(marlsc_env_t* env, int64_t num_envs, const marlsc_s
                              uint16_t* lines, int32_t* line_counts, int32_t* overflow_flag, void* stream) {
   if (!env || !orders || !lines || !line_counts || !overflow_flag) return set_error(MARLSC_EINVAL, "null argument");
   if (!env->ds.compact_ok) return set_error(MARLSC_EUNSUPPORTED, "lines exist for configurations that qualify for the compact layout");
-  if (num_envs < 1 || line_stride < 1) return set_error(MARLSC_EINVAL, "num_envs and line_stride must be positive");
+  if (num_envs < 1 || line_stride < 2 || (line_stride & 1)) return set_error(MARLSC_EINVAL, "num_envs must be positive and line_stride positive and even");
   if (!orders->order_offsets && !orders->order_counts) return set_error(MARLSC_EINVAL, "orders need order_offsets or order_counts");
   if (orders->order_qty_bytes != 1) return set_error(MARLSC_EUNSUPPORTED, "lines carry one-byte quantities");
   MARLSC_CUDA(cudaSetDevice(env->device));

@@ -166,7 +166,7 @@ sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t 
   const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
-  uint16_t* out = lines + e * (long long)stride * 32 + lane;
+  uint16_t* out = lines + e * (long long)stride * 32 + 2 * lane;     // entry p of this lane: out[(p >> 1) * 64 + (p & 1)]
   int row = 0, cnt = 0;
   bool over = false;
   for (int r0 = 0; r0 < R; r0 += 32) {
@@ -195,7 +195,7 @@ sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t 
               if (ub < p) {
                 int q = quantity_from(dp.cdf_qty + (size_t)(rr * S + s) * kCdf, dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
                 q = q < 1 ? 1 : (q > 255 ? 255 : q);
-                if (cnt < stride) out[(long long)cnt * 32] = (uint16_t)(q | (rm << 8) | (j << 14));
+                if (cnt < stride) out[(long long)(cnt >> 1) * 64 + (cnt & 1)] = (uint16_t)(q | (rm << 8) | (j << 14));
                 else over = true;
                 ++cnt;
               }
@@ -207,8 +207,8 @@ sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t 
     }
   }
   cnt = cnt < stride ? cnt : stride;
-  const int rounds = __reduce_max_sync(0xffffffffu, cnt);
-  for (int c = cnt; c < rounds; ++c) out[(long long)c * 32] = 0;     // pad this stream to the environment's round count
+  const int rounds = (__reduce_max_sync(0xffffffffu, cnt) + 1) & ~1;  // whole round pairs
+  for (int c = cnt; c < rounds; ++c) out[(long long)(c >> 1) * 64 + (c & 1)] = 0;     // pad this stream to the environment's round count
   if (lane == 0) counts[e] = rounds;
   if (over) atomicExch(overflow, 1);
 }
@@ -429,7 +429,7 @@ int marlsc_demand_sample_lines(marlsc_demand_t* d, int64_t num_envs, uint64_t se
                                const int32_t* region_map, uint16_t* lines, int32_t* line_counts, int32_t* overflow_flag,
                                void* stream) {
   if (!d || !lines || !line_counts || !overflow_flag) return set_error(MARLSC_EINVAL, "null argument");
-  if (num_envs < 1 || line_stride < 1) return set_error(MARLSC_EINVAL, "num_envs and line_stride must be positive");
+  if (num_envs < 1 || line_stride < 2 || (line_stride & 1)) return set_error(MARLSC_EINVAL, "num_envs must be positive and line_stride positive and even");
   if (d->S > 128) return set_error(MARLSC_EUNSUPPORTED, "lines address at most 128 SKUs");
   if (!region_map && d->R > 64) return set_error(MARLSC_EUNSUPPORTED, "lines address at most 64 regions");
   MARLSC_CUDA(cudaSetDevice(d->device));

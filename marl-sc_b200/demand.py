@@ -69,7 +69,8 @@ LINE_LANES = 32
 @dataclass
 class LineBatch:
     offsets: np.ndarray   # [E+1] int32, in rounds
-    lines: np.ndarray     # [n_rounds_pad, 32] uint16: qty | region << 8 | (sku // 32) << 14, 0 = padding
+    lines: np.ndarray     # [n_rounds_pad, 32] uint16 storage: qty | region << 8 | (sku // 32) << 14, 0 = padding; the entries
+                          # 2i, 2i+1 of lane l are the two halves of 32-bit word l of round pair i (see marlsc_b200.h)
     n_lines: int          # non-zero (order, SKU) cells
 
     @property
@@ -103,10 +104,13 @@ def pack_lines(batch: OrderBatch, region_map: Optional[Sequence[int]] = None) ->
     starts = np.cumsum(counts) - counts
     pos = np.arange(stream_sorted.shape[0]) - starts[stream_sorted]      # position inside the stream
     rounds = counts.reshape(E, LINE_LANES).max(axis=1) if E else np.zeros(0, np.int64)
+    rounds = (rounds + 1) & ~1                            # whole round pairs: a lane's entries 2i, 2i+1 share a 32-bit word
     offsets = np.zeros(E + 1, dtype=np.int32)
     offsets[1:] = np.cumsum(rounds)
     total = int(offsets[-1])
-    lines = np.zeros((max(total, 1), LINE_LANES), dtype=np.uint16)
+    lines = np.zeros((max(total, 2), LINE_LANES), dtype=np.uint16)
     entry = q[order] | (region[oj[order]] << 8) | ((s[order] // LINE_LANES) << 14)
-    lines[offsets[env[order]] + pos, s[order] % LINE_LANES] = entry.astype(np.uint16)
+    # entry p of lane l of an environment starting at round r0 sits at uint16 index (r0 + (p & ~1)) * 32 + 2 l + (p & 1)
+    flat = lines.reshape(-1)
+    flat[(offsets[env[order]] + (pos & ~1)) * LINE_LANES + 2 * (s[order] % LINE_LANES) + (pos & 1)] = entry.astype(np.uint16)
     return LineBatch(offsets=offsets, lines=lines, n_lines=int(q.shape[0]))

@@ -98,7 +98,8 @@ class BatchedInventoryEnv:
         self.diagnostics = diagnostics
 
         self.spec: EnvSpec = build_env_spec(env_config, self.obs_normalization, self.obs_stats, self.include_warehouse_id,
-                                            region_map=region_map, data_mode=meta.get("data_mode", "train"))
+                                            region_map=region_map, data_mode=meta.get("data_mode", "train"),
+                                            preprocessed_data=meta.get("preprocessed_data"))
         s = self.spec.scalars
         self.max_expected_lead_time = s["max_expected_lead"]
         self.ring_depth = s["ring_depth"]
@@ -117,10 +118,11 @@ class BatchedInventoryEnv:
         if layout not in (None, "wide", "compact"):
             raise ValueError("layout must be None, 'wide' or 'compact'")
         compact = L.marlsc_env_layout(self._h) == _capi.LAYOUT_COMPACT
-        wants_wide = bool(diagnostics or team_size or generic_kernel or fused_kernel) or self._stock_bound() >= 32768
+        wants_wide = (bool(diagnostics or team_size or generic_kernel or (fused_kernel and layout != "compact"))
+                      or self._stock_bound() >= 32768)
         if layout == "compact":
             if wants_wide:
-                raise ValueError("layout='compact' excludes diagnostics / team_size / generic_kernel / fused_kernel and needs "
+                raise ValueError("layout='compact' excludes diagnostics / team_size / generic_kernel and needs "
                                  "initial stock + episode_length * max order quantity < 32768")
             _capi.check(L.marlsc_env_set_layout(self._h, _capi.LAYOUT_COMPACT))
         elif compact and (layout == "wide" or wants_wide):
@@ -175,6 +177,9 @@ class BatchedInventoryEnv:
                 lost_sales=torch.zeros((E, W, S), dtype=torch.float32, device=dev))
         self.timestep = 0
         self._seed, self._episode = seed, 0  # reproducible device-side initial stock (see _initial_inventory)
+        self._frame = None                   # empirical demand: the packed frame on the device (marlsc_b200.data)
+        self._frame_start = None             # ... and every environment's window start for the running episode
+        self._empirical = env_config.components.demand_sampler.type == "empirical"
         self._dd = None                      # device demand sampler state (enable_device_demand)
         self._dl = None                      # device lead-time sampler state (enable_device_leads)
         self._demand_step = 0
@@ -254,6 +259,31 @@ class BatchedInventoryEnv:
                                                    self._stream()))
         d["step"] += 1
         return d["actual"]
+
+    def lines_from_orders(self, orders: DeviceOrders, stride: int = 128) -> DeviceLines:
+        """Dense device orders -> sparse lines on the device (``marlsc_lines_from_orders``), compacted to the CSR form.
+        For pre-converting replayed demand once; ``step`` also accepts dense orders and converts them per call."""
+        if self.layout != "compact":
+            raise ValueError("demand lines need the compact layout")
+        E, dev = self.num_envs, self.device
+        padded = torch.empty((E, stride, 32), dtype=torch.int16, device=dev)
+        counts = torch.empty(E, dtype=torch.int32, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        io = _capi.StepIOC()
+        io.order_offsets, io.order_region, io.order_qty = orders.offsets.data_ptr(), orders.region.data_ptr(), orders.qty.data_ptr()
+        io.order_qty_bytes = orders.qty_bytes
+        _capi.check(_capi.lib().marlsc_lines_from_orders(self._h, E, C.byref(io), stride, padded.data_ptr(), counts.data_ptr(),
+                                                         flag.data_ptr(), self._stream()))
+        if int(flag.item()):
+            raise ValueError(f"a line stream needs more than {stride} rounds; raise stride")
+        offsets = torch.zeros(E + 1, dtype=torch.int32, device=dev)
+        offsets[1:] = counts.cumsum(0)
+        keep = torch.arange(stride, device=dev)[None, :] < counts[:, None]
+        lines = padded[keep]                                           # [n_rounds, 32]
+        n_rounds = int(offsets[-1].item())
+        if n_rounds == 0:
+            lines = torch.zeros((1, 32), dtype=torch.int16, device=dev)
+        return DeviceLines(offsets, lines.contiguous(), int((lines != 0).sum().item()), n_rounds)
 
     def demand_overflowed(self) -> bool:
         """True when some environment drew more orders than max_orders_per_env (the surplus was dropped)."""
@@ -388,6 +418,7 @@ class BatchedInventoryEnv:
                 for name, comp in (("demand_sampler", self.demand_samplers[i]), ("lead_time_sampler", self.lead_time_samplers[i])):
                     comp.reset(rng=sm.get_rng(name))
         self._episode += 1
+        self._frame_start = None
         if init_inventory is None:
             init, per_env = self._initial_inventory()
         else:
@@ -415,6 +446,28 @@ class BatchedInventoryEnv:
         return obs_out
 
     # ------------------------------------------------------------------ step
+    def frame_orders(self) -> DeviceOrders:
+        """This step's orders of every environment from the empirical demand frame (reference
+        components/demand_sampler.py:214-261), sliced on the device. With host samplers the window starts are the ones
+        their reference-identical NumPy streams draw; without, one device draw per episode."""
+        from ..data import DeviceDemandFrame
+        if self._frame is None:
+            from ..registry import get_demand_sampler
+            smp = self.demand_samplers[0] if self.demand_samplers else get_demand_sampler(self.env_config, context=self.spec.context)
+            self._frame = DeviceDemandFrame(smp.frame, self.episode_length, self.device)
+        if self._frame_start is None:
+            if self._host_samplers:
+                starts = torch.tensor([smp.start_index() for smp in self.demand_samplers], dtype=torch.int64)
+            else:
+                g = torch.Generator()
+                g.manual_seed((int(self._seed or 0) * 1000003 + 7919 * self._episode) & 0x7fffffffffffffff)
+                starts = torch.randint(0, self._frame.max_start() + 1, (self.num_envs,), generator=g)
+            self._frame_start = starts.to(self.device)
+        offsets, region, qty, n = self._frame.step_orders(self._frame_start, self.timestep)
+        if self._frame.qty_bytes == 2:
+            qty = qty.view(torch.int16)
+        return DeviceOrders(offsets, region, qty, n)
+
     def sample_host_demand(self) -> Tuple[OrderBatch, Optional[np.ndarray]]:
         """Draw this step's orders (and lead times) from the per-environment host samplers, in the
         reference's call order: lead times first (multi_env.py:866), then demand (:295)."""
@@ -450,6 +503,10 @@ class BatchedInventoryEnv:
             orders = self._empty_orders
         if self.stochastic_lead and actual_lead is None and self._dl is not None:
             actual_lead = self.sample_device_leads()
+        if orders is None and self._empirical:
+            orders = self.frame_orders()
+            if self.stochastic_lead and actual_lead is None:
+                actual_lead = np.stack([lt.sample() for lt in self.lead_time_samplers]).astype(np.uint8)
         if orders is None:
             host_orders, host_leads = self.sample_host_demand()
             orders = host_orders
@@ -518,13 +575,19 @@ class BatchedInventoryEnv:
 class HostRollout:
     """Rollout segments driven from HOST buffers through ``marlsc_env_rollout_host``: the reference-facing
     way to call the path (NumPy/pinned tensors in, rewards out) with the copies of step i+1 overlapped with
-    the kernel of step i. Holds the two device staging sets the C call needs."""
+    the kernel of step i. Holds the two device staging sets the C call needs.
 
-    def __init__(self, env: BatchedInventoryEnv, max_orders_per_step: int, qty_bytes: int = 1):
+    Dense orders + float actions (``run``) work with every layout; the compact layout also takes sparse demand
+    lines and integer order quantities (``run_lines``), which is 2.3x fewer bytes over PCIe at the large shape."""
+
+    def __init__(self, env: BatchedInventoryEnv, max_orders_per_step: int = 0, qty_bytes: int = 1, max_rounds_per_step: int = 0):
         self.env = env
         E, W, S, dev = env.num_envs, env.n_warehouses, env.n_skus, env.device
         self.qty_bytes = qty_bytes
         self.max_orders = int(max_orders_per_step)
+        self.max_rounds = int(max_rounds_per_step)
+        if self.max_rounds and env.layout != "compact":
+            raise ValueError("demand lines need the compact layout")
         self.sets = []
         for _ in range(2):
             self.sets.append(dict(
@@ -532,28 +595,58 @@ class HostRollout:
                 region=torch.empty(max(1, self.max_orders), dtype=torch.int16, device=dev),
                 qty=torch.empty(max(16, self.max_orders * S * qty_bytes + 16), dtype=torch.uint8, device=dev),
                 lead=torch.empty((E, W, S), dtype=torch.uint8, device=dev) if env.stochastic_lead else None,
-                obs=torch.empty_like(env.obs)))
+                obs=torch.empty_like(env.obs),
+                lines=torch.empty((max(1, self.max_rounds), 32), dtype=torch.int16, device=dev) if self.max_rounds else None,
+                line_offsets=torch.empty(E + 1, dtype=torch.int32, device=dev) if self.max_rounds else None,
+                action_qty=torch.empty((E, W, S), dtype=torch.uint8, device=dev) if self.max_rounds else None))
         self._staging = (_capi.StepIOC * 2)()
         for i, st in enumerate(self.sets):
-            self._staging[i] = _capi.StepIOC(st["actions"].data_ptr(), st["offsets"].data_ptr(), st["region"].data_ptr(),
-                                             st["qty"].data_ptr(), qty_bytes, _ptr(st["lead"]), None, st["obs"].data_ptr(),
-                                             env.truncated.data_ptr(), None, None, None, None, None, None, None)
+            io = _capi.StepIOC(st["actions"].data_ptr(), st["offsets"].data_ptr(), st["region"].data_ptr(),
+                               st["qty"].data_ptr(), qty_bytes, _ptr(st["lead"]), None, st["obs"].data_ptr(),
+                               env.truncated.data_ptr(), None, None, None, None, None, None, None)
+            io.lines, io.line_offsets, io.action_qty = _ptr(st["lines"]), _ptr(st["line_offsets"]), _ptr(st["action_qty"])
+            self._staging[i] = io
 
-    def run(self, actions, offsets, regions, qtys, n_orders, rewards_host, rewards_dev, leads=None) -> torch.Tensor:
-        """Each argument is a per-step list of (pinned) host tensors; ``rewards_host`` / ``rewards_dev`` are
-        [T,E,W] float32 (pinned host / device). Steps the env T times starting at its current timestep and
-        returns the observation buffer that holds the last step's observations."""
-        env, T = self.env, len(actions)
-        if max(n_orders) > self.max_orders:
-            raise ValueError("a step has more orders than the staging buffers hold")
+    def _call(self, hs, T, rewards_dev) -> torch.Tensor:
+        env = self.env
         if env.timestep + T > env.episode_length:
             raise ValueError("segment crosses the end of the episode; reset first")
-        hs = (_capi.HostStepC * T)()
-        for i in range(T):
-            hs[i] = _capi.HostStepC(actions[i].data_ptr(), offsets[i].data_ptr(), regions[i].data_ptr(), qtys[i].data_ptr(),
-                                    int(n_orders[i]), None if leads is None else leads[i].data_ptr(),
-                                    rewards_host[i].data_ptr(), None)
         _capi.check(_capi.lib().marlsc_env_rollout_host(env._h, C.byref(env._state), self._staging, hs, T, env.timestep,
                                                         rewards_dev.data_ptr(), env._stream()))
         env.timestep += T
         return self.sets[(T - 1) & 1]["obs"]
+
+    def run(self, actions, offsets, regions, qtys, n_orders, rewards_host, rewards_dev, leads=None, obs_host=None) -> torch.Tensor:
+        """Each argument is a per-step list of (pinned) host tensors; ``rewards_host`` / ``rewards_dev`` are
+        [T,E,W] float32 (pinned host / device); ``obs_host`` an optional per-step list of pinned [E,W,obs_dim] tensors the
+        observations are copied back into. Steps the env T times starting at its current timestep and
+        returns the observation buffer that holds the last step's observations."""
+        T = len(actions)
+        if max(n_orders) > self.max_orders:
+            raise ValueError("a step has more orders than the staging buffers hold")
+        hs = (_capi.HostStepC * T)()
+        for i in range(T):
+            hs[i] = _capi.HostStepC(actions[i].data_ptr(), offsets[i].data_ptr(), regions[i].data_ptr(), qtys[i].data_ptr(),
+                                    int(n_orders[i]), None if leads is None else leads[i].data_ptr(),
+                                    rewards_host[i].data_ptr(), None if obs_host is None else obs_host[i].data_ptr())
+        return self._call(hs, T, rewards_dev)
+
+    def run_lines(self, actions, line_offsets, lines, n_rounds, rewards_host, rewards_dev, obs_host=None) -> torch.Tensor:
+        """Compact layout: ``actions`` is a per-step list of pinned host tensors, float32 [E,W,S] actions or uint8 [E,W,S]
+        order quantities; ``line_offsets`` / ``lines`` / ``n_rounds`` the step's demand as packed by
+        ``marlsc_b200.demand.pack_lines`` (pinned int32 [E+1], int16/uint16 [n_rounds,32])."""
+        T = len(actions)
+        if max(n_rounds) > self.max_rounds:
+            raise ValueError("a step has more line rounds than the staging buffers hold")
+        hs = (_capi.HostStepC * T)()
+        for i in range(T):
+            h = _capi.HostStepC()
+            if actions[i].dtype == torch.uint8:
+                h.action_qty = actions[i].data_ptr()
+            else:
+                h.actions = actions[i].data_ptr()
+            h.lines, h.line_offsets, h.n_rounds = lines[i].data_ptr(), line_offsets[i].data_ptr(), int(n_rounds[i])
+            h.rewards = rewards_host[i].data_ptr()
+            h.obs = None if obs_host is None else obs_host[i].data_ptr()
+            hs[i] = h
+        return self._call(hs, T, rewards_dev)

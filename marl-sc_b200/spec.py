@@ -76,10 +76,11 @@ class EnvSpec:
 def build_env_spec(env_config: EnvironmentConfig, obs_normalization: str = "off",
                    obs_stats: Optional[Tuple[np.ndarray, np.ndarray]] = None, include_warehouse_id: bool = False,
                    region_map: Optional[Sequence[int]] = None, context: Optional[EnvironmentContext] = None,
-                   seed_manager=None, data_mode: str = "train") -> EnvSpec:
+                   seed_manager=None, data_mode: str = "train", preprocessed_data=None) -> EnvSpec:
     if obs_normalization not in _capi.NORM:
         raise ValueError(f"Unknown obs_normalization: {obs_normalization}. Available: {list(_capi.NORM)}")
-    ctx = context or create_environment_context(env_config, seed_manager=seed_manager, data_mode=data_mode)
+    ctx = context or create_environment_context(env_config, seed_manager=seed_manager, data_mode=data_mode,
+                                                preprocessed_data=preprocessed_data)
     comps = dict(
         demand_sampler=get_demand_sampler(env_config, context=ctx),
         demand_allocator=get_demand_allocator(env_config, context=ctx),

@@ -108,6 +108,36 @@ def make_env(cfg, seed: Optional[int], env_meta: Optional[Dict[str, Any]] = None
     return InventoryEnvironment(cfg, seed=seed, env_meta=env_meta)
 
 
+def attach_empirical_sampler(env, frame, data_mode: str = "train"):
+    """Give a reference env the reference's own EmpiricalDemandSampler over ``frame`` (columns timestep, region_id,
+    order_id, sku_id, quantity): the raw CSVs its preprocessing needs are not shipped, everything after the frame is."""
+    activate()
+    from src.data.preprocessor import PreprocessedData
+    from src.environment.components.demand_sampler import EmpiricalDemandSampler
+
+    ctx = env.context if hasattr(env, "context") else None
+    if ctx is None:
+        from src.environment.context import create_environment_context
+        ctx = create_environment_context(env.env_config)
+    ctx.preprocessed_data = PreprocessedData(demand_data=frame, val_demand_data=None)
+    ctx.data_mode = data_mode
+    ctx.episode_length = env.env_config.episode_length
+    env.demand_sampler = EmpiricalDemandSampler(ctx, None)
+    return env.demand_sampler
+
+
+def reference_map_excluded_regions(order_region_ids, warehouse_to_region_df, selected_region_ids):
+    """The reference's DataProcessor.map_excluded_regions (src/data/preprocessor.py:382-441) without its CSV-loading
+    constructor."""
+    activate()
+    from src.data.preprocessor import DataProcessor
+
+    proc = object.__new__(DataProcessor)
+    proc.warehouse_to_region_df = warehouse_to_region_df
+    proc.selected_region_ids = selected_region_ids
+    return proc.map_excluded_regions(order_region_ids)
+
+
 def derive_env_seed(base: int, worker: int, idx: int) -> int:
     activate()
     from src.utils.seed_manager import SeedManager
@@ -158,8 +188,20 @@ class ReplayDemand:
         return [self._Order(region_id=r, sku_demands=q.copy()) for r, q in self.steps[timestep]]
 
 
-def run_episode(env, actions, reset: bool = True) -> Dict[str, Any]:
+def base_stock_policy(env, level):
+    """The reference's base-stock heuristic (src/experiments/run_baselines.py:188-207) for given levels [W,S]:
+    order up to the level, clipped to the order maximum, as a float32 action."""
+    import numpy as np
+
+    maxq = np.asarray(env.env_config.action_space.params.max_order_quantities, dtype=np.float64)
+    qty = np.clip(level - env.inventory - env._compute_pending_matrix(), 0.0, maxq)
+    return (2.0 * qty / maxq - 1.0).astype(np.float32)
+
+
+def run_episode(env, actions, reset: bool = True, policy=None) -> Dict[str, Any]:
     """Step the reference env through ``actions[T, W, S]`` (float32 in [-1, 1]) and dump everything.
+    With ``policy`` (env -> float32 [W,S]) the actions are computed from the env's state step by step and written
+    into ``actions``.
 
     Returns per-step stacks of the quantities listed in SURVEY.md section 8c ("parity classes").
     """
@@ -182,6 +224,8 @@ def run_episode(env, actions, reset: bool = True) -> Dict[str, Any]:
         "obs0_local": np.stack([np.asarray(obs[a][:D], dtype=np.float64) for a in env.agents]),
     }
     for t in range(T):
+        if policy is not None:
+            actions[t] = policy(env)
         act = {a: actions[t, i].astype(np.float32) for i, a in enumerate(env.agents)}
         obs, rew, term, trunc, infos = env.step(act)
         info = infos[env.agents[0]]

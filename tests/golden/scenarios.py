@@ -183,6 +183,56 @@ def large_network(lambda_orders: float = 1.0, probability_skus: float = 0.2,
         features=dict(DEFAULT_FEATURES))
 
 
+def empirical_regionmap() -> Dict[str, Any]:
+    """Empirical demand (reference components/demand_sampler.py:166-271) with the excluded-region mapping
+    (src/data/preprocessor.py:382-441): the large network's shape with 10 included regions; the demand frame carries 50
+    raw regions, 40 of which are mapped onto the included ones (tests/golden/make_golden.py builds the frame)."""
+    d = large_network(episode_length=24)
+    W, S, R = 10, 100, 10
+    rng = np.random.default_rng(3)
+    base = 0.05 + 0.045 * np.arange(W)
+    out_var = np.stack([rng.permutation(base) for _ in range(R)], axis=1)
+    d["n_regions"] = R
+    d["cost_structure"]["shipment_cost"]["outbound_fixed"] = [[0.0] * R] * W
+    d["cost_structure"]["shipment_cost"]["outbound_variable"] = np.round(out_var, 6).tolist()
+    d["cost_structure"]["distances"] = np.round(50 + 450 * rng.random((W, R)), 3).tolist()
+    d["components"]["demand_sampler"] = dict(type="empirical", params=None)
+    d["initial_inventory"] = dict(type="custom", params=dict(values=25))
+    return d
+
+
+def empirical_frame(n_raw_regions: int = 50, n_included: int = 10, n_skus: int = 100, n_days: int = 40, seed: int = 11):
+    """Synthetic stand-in for the reference's raw order data: (frame with RAW region ids, warehouse-to-region cost table,
+    all region ids, selected region ids). Region ids are strings like the reference's CSVs; a few excluded regions have no
+    warehouse pair at all and a few share no warehouse with an included region (both fallback rules)."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    all_ids = [f"REG_{i:02d}" for i in range(n_raw_regions)]
+    selected = [all_ids[i] for i in sorted(rng.choice(n_raw_regions, n_included, replace=False))]
+    wh = [f"WH_{i}" for i in range(10)]
+    rows = []
+    for i, rid in enumerate(all_ids):
+        if rid not in selected and i % 11 == 3:
+            continue                                         # no warehouse pair: first included region
+        if rid not in selected and i % 13 == 5:
+            rows.append(dict(sourcenodeid="WH_X", destinationregionid=rid, fixed_costs=1.0))   # no shared warehouse
+            continue
+        for wname in rng.choice(wh, int(rng.integers(2, 6)), replace=False):
+            rows.append(dict(sourcenodeid=wname, destinationregionid=rid, fixed_costs=float(np.round(rng.uniform(1, 20), 3))))
+    wtr = pd.DataFrame(rows)
+    recs = []
+    oid = 0
+    for day in range(3, 3 + n_days):                         # timesteps need not start at 0
+        for _ in range(int(rng.integers(30, 60))):
+            rid = all_ids[int(rng.integers(0, n_raw_regions))]
+            oid += 1
+            skus = rng.choice(n_skus + 3, int(rng.integers(1, 25)))          # repeats (summed) and ids >= n_skus (dropped)
+            for sk in skus:
+                recs.append(dict(timestep=day, region_raw=rid, order_id=f"SO{oid:06d}", sku_id=int(sk),
+                                 quantity=float(rng.integers(1, 9))))
+    return pd.DataFrame(recs), wtr, all_ids, selected
+
+
 def _obs_stats(dim: int, seed: int):
     rng = np.random.default_rng(seed)
     return (rng.normal(5.0, 3.0, dim).astype(np.float32), rng.uniform(0.5, 4.0, dim).astype(np.float32))
@@ -199,6 +249,15 @@ SCENARIOS = {
                                   action_seed=3, allow_region_mismatch=True),
     "large_network": dict(env=large_network, n_envs=2, steps=12, base_seed=2024, action_seed=4,
                           allow_region_mismatch=True),
+    # the flagship shape in steady state: ring depth 10 wraps three times; "lite" files keep the state, ordered
+    # quantities, per-region results, costs, rewards and observations but not the [W,R,S] shipment cube
+    "large_network_long": dict(env=large_network, n_envs=8, steps=32, base_seed=2025, action_seed=5,
+                               allow_region_mismatch=True, lite=True),
+    # ... and driven by the base-stock heuristic the benchmark replays (stock settles near 5 units per cell)
+    "large_network_basestock": dict(env=large_network, n_envs=8, steps=36, base_seed=2026, action_seed=6,
+                                    allow_region_mismatch=True, lite=True, policy="base_stock"),
+    "empirical_regionmap": dict(env=empirical_regionmap, n_envs=4, steps=24, base_seed=31, action_seed=7,
+                                allow_region_mismatch=True, lite=True, empirical=True),
 }
 
 

@@ -9,7 +9,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NAMES = ["small_default", "allfeat_ratio_stochastic", "basestock_cost_meanstd",
-         "regions_ne_warehouses", "large_network"]
+         "regions_ne_warehouses", "large_network", "large_network_long", "large_network_basestock"]
 
 INT_KEYS = ("inventory", "pending", "ordered", "fulfilled", "unfulfilled", "ship_counts", "ship_qty",
             "ship_by_sku", "lost_orders")
@@ -21,6 +21,10 @@ class Golden:
         z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
         self.name = name
         self.z = {k: z[k] for k in z.files}
+        if "obs_whole" in self.z:                      # "lite" files: whole-number entries as int16 + the others as a list
+            obs = self.z.pop("obs_whole").astype(np.float32)
+            obs.reshape(-1)[self.z.pop("obs_frac_idx")] = self.z.pop("obs_frac_val")
+            self.z["obs_local"] = obs.astype(np.float64)
         self.env: Dict[str, Any] = json.loads(str(self.z["env_json"]))
         self.meta: Dict[str, Any] = json.loads(str(self.z["meta_json"]))
         self.N, self.T = self.meta["n_envs"], self.meta["steps"]

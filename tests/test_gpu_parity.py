@@ -43,17 +43,22 @@ def test_cuda_matches_reference_auto_team(name):
     _run(Golden(name))
 
 
-@pytest.mark.parametrize("mode", ["auto", "split", "fused", "generic"])
+@pytest.mark.parametrize("mode", ["auto", "compact_fused", "split", "fused", "generic"])
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_without_diagnostics(name, mode):
     """No diagnostic outputs. ``auto``: the compact layout and its fused kernel where the configuration qualifies (the
     large networks), else the wide lean path; ``split``: the wide layout's lean path - the four-kernel split step for
     teams of 8+ lanes, else the lean fused kernel; ``fused`` keeps lean launches in the wide fused kernel; ``generic``
     forces the generic instantiation."""
-    used = _run(Golden(name), diagnostics=False, generic=mode == "generic", fused=mode == "fused",
-                layout="wide" if mode == "split" else None)
+    if mode == "compact_fused":
+        if not name.startswith("large_network"):
+            pytest.skip("configuration does not qualify for the compact layout")
+        used = _run(Golden(name), diagnostics=False, fused=True, layout="compact")
+    else:
+        used = _run(Golden(name), diagnostics=False, generic=mode == "generic", fused=mode == "fused",
+                    layout="wide" if mode == "split" else None)
     if name.startswith("large_network"):
-        assert used == ("compact" if mode == "auto" else "wide")
+        assert used == ("compact" if mode in ("auto", "compact_fused") else "wide")
 
 
 @pytest.mark.parametrize("team", [1, 2, 4, 8, 16, 32])
@@ -940,17 +945,19 @@ def _lean_env_dict(rng, W, S, R, lost, pen_uniform, lead_hi, scope="agent", dema
 
 
 @pytest.mark.parametrize("W,S,R,lost,pen_uniform,max_orders,lead_hi,variant", [
-    (7, 70, 9, "closest", False, 9, 3, "lines"),            # ragged last slot, per-SKU penalties (float64 lost sums), W in two chunks
+    (7, 68, 9, "closest", False, 9, 3, "lines"),            # ragged last slot, per-SKU penalties (float64 lost sums), W in two chunks
     (10, 100, 50, "shipment", False, 80, 10, "lines"),      # the large shape, leads up to 10 (ring wraps), > 64 orders per step
     (16, 128, 64, "shipment", True, 40, 16, "lines"),       # every limit of the layout at once: W 16, S 128, R 64, L 16
-    (5, 34, 3, "shipment", True, 12, 1, "lines"),           # a single ring plane (L = 1), one warehouse chunk
+    (5, 36, 3, "shipment", True, 12, 1, "lines"),           # a single ring plane (L = 1), one warehouse chunk
     (10, 100, 50, "shipment", True, 30, 6, "dense"),        # dense order rows converted on the device (marlsc_lines_from_orders)
     (10, 100, 50, "closest", True, 30, 6, "qty_actions"),   # integer order quantities instead of float actions
     (6, 64, 12, "shipment", True, 20, 4, "norm_id_team"),   # fixed mean/std normalisation, one-hot id, team reward, home-demand block
     (10, 100, 50, "shipment", True, 30, 6, "region_map"),   # 50 raw regions mapped onto 10 included ones (preprocessor.py:382-441)
 ])
-def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi, variant):
-    """The compact layout's fused kernel (csrc/env_compact.cu) against the oracle: scarce stock (most lines are split or
+@pytest.mark.parametrize("fused", [False, True])
+def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi, variant, fused):
+    """The compact layout's kernels (csrc/env_compact.cu: the split step K1a'-K1d, and with ``fused`` the single fused
+    kernel) against the oracle: scarce stock (most lines are split or
     lost), environments without orders, all-zero orders, a batch that does not fill the last CTA, a mid-run reset, ring
     wrap-around, and every way of feeding it (lines packed on the host, dense rows converted on the device, integer
     quantity actions, a region map)."""
@@ -972,7 +979,8 @@ def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi,
         meta = dict(obs_normalization="meanstd_custom", obs_stats=stats, include_warehouse_id=True)
         okw = dict(obs_normalization="meanstd_custom", obs_stats=stats, include_warehouse_id=True)
     E, T = 11, 2 * lead_hi + 7
-    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, env_meta=meta, region_map=region_map)
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, env_meta=meta, region_map=region_map,
+                              layout="compact", fused_kernel=fused)
     assert env.layout == "compact"
     oracles = [OracleEnv(env_dict, **okw) for _ in range(E)]
     maxq = np.asarray(env_dict["action_space"]["params"]["max_order_quantities"])

@@ -13,14 +13,16 @@ def test_oracle_reproduces_reference(name):
     for i in range(g.N):
         env = OracleEnv(g.env, **g.oracle_kwargs())
         obs0 = env.reset(g["init_inventory"][i])
-        np.testing.assert_allclose(obs0, g["obs0_local"][i], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(obs0, g["obs0_local"][i], rtol=1e-6 if g.meta.get("lite") else 1e-12, atol=0)
         for t in range(g.T):
             out = env.step(g["actions"][i, t], g.orders(i, t), g.leads(i, t))
             for k in INT_KEYS:
-                assert np.array_equal(out[k], g[k][i, t]), (name, i, t, k)
+                if k in g.z:                             # "lite" goldens do not carry the [W,R,S] shipment cube
+                    assert np.array_equal(out[k], g[k][i, t]), (name, i, t, k)
             for k in FLOAT_KEYS:
-                np.testing.assert_allclose(out[k], g[k][i, t], rtol=1e-12, atol=1e-12,
-                                           err_msg=f"{name} env {i} step {t} {k}")
+                # observations of "lite" goldens are stored as the float32 the reference emits
+                tol = 1e-6 if (k == "obs_local" and g.meta.get("lite")) else 1e-12
+                np.testing.assert_allclose(out[k], g[k][i, t], rtol=tol, atol=tol, err_msg=f"{name} env {i} step {t} {k}")
             assert bool(out["trunc"]) == bool(g["trunc"][i, t])
 
 
