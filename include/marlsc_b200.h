@@ -196,6 +196,12 @@ typedef struct marlsc_step_io {
   /* Integer order quantities instead of float actions (direct action space, COMPACT layout): uint8 [E,W,S], the quantity
    * itself (clipped to the SKU's maximum), a quarter of the bytes of `actions` for callers that decide in units. */
   const uint8_t* action_qty;     /* [E,W,S] or NULL; replaces actions when set */
+  /* Base-stock heuristic evaluated inside the step (COMPACT layout, split step): when actions and action_qty are both
+   * NULL and base_stock_level is set, every cell's action is what marlsc_policy_base_stock would have produced from the
+   * state before this step - 2 clip(level - on_hand - in_transit, 0, max_qty) / max_qty - 1 in float32 - and is rescaled
+   * like any other action. Saves the policy launch and two passes over the action tensor. */
+  const float* base_stock_level; /* device float32 [W,S], or [E,W,S] when base_stock_per_env != 0; or NULL */
+  int32_t base_stock_per_env;
 } marlsc_step_io_t;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

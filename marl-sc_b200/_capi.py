@@ -59,7 +59,7 @@ class StepIOC(C.Structure):
                 ("d_ship_count", C.c_void_p), ("d_unfulfilled", C.c_void_p), ("d_lost_orders", C.c_void_p),
                 ("d_lost_sales", C.c_void_p), ("order_counts", C.c_void_p), ("order_stride", C.c_int32),
                 ("lines", C.c_void_p), ("line_offsets", C.c_void_p), ("line_counts", C.c_void_p), ("line_stride", C.c_int32),
-                ("action_qty", C.c_void_p)]
+                ("action_qty", C.c_void_p), ("base_stock_level", C.c_void_p), ("base_stock_per_env", C.c_int32)]
 
 
 class HostStepC(C.Structure):

@@ -100,9 +100,10 @@ class EmpiricalDemandSampler(BaseDemandSampler):
                 pre._packed = cache
             except AttributeError:
                 pass
-        key = ("val" if use_val else "train", self.n_skus)
+        rmap = getattr(context, "region_map", None)     # frame with raw region ids: mapped before the orders are grouped
+        key = ("val" if use_val else "train", self.n_skus, None if rmap is None else tuple(int(x) for x in rmap))
         if key not in cache:
-            cache[key] = pack_demand_frame(self.data, self.n_skus)
+            cache[key] = pack_demand_frame(self.data, self.n_skus, rmap)
         self.frame = cache[key]
         self.available_timesteps = [int(t) for t in self.frame.timesteps]
         self.max_timestep = max(self.available_timesteps) if self.available_timesteps else 0

@@ -8,7 +8,8 @@ hot path: only MLP actor/critic descriptions are accepted.
 
 One deliberate extension: ``EnvironmentConfig.allow_region_mismatch`` (default False) lifts the
 ``n_regions == n_warehouses`` rule (reference schema.py:670-675) that the env code itself never relies
-on, so the 10 warehouse x 50 region network of BASELINE.json can be described.
+on, so the 10 warehouse x 50 region network of BASELINE.json can be described; ``allow_empirical_frame`` lets the
+``empirical`` demand sampler run on a caller-supplied demand frame with a ``custom`` data source.
 """
 from __future__ import annotations
 
@@ -353,6 +354,10 @@ class EnvironmentConfig(_Strict):
     data_source: DataSourceConfig = Field(..., discriminator="type")
     features: FeatureConfig = Field(default_factory=FeatureConfig)
     allow_region_mismatch: bool = False
+    # extension: the empirical sampler replays a demand frame handed in through env_meta["preprocessed_data"]
+    # (marlsc_b200.data) with cost tables given in the config, because the raw CSVs the reference's real_world data
+    # source preprocesses are not part of its repository
+    allow_empirical_frame: bool = False
 
     @model_validator(mode="after")
     def _shape_checks(self):
@@ -419,7 +424,8 @@ class EnvironmentConfig(_Strict):
                 alloc.params["max_splits"] = self.n_warehouses - 1
             elif ms >= self.n_warehouses:
                 raise ValueError(f"demand_allocator.greedy max_splits must be < n_warehouses={self.n_warehouses}")
-        if isinstance(self.components.demand_sampler, DemandSamplerEmpirical) and self.data_source.type != "real_world":
+        if (isinstance(self.components.demand_sampler, DemandSamplerEmpirical) and self.data_source.type != "real_world"
+                and not self.allow_empirical_frame):
             raise ValueError("demand_sampler.type='empirical' requires data_source.type='real_world', "
                              f"got data_source.type='{self.data_source.type}'")
         if self.data_source.type == "custom":

@@ -31,6 +31,7 @@ class EnvironmentContext:
     distances: np.ndarray
     preprocessed_data: Optional[object] = None
     data_mode: str = "train"
+    region_map: Optional[object] = None   # raw -> included region ids of the demand frame (marlsc_b200.data.build_region_map)
 
 
 def convert_cost_structure(cs: CostStructureConfig) -> Tuple[Union[float, np.ndarray], Union[float, np.ndarray]]:
@@ -42,7 +43,7 @@ def convert_cost_structure(cs: CostStructureConfig) -> Tuple[Union[float, np.nda
 
 
 def create_environment_context(env_config: EnvironmentConfig, seed_manager=None, data_mode: str = "train",
-                               preprocessed_data=None) -> EnvironmentContext:
+                               preprocessed_data=None, region_map=None) -> EnvironmentContext:
     """``preprocessed_data`` (``marlsc_b200.data.PreprocessedData``) carries the demand frame of the ``empirical`` demand
     sampler; the reference builds it from raw CSVs that are not part of its repository (context.py:66-113)."""
     if env_config.data_source.type != "custom":
@@ -59,4 +60,4 @@ def create_environment_context(env_config: EnvironmentConfig, seed_manager=None,
             outbound_fixed=np.array(sc.outbound_fixed, dtype=float), outbound_variable=np.array(sc.outbound_variable, dtype=float),
             inbound_fixed=np.array(sc.inbound_fixed, dtype=float), inbound_variable=np.array(sc.inbound_variable, dtype=float)),
         sku_weights=np.array(cs.sku_weights, dtype=float), distances=np.array(cs.distances, dtype=float),
-        preprocessed_data=preprocessed_data, data_mode=data_mode)
+        preprocessed_data=preprocessed_data, data_mode=data_mode, region_map=region_map)

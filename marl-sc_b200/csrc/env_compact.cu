@@ -544,7 +544,7 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
   uint32_t x[kCompactMaxL - 1];
   if (mine) {
     if (io.action_qty) aqw = reinterpret_cast<const uint32_t*>(io.action_qty + e * WS + w * S)[c4];
-    else a4 = reinterpret_cast<const float4*>(io.actions + e * WS + w * S)[c4];
+    else if (io.actions) a4 = reinterpret_cast<const float4*>(io.actions + e * WS + w * S)[c4];
     iv = *inv4;
     arr4 = row4[pa * S4];
     le4 = reinterpret_cast<const uint32_t*>(sp.lead_u8 + w * S)[c4];
@@ -552,6 +552,10 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
     for (int k = 0; k < kCompactMaxL - 1; ++k)
       if (k < L - 1) x[k] = row4[s_poff[k]];
   }
+  const bool policy = !io.actions && !io.action_qty;  // base-stock heuristic in place of given actions (marlsc_step_io.base_stock_level)
+  float4 lv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (policy && mine)
+    lv4 = reinterpret_cast<const float4*>(io.base_stock_level + (io.base_stock_per_env ? e * WS : 0) + w * S)[c4];
   const uint32_t img = sm_addr(smem) + (threadIdx.x >> 5) * (uint32_t)(L * S);   // this warp's row image, slot-major
   if (mine) {
 #pragma unroll
@@ -559,8 +563,24 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
       if (k < L - 1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(img + (uint32_t)(k * S + 4 * lane)), "r"(x[k]) : "memory");
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(img + (uint32_t)((L - 1) * S + 4 * lane)), "r"(0u) : "memory");
   }
-  const float af[4] = {a4.x, a4.y, a4.z, a4.w};
+  float af[4] = {a4.x, a4.y, a4.z, a4.w};
   const uint32_t ivv[4] = {iv.x & 0xffffu, iv.x >> 16, iv.y & 0xffffu, iv.y >> 16};
+  if (policy && mine) {
+    // reference make_bs_newsvendor_action_fn (run_baselines.py:188-207): order up to the level given on-hand stock and
+    // everything in transit - every plane of the ring, the arrivals of this step included (the policy acts before them)
+    const float lv[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t pend = (arr4 >> (8 * j)) & 0xffu;
+#pragma unroll
+      for (int k = 0; k < kCompactMaxL - 1; ++k)
+        if (k < L - 1) pend += (x[k] >> (8 * j)) & 0xffu;
+      const double mxd = sp.action_max[4 * lane + j];
+      double qd = (double)lv[j] - (double)ivv[j] - (double)pend;
+      qd = qd < 0.0 ? 0.0 : (qd > mxd ? mxd : qd);
+      af[j] = (float)(2.0 * qd / mxd - 1.0);
+    }
+  }
   uint32_t ni[4];
   int nQ = 0, nPos = 0;
   double inb = 0.0;

@@ -415,8 +415,10 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   int rc = check_state(env, state);
   if (rc) return rc;
   if (!io) return set_error(MARLSC_EINVAL, "null io");
-  if ((!io->actions && !io->action_qty) || !io->rewards || !io->obs)
-    return set_error(MARLSC_EINVAL, "io.actions (or io.action_qty), io.rewards and io.obs must not be NULL");
+  if ((!io->actions && !io->action_qty && !io->base_stock_level) || !io->rewards || !io->obs)
+    return set_error(MARLSC_EINVAL, "io.actions (or io.action_qty / io.base_stock_level), io.rewards and io.obs must not be NULL");
+  if (io->base_stock_level && !io->actions && !io->action_qty && (env->layout != MARLSC_LAYOUT_COMPACT || env->force_fused))
+    return set_error(MARLSC_EINVAL, "io.base_stock_level needs a handle with the COMPACT layout running the split step");
   if (io->lines) {
     if (env->layout != MARLSC_LAYOUT_COMPACT) return set_error(MARLSC_EINVAL, "io.lines needs a handle with the COMPACT layout");
     if (!io->line_offsets && !io->line_counts) return set_error(MARLSC_EINVAL, "io.lines needs io.line_offsets or io.line_counts");

@@ -93,12 +93,17 @@ class DemandFrame:
         return self.order_region[a:b], self.order_qty[a:b]
 
 
-def pack_demand_frame(df, n_skus: int) -> DemandFrame:
+def pack_demand_frame(df, n_skus: int, region_map: Optional[Sequence[int]] = None) -> DemandFrame:
     """Group the frame's rows into orders once: ``(timestep, region_id, order_id)`` groups in sorted order, quantities
-    of the same SKU summed, SKU ids outside ``[0, n_skus)`` dropped (demand_sampler.py:247-258)."""
+    of the same SKU summed, SKU ids outside ``[0, n_skus)`` dropped (demand_sampler.py:247-258). With ``region_map`` the
+    frame carries RAW region ids and is mapped first, as the reference's preprocessing does before it stores the frame
+    (preprocessor.py:650) - the orders of a step are then sequenced by their MAPPED region, which is the order the
+    greedy allocation sees them in."""
     import pandas as pd
     if len(df) == 0:
         return DemandFrame(np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.int16), np.zeros((0, n_skus), np.uint8))
+    if region_map is not None:
+        df = df.assign(region_id=np.asarray(region_map, dtype=np.int64)[df["region_id"].to_numpy(dtype=np.int64)])
     keys = df[["timestep", "region_id", "order_id"]]
     # group ids in the order pandas' groupby (sort=True) yields them: timestep, then region_id, then order_id
     order_idx, uniques = pd.factorize(pd.MultiIndex.from_frame(keys), sort=True)

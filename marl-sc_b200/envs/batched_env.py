@@ -223,18 +223,32 @@ class BatchedInventoryEnv:
             _capi.check(L.marlsc_demand_create(self.n_regions, self.n_skus, dbl(keep[0]), dbl(keep[1]), dbl(keep[2]),
                                                self.device.index, C.byref(h)))
         E, S, dev = self.num_envs, self.n_skus, self.device
-        self._dd = dict(handle=h, seed=int(seed), omax=omax,
-                        counts=torch.zeros(E, dtype=torch.int32, device=dev),
-                        region=torch.zeros(E * omax, dtype=torch.int16, device=dev),
-                        qty=torch.zeros(E * omax * S + 16, dtype=torch.uint8, device=dev),
-                        overflow=torch.zeros(1, dtype=torch.int32, device=dev))
+        self._dd = dict(handle=h, seed=int(seed), omax=omax, overflow=torch.zeros(1, dtype=torch.int32, device=dev))
+        if self.layout == "compact":
+            # the sampler writes sparse lines, the compact kernels' native demand format: a stream holds the cells of four
+            # SKUs of every order, mean lam_orders * p * 4 per step; six sigma and some slack on top, whole round pairs
+            per_stream = float((lam_o * prob).sum()) * 4.0
+            stride = (int(np.ceil(per_stream + 6.0 * np.sqrt(max(per_stream, 1.0)) + 8.0)) + 1) & ~1
+            rm = self.spec.tables["region_map"]
+            self._dd.update(lines=torch.zeros((E * stride, 32), dtype=torch.int16, device=dev), stride=stride,
+                            counts=torch.zeros(E, dtype=torch.int32, device=dev),
+                            region_map=None if rm is None else torch.from_numpy(np.ascontiguousarray(rm, np.int32)).to(dev))
+        else:
+            self._dd.update(counts=torch.zeros(E, dtype=torch.int32, device=dev),
+                            region=torch.zeros(E * omax, dtype=torch.int16, device=dev),
+                            qty=torch.zeros(E * omax * S + 16, dtype=torch.uint8, device=dev))
 
     def sample_device_demand(self) -> None:
         """Fill the device order buffers for the next step (called by step() when no orders are passed)."""
         d = self._dd
-        _capi.check(_capi.lib().marlsc_demand_sample(d["handle"], self.num_envs, d["seed"], self._demand_step, d["omax"],
-                                                     d["counts"].data_ptr(), d["region"].data_ptr(), d["qty"].data_ptr(),
-                                                     d["overflow"].data_ptr(), self._stream()))
+        if "lines" in d:
+            _capi.check(_capi.lib().marlsc_demand_sample_lines(d["handle"], self.num_envs, d["seed"], self._demand_step, d["stride"],
+                                                               _ptr(d["region_map"]), d["lines"].data_ptr(), d["counts"].data_ptr(),
+                                                               d["overflow"].data_ptr(), self._stream()))
+        else:
+            _capi.check(_capi.lib().marlsc_demand_sample(d["handle"], self.num_envs, d["seed"], self._demand_step, d["omax"],
+                                                         d["counts"].data_ptr(), d["region"].data_ptr(), d["qty"].data_ptr(),
+                                                         d["overflow"].data_ptr(), self._stream()))
         self._demand_step += 1
 
     def enable_device_leads(self, seed: int = 0) -> None:
@@ -479,9 +493,10 @@ class BatchedInventoryEnv:
         per_env = [ds.sample(self.timestep) for ds in self.demand_samplers]
         return pack_orders(per_env, self.n_skus), leads
 
-    def step(self, actions: torch.Tensor, orders: Union[DeviceOrders, OrderBatch, DeviceLines, LineBatch, None] = None,
+    def step(self, actions: Optional[torch.Tensor], orders: Union[DeviceOrders, OrderBatch, DeviceLines, LineBatch, None] = None,
              actual_lead: Union[torch.Tensor, np.ndarray, None] = None, obs_out: Optional[torch.Tensor] = None,
-             rewards_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, bool]:
+             rewards_out: Optional[torch.Tensor] = None, base_stock_level: Optional[torch.Tensor] = None
+             ) -> Tuple[torch.Tensor, torch.Tensor, bool]:
         """Advance every environment by one timestep.
 
         actions: float32 [E,W,S] in [-1,1] on the device. orders: this step's demand; ``None`` draws
@@ -491,12 +506,23 @@ class BatchedInventoryEnv:
         The returned tensors are reused by the next call unless ``obs_out`` / ``rewards_out`` are given.
         """
         E, W, S = self.num_envs, self.n_warehouses, self.n_skus
-        qty_actions = actions.dtype == torch.uint8
-        if qty_actions and self.layout != "compact":
-            raise ValueError("uint8 quantity actions need the compact layout")
-        if actions.shape != (E, W, S) or (actions.dtype != torch.float32 and not qty_actions) or actions.device != self.device:
-            raise ValueError(f"actions must be a float32 (or, compact layout, uint8 quantity) tensor of shape {(E, W, S)} on {self.device}")
-        actions = actions.contiguous()
+        level = None
+        if actions is None:
+            # the base-stock heuristic evaluated inside the step kernel (compact layout): ``base_stock_level`` [W,S] or [E,W,S]
+            if base_stock_level is None:
+                raise ValueError("actions is None: pass base_stock_level to let the step evaluate the base-stock heuristic")
+            if self.layout != "compact":
+                raise ValueError("the in-step base-stock policy needs the compact layout; use base_stock_actions() + step(actions)")
+            level = base_stock_level.to(device=self.device, dtype=torch.float32).contiguous()
+            if level.shape not in ((W, S), (E, W, S)):
+                raise ValueError(f"base_stock_level must have shape {(W, S)} or {(E, W, S)}")
+        qty_actions = actions is not None and actions.dtype == torch.uint8
+        if actions is not None:
+            if qty_actions and self.layout != "compact":
+                raise ValueError("uint8 quantity actions need the compact layout")
+            if actions.shape != (E, W, S) or (actions.dtype != torch.float32 and not qty_actions) or actions.device != self.device:
+                raise ValueError(f"actions must be a float32 (or, compact layout, uint8 quantity) tensor of shape {(E, W, S)} on {self.device}")
+            actions = actions.contiguous()
         use_dd = orders is None and self._dd is not None
         if use_dd:
             self.sample_device_demand()
@@ -554,20 +580,26 @@ class BatchedInventoryEnv:
             for k in ("ship_by_sku", "ship_counts", "unfulfilled", "lost_orders"):
                 d[k].zero_()
         io = _capi.StepIOC(
-            None if qty_actions else actions.data_ptr(), orders.offsets.data_ptr(), orders.region.data_ptr(), orders.qty.data_ptr(),
+            None if (qty_actions or actions is None) else actions.data_ptr(), orders.offsets.data_ptr(), orders.region.data_ptr(), orders.qty.data_ptr(),
             orders.qty_bytes, _ptr(lead_t), rew.data_ptr(), out.data_ptr(), self.truncated.data_ptr(),
             _ptr(d.get("cost_breakdown")), _ptr(d.get("ordered")), _ptr(d.get("ship_by_sku")), _ptr(d.get("ship_counts")),
             _ptr(d.get("unfulfilled")), _ptr(d.get("lost_orders")), _ptr(d.get("lost_sales")))
         if qty_actions:
             io.action_qty = actions.data_ptr()
+        if level is not None:
+            io.actions = None
+            io.base_stock_level, io.base_stock_per_env = level.data_ptr(), int(level.dim() == 3)
         if lines is not None:
             io.lines, io.line_offsets = lines.lines.data_ptr(), lines.offsets.data_ptr()
         if use_dd:
             dd = self._dd
-            io.order_offsets, io.order_region, io.order_qty, io.order_qty_bytes = None, dd["region"].data_ptr(), dd["qty"].data_ptr(), 1
-            io.order_counts, io.order_stride = dd["counts"].data_ptr(), dd["omax"]
+            if "lines" in dd:
+                io.lines, io.line_offsets, io.line_counts, io.line_stride = dd["lines"].data_ptr(), None, dd["counts"].data_ptr(), dd["stride"]
+            else:
+                io.order_offsets, io.order_region, io.order_qty, io.order_qty_bytes = None, dd["region"].data_ptr(), dd["qty"].data_ptr(), 1
+                io.order_counts, io.order_stride = dd["counts"].data_ptr(), dd["omax"]
         _capi.check(_capi.lib().marlsc_env_step(self._h, C.byref(self._state), C.byref(io), self.timestep, self._stream()))
-        self._keep = (actions, orders, lines, lead_t)   # keep inputs alive until the stream has consumed them
+        self._keep = (actions, orders, lines, lead_t, level)   # keep inputs alive until the stream has consumed them
         self.timestep += 1
         return out, rew, self.timestep >= self.episode_length
 

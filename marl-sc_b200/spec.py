@@ -79,8 +79,14 @@ def build_env_spec(env_config: EnvironmentConfig, obs_normalization: str = "off"
                    seed_manager=None, data_mode: str = "train", preprocessed_data=None) -> EnvSpec:
     if obs_normalization not in _capi.NORM:
         raise ValueError(f"Unknown obs_normalization: {obs_normalization}. Available: {list(_capi.NORM)}")
+    empirical = env_config.components.demand_sampler.type == "empirical"
     ctx = context or create_environment_context(env_config, seed_manager=seed_manager, data_mode=data_mode,
-                                                preprocessed_data=preprocessed_data)
+                                                preprocessed_data=preprocessed_data,
+                                                region_map=region_map if empirical else None)
+    if empirical:
+        # the empirical sampler maps its frame's raw region ids itself, before it sequences the orders of a step
+        # (reference preprocessor.py:650); the kernels then see included region ids only
+        region_map = None
     comps = dict(
         demand_sampler=get_demand_sampler(env_config, context=ctx),
         demand_allocator=get_demand_allocator(env_config, context=ctx),

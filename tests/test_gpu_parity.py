@@ -122,12 +122,16 @@ def test_lean_equals_generic_under_stockouts(fixed_cost, team, fused):
         orders = pack_orders([smp.sample(t) for smp in samplers], 100)
         ob1, r1, _ = lean.step(act, orders=orders)
         ob2, r2, _ = gen.step(act, orders=orders)
-        assert torch.equal(lean.inventory, gen.inventory), f"inventory differs at step {t}"
-        assert torch.equal(lean.ring_qty, gen.ring_qty)
+        assert torch.equal(lean.inventory.to(torch.int32), gen.inventory), f"inventory differs at step {t}"
+        if lean.layout == gen.layout:
+            assert torch.equal(lean.ring_qty, gen.ring_qty)
+        else:                                           # compact ring is indexed by arrival time: compare what is in transit
+            assert torch.equal(lean.pending_matrix(), gen.pending_matrix())
         np.testing.assert_allclose(r1.cpu().numpy(), r2.cpu().numpy(), rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(ob1.cpu().numpy(), ob2.cpu().numpy(), rtol=1e-6, atol=1e-6)
         lost_any = lost_any or bool((lean.inventory == 0).any())
     assert lost_any, "workload was meant to run out of stock"
+    assert lean.layout == ("compact" if (fixed_cost == 0.0 and team == 0 and not fused) else "wide")
 
 
 def test_cuda_region_map():
@@ -1030,4 +1034,135 @@ def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi,
             assert bool(trunc) == bool(out["trunc"])
             lost_any = lost_any or out["lost_orders"].sum() > 0
     assert lost_any, "workload was meant to lose sales"
+    env.close()
+
+
+def test_compact_device_demand_lines_and_in_step_base_stock():
+    """All-device pipeline on the compact layout: (i) the sampler writing lines (marlsc_demand_sample_lines) draws the
+    orders the dense sampler draws for the same (seed, step) - an environment fed the dense rows ends in the same state;
+    (ii) the base-stock heuristic evaluated inside the step (marlsc_step_io.base_stock_level) equals the policy kernel
+    (marlsc_policy_base_stock) followed by a step with its actions."""
+    from golden.scenarios import large_network
+    from marlsc_b200 import _capi
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv, DeviceOrders
+    d = large_network()
+    d["episode_length"] = 30
+    cfg = environment_config_from_dict(dict(d, allow_region_mismatch=True))
+    E = 37
+    a = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, device_demand=True, demand_seed=5)     # lines, in-step policy
+    b = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False)                                        # dense rows, policy kernel
+    assert a.layout == b.layout == "compact" and "lines" in a._dd
+    smp = a.spec.components["demand_sampler"]
+    lam_o, prob, lam_q = smp.dense_params()
+    omax = 128
+    L = _capi.lib()
+    h = __import__("ctypes").c_void_p()
+    import ctypes as C
+    dbl = lambda x: np.ascontiguousarray(x, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))   # noqa: E731
+    keep = [np.ascontiguousarray(v, np.float64) for v in (lam_o, prob, lam_q)]
+    _capi.check(L.marlsc_demand_create(50, 100, dbl(keep[0]), dbl(keep[1]), dbl(keep[2]), 0, C.byref(h)))
+    counts = torch.zeros(E, dtype=torch.int32, device="cuda")
+    region = torch.zeros(E * omax, dtype=torch.int16, device="cuda")
+    qty = torch.zeros(E * omax * 100 + 16, dtype=torch.uint8, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rng = np.random.default_rng(0)
+    level = torch.from_numpy(rng.uniform(5, 60, (10, 100)).astype(np.float32)).cuda()
+    a.reset()
+    b.reset()
+    for t in range(24):
+        _capi.check(L.marlsc_demand_sample(h, E, 5, t, omax, counts.data_ptr(), region.data_ptr(), qty.data_ptr(), flag.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        cnt = counts.cpu().numpy()
+        offs = np.zeros(E + 1, np.int32)
+        offs[1:] = np.cumsum(cnt)
+        rows = np.concatenate([np.arange(e * omax, e * omax + cnt[e]) for e in range(E)])
+        reg = region.cpu().numpy()[rows]
+        q = qty.cpu().numpy()[:E * omax * 100].reshape(E * omax, 100)[rows]
+        pad = np.zeros((-(q.size)) % 16 + 16, np.uint8)
+        dense = DeviceOrders(torch.from_numpy(offs).cuda(), torch.from_numpy(reg).cuda(),
+                             torch.from_numpy(np.concatenate([q.reshape(-1), pad])).cuda(), int(offs[-1]))
+        oa, ra, _ = a.step(None, base_stock_level=level)                              # K4 lines + policy inside K1a'
+        ob, rb, _ = b.step(b.base_stock_actions(level), orders=dense)                 # K5, then K1 on the dense rows
+        assert torch.equal(a.inventory, b.inventory), t
+        assert torch.equal(a.ring_qty, b.ring_qty), t
+        assert torch.equal(oa, ob) and torch.equal(ra, rb), t
+    assert not a.demand_overflowed() and int(flag.item()) == 0
+    L.marlsc_demand_destroy(h)
+    a.close()
+    b.close()
+
+
+def test_empirical_demand_with_region_map_matches_reference():
+    """Golden scenario of SURVEY 8a rows A7 + A12: the reference env with its own EmpiricalDemandSampler over a demand
+    frame whose 50 raw regions went through the reference's map_excluded_regions. Here: the RAW frame packed by
+    pack_demand_frame, the region map from build_region_map, environments seeded like the reference's (window starts
+    from the same NumPy stream), orders sliced from the frame on the device - trajectories must match bit-exactly."""
+    import pandas as pd
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.data import PreprocessedData, build_region_map
+    from marlsc_b200.envs import BatchedInventoryEnv
+    g = Golden("empirical_regionmap")
+    z = g.z
+    wtr = pd.DataFrame(dict(sourcenodeid=z["wtr_source"], destinationregionid=z["wtr_dest"], fixed_costs=z["wtr_cost"]))
+    raw = pd.DataFrame(dict(timestep=z["frame_timestep"], region_id=z["frame_region_raw"].astype(int), order_id=z["frame_order"],
+                            sku_id=z["frame_sku"].astype(int), quantity=z["frame_qty"].astype(float)))
+    rmap = build_region_map(list(z["all_region_ids"]), wtr, list(z["selected_region_ids"]))
+    cfg = environment_config_from_dict(dict(g.env, allow_region_mismatch=True, allow_empirical_frame=True))
+    for layout in ("compact", "wide"):
+        env = BatchedInventoryEnv(cfg, g.N, device="cuda:0", env_seeds=[int(s) for s in z["env_seeds"]], region_map=rmap,
+                                  env_meta=dict(preprocessed_data=PreprocessedData(raw)), layout=layout)
+        assert env.layout == layout
+        obs0 = env.reset()
+        np.testing.assert_allclose(obs0.cpu().numpy(), g["obs0_local"], rtol=1e-5, atol=1e-6)
+        assert env._frame_start is None
+        for t in range(g.T):
+            obs, rew, trunc = env.step(torch.from_numpy(g["actions"][:, t]).cuda())
+            if t == 0:
+                assert env._frame_start.cpu().tolist() == [int(x) for x in z["window_start"]]
+            out = dict(inventory=env.inventory.cpu().numpy(), rewards=rew.cpu().numpy(), obs=obs.cpu().numpy(),
+                       trunc=env.truncated.cpu().numpy())
+            compare_step(g, t, out, what=f"empirical {layout} ")
+            assert np.array_equal(env.pending_matrix().cpu().numpy(), g["pending"][:, t])
+        env.close()
+
+
+def test_config2_4096_envs_100_steps_strided_oracle_check():
+    """BASELINE configs[1]: the default small env batched to 4,096 instances, T = 100, uniform float32 actions, demand from
+    the device sampler; 64 strided environments - the first and the last of the batch (last CTA) among them - are
+    replayed through the oracle with the orders the sampler drew for them: inventory exact, rewards / observations 1e-5."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    from oracle.inventory_oracle import OracleEnv
+    env_dict = small_default()
+    cfg = environment_config_from_dict(env_dict)
+    E, T = 4096, 100
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, device_demand=True, demand_seed=2)
+    picks = np.unique(np.concatenate([np.arange(0, E, 65), [E - 1, E - 2, E - 127, E - 128, E - 129]]))
+    assert len(picks) >= 64
+    obs = env.reset()
+    init = env.inventory.cpu().numpy()
+    oracles = {}
+    for i in picks:
+        o = OracleEnv(env_dict)
+        np.testing.assert_allclose(obs[i].cpu().numpy(), o.reset(init[i]), rtol=1e-5, atol=1e-6)
+        oracles[int(i)] = o
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    d = env._dd
+    omax = d["omax"]
+    for t in range(T):
+        act = torch.rand((E, 3, 2), device="cuda:0", generator=gen) * 2 - 1
+        obs, rew, trunc = env.step(act)
+        counts = d["counts"].cpu().numpy()
+        region = d["region"].cpu().numpy().reshape(E, omax)
+        qty = d["qty"].cpu().numpy()[:E * omax * 2].reshape(E, omax, 2)
+        a_h, inv, r, ob = act.cpu().numpy(), env.inventory.cpu().numpy(), rew.cpu().numpy(), obs.cpu().numpy()
+        for i, o in oracles.items():
+            out = o.step(a_h[i], [(int(region[i, j]), qty[i, j].astype(float)) for j in range(counts[i])])
+            assert np.array_equal(inv[i], out["inventory"]), (t, i)
+            np.testing.assert_allclose(r[i], out["rewards"], rtol=1e-5, atol=1e-6, err_msg=f"t={t} env={i}")
+            np.testing.assert_allclose(ob[i], out["obs_local"], rtol=1e-5, atol=1e-6, err_msg=f"t={t} env={i}")
+            assert bool(trunc) == bool(out["trunc"])
+    assert bool(trunc) and not env.demand_overflowed()
     env.close()

@@ -351,3 +351,68 @@ def test_running_meanstd_filter_and_column_standardisation():
     standardize_columns_(x, 3)
     assert torch.allclose(x.reshape(-1, 3).mean(0), torch.zeros(3), atol=1e-5)
     assert torch.allclose(x.reshape(-1, 3).std(0, unbiased=False)[:2], torch.ones(2), atol=1e-4)
+
+
+# ------------------------------------------------------------------ empirical demand + excluded-region mapping (A7, A12)
+def _empirical_golden():
+    import pandas as pd
+    z = np.load(os.path.join(ROOT, "tests", "golden", "empirical_regionmap.npz"))
+    wtr = pd.DataFrame(dict(sourcenodeid=z["wtr_source"], destinationregionid=z["wtr_dest"], fixed_costs=z["wtr_cost"]))
+    raw = pd.DataFrame(dict(timestep=z["frame_timestep"], region_id=z["frame_region_raw"].astype(int), order_id=z["frame_order"],
+                            sku_id=z["frame_sku"].astype(int), quantity=z["frame_qty"].astype(float)))
+    return z, wtr, raw
+
+
+def test_region_map_builder_matches_reference_mapping():
+    """build_region_map against what the reference's DataProcessor.map_excluded_regions (preprocessor.py:382-441) made of
+    every raw region of the golden frame - shared-warehouse argmin of the mean fixed cost, both fallbacks included."""
+    from marlsc_b200.data import build_region_map, map_excluded_regions
+    import pandas as pd
+    z, wtr, _ = _empirical_golden()
+    all_ids, selected = list(z["all_region_ids"]), list(z["selected_region_ids"])
+    rmap = build_region_map(all_ids, wtr, selected)
+    assert np.array_equal(rmap, z["region_map"])
+    assert all(rmap[all_ids.index(s)] == i for i, s in enumerate(selected))          # included regions map to themselves
+    assert len(set(rmap)) > 3 and rmap.count(0) > 2                                  # the rule spreads them; fallbacks hit region 0
+    ser = pd.Series(all_ids)
+    mapped = map_excluded_regions(ser, wtr, selected)
+    assert [selected.index(x) for x in mapped] == rmap
+
+
+def test_empirical_sampler_replays_reference_orders():
+    """pack_demand_frame + EmpiricalDemandSampler over the RAW golden frame with the region map applied must emit, for
+    the reference's seeds, exactly the orders the reference's EmpiricalDemandSampler emitted (window start from the
+    same rng.integers draw, (region_id, order_id) grouping order, duplicate SKU rows summed, SKU ids >= n_skus dropped)."""
+    from golden_io import Golden
+    from marlsc_b200.components import EmpiricalDemandSampler
+    from marlsc_b200.context import create_environment_context
+    from marlsc_b200.data import PreprocessedData, pack_demand_frame
+    from marlsc_b200.seeds import ENVIRONMENT_SEEDS, SeedManager
+    z, wtr, raw = _empirical_golden()
+    g = Golden("empirical_regionmap")
+    rmap = z["region_map"]
+    mapped = raw.assign(region_id=rmap[raw["region_id"].to_numpy()])                 # what the reference's preprocessing stores
+    frame = pack_demand_frame(mapped, g.S)
+    assert frame.n_timesteps == 40 and frame.order_qty.dtype == np.uint8
+    with pytest.raises(Exception, match="requires data_source.type='real_world'"):   # the reference's rule, unless lifted
+        environment_config_from_dict(dict(g.env, allow_region_mismatch=True))
+    cfg = environment_config_from_dict(dict(g.env, allow_region_mismatch=True, allow_empirical_frame=True))
+    ctx = create_environment_context(cfg, preprocessed_data=PreprocessedData(mapped))
+    for i in range(g.N):
+        sm = SeedManager(root_seed=int(z["env_seeds"][i]), seed_registry=ENVIRONMENT_SEEDS)
+        sm.advance_episode()
+        smp = EmpiricalDemandSampler(ctx, cfg.components.demand_sampler)
+        smp.reset(sm.get_rng("demand_sampler"))
+        assert smp.start_index() == int(z["window_start"][i])
+        for t in range(g.T):
+            mine = smp.sample(t)
+            ref = g.orders(i, t)
+            assert len(mine) == len(ref)
+            for o, (r, q) in zip(mine, ref):
+                assert o.region_id == r and np.array_equal(o.sku_demands, q)
+    # too short a frame fails like the reference
+    with pytest.raises(ValueError, match="episode_length"):
+        EmpiricalDemandSampler(create_environment_context(cfg, preprocessed_data=PreprocessedData(mapped[mapped["timestep"] < 10])),
+                               cfg.components.demand_sampler)
+    with pytest.raises(ValueError, match="requires preprocessed_data"):
+        EmpiricalDemandSampler(create_environment_context(cfg), cfg.components.demand_sampler)
