@@ -210,19 +210,69 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, n_envs * W * steps
 
 
-def cpu_port(env_dict, n_envs_per_worker, steps, workers):
+def _ref_worker(args):
+    """The reference's own InventoryEnvironment (oracle/_ref, or /root/reference in the build container) under the
+    base-stock heuristic with its own Poisson demand sampler: the same segment the GPU arm times, on one host core."""
+    env_dict, n_envs, steps, seed, z = args
+    import numpy as np
+    from oracle import ref_harness as H
+    from oracle.gae_oracle import gae_targets
+    large = env_dict["n_regions"] != env_dict["n_warehouses"]
+    cfg = H.env_config_from_dict(env_dict, allow_region_mismatch=large)
+    W, S, R = env_dict["n_warehouses"], env_dict["n_skus"], env_dict["n_regions"]
+    p = env_dict["components"]["demand_sampler"]["params"]
+    lam_o, prob = np.broadcast_to(np.asarray(p["lambda_orders"], float), (R,)), np.broadcast_to(np.asarray(p["probability_skus"], float), (R,))
+    lam_q = np.broadcast_to(np.asarray(p["lambda_quantity"], float), (R, S))
+    out_var = np.asarray(env_dict["cost_structure"]["shipment_cost"]["outbound_variable"], float)
+    first = np.argsort(out_var, axis=0, kind="stable")[0]
+    ed = np.zeros((W, S))
+    for r in range(R):
+        ed[first[r]] += lam_o[r] * prob[r] * lam_q[r]
+    lead = np.asarray(env_dict["components"]["lead_time_sampler"]["params"]["expected_lead_times"], float)
+    level = lead * ed + z * np.sqrt(lead * ed)
+    envs = [H.make_env(cfg, seed=H.derive_env_seed(seed, 0, i)) for i in range(n_envs)]
+    for e in envs:
+        e.reset()
+    vals = np.random.default_rng(seed).normal(-30, 5, (steps + 1, n_envs * W)).astype(np.float32)
+    t0 = time.perf_counter()
+    rew = np.zeros((steps, n_envs, W), np.float32)
+    for i, e in enumerate(envs):
+        for t in range(steps):
+            act = H.base_stock_policy(e, level)
+            _, r, _, _, _ = e.step({a: act[k] for k, a in enumerate(e.agents)})
+            rew[t, i] = [r[a] for a in e.agents]
+    gae_targets(rew.reshape(steps, -1), vals, GAMMA, LAM)
+    return time.perf_counter() - t0, n_envs * W * steps
+
+
+def cpu_port(env_dict, n_envs_per_worker, steps, workers, kind="port", z=2.0):
     import multiprocessing as mp
-    jobs = [(env_dict, n_envs_per_worker, steps, 17 + k) for k in range(workers)]
+    if kind == "reference":
+        from oracle import ref_harness as H
+        os.environ.update(H.STABLE_SORT_ENV)               # inherited by the workers: stable argsort ties (SURVEY 7.2-1)
+        fn, jobs = _ref_worker, [(env_dict, n_envs_per_worker, steps, 17 + k, z) for k in range(workers)]
+    else:
+        fn, jobs = _cpu_worker, [(env_dict, n_envs_per_worker, steps, 17 + k) for k in range(workers)]
     t0 = time.perf_counter()
     if workers == 1:
-        res = [_cpu_worker(jobs[0])]
+        res = [fn(jobs[0])]
     else:
         with mp.get_context("spawn").Pool(workers) as pool:
-            res = pool.map(_cpu_worker, jobs)
+            res = pool.map(fn, jobs)
     wall = time.perf_counter() - t0
     agent_steps = sum(r[1] for r in res)
     busy = max(r[0] for r in res)
     return agent_steps / busy, agent_steps, wall
+
+
+def reference_kind():
+    """"reference" when the reference's own env can be imported here (oracle/_ref made by oracle/make_ref.py, or the build
+    container's /root/reference), else "port" (oracle/inventory_oracle.py)."""
+    try:
+        from oracle import ref_harness as H
+        return "reference" if H.available() else "port"
+    except Exception:
+        return "port"
 
 
 # --------------------------------------------------------------------------------------- reference arm
@@ -234,28 +284,95 @@ def run_reference(args):
     large = args.workload == "large"
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    n_env, seg = (4, 25) if large else (32, 100)          # per worker and bench step: a few seconds
+    kind = reference_kind()
+    # per worker and bench step: the GPU arm's segment (SEG env steps) of a few environments - a few seconds of host work
+    n_env = (2 if large else 16) if kind == "reference" else (4 if large else 32)
+    seg = SEG
     values = []
     for _ in range(args.warmup):
-        cpu_port(env_dict, n_env, seg, workers)
+        cpu_port(env_dict, n_env, seg, workers, kind, args.z)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        v, n, _ = cpu_port(env_dict, n_env, seg, workers)
+        v, n, _ = cpu_port(env_dict, n_env, seg, workers, kind, args.z)
         values.append(v)
         total += n
     wall = time.perf_counter() - t0
     value = statistics.mean(values)
-    sample = f"{workers} processes x {n_env} envs x {seg} env steps + NumPy GAE per bench step (pre-sampled demand)"
-    W = env_dict["n_warehouses"]
+    what = ("the reference's own InventoryEnvironment (unmodified copy under oracle/_ref), its own Poisson demand sampler, "
+            "base-stock heuristic z=%g" % args.z) if kind == "reference" else "the CPU oracle port (oracle/inventory_oracle.py), pre-sampled demand"
+    sample = f"{workers} processes x {n_env} envs x {seg} env steps + NumPy GAE per bench step; {what}"
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * wall / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic", config=dict(cfg, segment_env_steps=seg, gamma=GAMMA, lam=LAM),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=workers, kind="port", sample=sample),
+                dtype="f64", data="synthetic", config=dict(cfg, segment_env_steps=seg, gamma=GAMMA, lam=LAM,
+                                                           actions=f"base-stock heuristic z={args.z}"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=workers, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
-                note="reference is pure Python (no C sources to build into oracle/_ref); timed: the CPU oracle port of its "
-                     "algorithm, pinned to the reference by tests/golden")
+                note=("timed: the reference's own Python env step + a NumPy GAE restatement (RLlib, which owns GAE in the "
+                      "reference, is not installable here)") if kind == "reference" else
+                     "oracle/_ref is missing (run oracle/make_ref.py where /root/reference is mounted): timed the CPU oracle port")
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- learner collective
+def learner_allreduce_record(dev, world, rank, minibatch_envs=8192):
+    """The only collective of the path: one MAPPO-sized PPO minibatch - actor [14->256->256->2], centralised
+    critic [56->64->64->1] (reference config_files/algorithms/mappo.yaml:43-55, wiring src/algorithms/mappo.py:142-157) -
+    forward + backward with the gradients all-reduced over NCCL from the backward hooks (rollout/ppo.py GradBuckets), timed
+    with CUDA events on every rank (max over ranks), and the bare all-reduce of the same flat buffer for its bus bandwidth."""
+    import torch
+    import torch.distributed as dist
+    from marlsc_b200.rollout import ActorCritic, PPOLearner
+    torch.manual_seed(0)
+    W, D, S = 3, 14, 2
+    pol = ActorCritic(D, W, S, actor_hidden=(256, 256), critic_hidden=(64, 64), critic_obs_type="global", logstd_init=-1.2,
+                      logstd_floor=-3.5).to(dev)
+    learner = PPOLearner(pol, lr=5e-4, grad_clip=5.0, use_kl_loss=True)
+    B = minibatch_envs
+    g = torch.Generator(device=dev).manual_seed(rank)
+    obs = torch.randn((B, W, D), device=dev, generator=g)
+    with torch.no_grad():
+        mean = pol.action_mean(obs)
+        act = mean + 0.3 * torch.randn(mean.shape, device=dev, generator=g)
+        logp = pol.log_prob(mean, act)
+    adv, tgt = torch.randn((B, W), device=dev, generator=g), torch.randn((B, W), device=dev, generator=g)
+    ls_old = pol.clamped_log_std().detach().reshape(1, S).clone()
+
+    def step():
+        learner.step_on(obs, act, logp, adv, tgt, mean, ls_old)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(5):
+        step()
+    ms_step = timed(step, 20)
+    n_par = sum(p.numel() for p in learner.params)
+    flat = torch.zeros(n_par, device=dev)
+    for _ in range(5):
+        dist.all_reduce(flat)
+    ms_ar = timed(lambda: dist.all_reduce(flat), 50)
+    nbytes = n_par * 4
+    big = torch.zeros(64 << 20, device=dev)                       # 256 MB: what the links sustain
+    for _ in range(3):
+        dist.all_reduce(big)
+    ms_big = timed(lambda: dist.all_reduce(big), 10)
+    bus = lambda b, ms: 2.0 * (world - 1) / world * b / (ms * 1e-3) / 1e9     # noqa: E731  (ring all-reduce bus bandwidth)
+    return dict(ranks=world, parameters=n_par, bytes=nbytes, buckets=len(learner.buckets.buckets),
+                minibatch_agent_samples=B * W, ms_minibatch_step_with_allreduce=ms_step, ms_allreduce_alone=ms_ar,
+                busbw_gbs_gradient_allreduce=bus(nbytes, ms_ar), busbw_gbs_256mb_allreduce=bus(big.numel() * 4, ms_big),
+                note="gradient all-reduce of a 0.3 MB buffer is latency-bound; the 256 MB figure shows the NVLink/NVSwitch "
+                     "bandwidth NCCL reaches on this box; no collective runs on the step / GAE path")
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -301,9 +418,11 @@ def run_ours(args):
         for dm in dense_demand:
             demand.append(env.lines_from_orders(dm))
         mean_lines = float(np.mean([dm.n_lines for dm in demand])) / E
-        if args.policy != "base_stock" or args.no_e2e:
-            dense_demand = dense_demand[:4]
+        spot_dense = dense_demand[:SEG]                # the oracle spot check replays the first segment
+        dense_demand = dense_demand[:4]
         torch.cuda.empty_cache()
+    else:
+        spot_dense = dense_demand[:SEG]
     if args.policy == "uniform":
         lo, hi = ACTION_RANGE
         actions = [(torch.rand((E, W, S), device=dev, generator=gen) * (hi - lo) + lo) for _ in range(n_in)]
@@ -471,7 +590,41 @@ def run_ours(args):
         except RuntimeError as ex:                                   # pinned allocation of 2 x 3.1 GB refused
             e2e_obs = dict(unavailable=str(ex)[:120])
 
-    # ---- everything on the device: base-stock policy kernel (K5) -> Poisson demand kernel (K4) -> K1 ------
+    # ---- parity spot check on the benchmarked trajectory itself (outside every timed region) -------------------
+    # 8 strided environments of this rank's batch, the first SEG steps of the replayed episode: the same demand and
+    # actions through the CPU oracle, compared with what the timed kernels compute at this batch size
+    spot = None
+    if rank == 0 and not args.no_spot_check:
+        from oracle.inventory_oracle import OracleEnv
+        picks = sorted(set(int(x) for x in np.linspace(0, E - 1, 8)))
+        env.reset(obs_out=obs_buf[0])
+        orcs = {i: OracleEnv(env_dict) for i in picks}
+        init = env.inventory[picks].cpu().numpy()
+        for k, i in enumerate(picks):
+            orcs[i].reset(init[k])
+        ok, worst = True, 0.0
+        for t in range(min(SEG, len(spot_dense))):
+            env.step(actions[t], orders=demand[t], obs_out=obs_buf[0], rewards_out=rewards[0])
+            dm = spot_dense[t]
+            off = dm.offsets.cpu().numpy()
+            inv_d, rew_d, obs_d, act_h = (env.inventory[picks].cpu().numpy(), rewards[0][picks].cpu().numpy(),
+                                          obs_buf[0][picks].cpu().numpy(), actions[t][picks].cpu().numpy())
+            for k, i in enumerate(picks):
+                a, b = int(off[i]), int(off[i + 1])
+                reg = dm.region[a:b].cpu().numpy()
+                q = dm.qty[a * S:b * S].cpu().numpy().reshape(b - a, S)
+                out = orcs[i].step(act_h[k], [(int(reg[j]), q[j].astype(float)) for j in range(b - a)])
+                ok = ok and np.array_equal(inv_d[k], out["inventory"])
+                err = max(float(np.max(np.abs(rew_d[k] - out["rewards"]) / (np.abs(out["rewards"]) + 1e-6))),
+                          float(np.max(np.abs(obs_d[k] - out["obs_local"]) / (np.abs(out["obs_local"]) + 1.0))))
+                worst = max(worst, err)
+        ok = ok and worst < 1e-5
+        spot = dict(envs=len(picks), steps=min(SEG, len(spot_dense)), ok=bool(ok), max_rel_err=worst,
+                    what="inventory exact, rewards / observations relative error vs oracle/inventory_oracle.py on strided "
+                         "environments of the timed batch (same demand, same actions)")
+        env.reset(obs_out=obs_buf[0])
+
+    # ---- everything on the device: demand sampler (K4) -> env step with the base-stock heuristic inside -----------
     on_device = None
     if args.workload == "large" and not args.no_e2e:
         from marlsc_b200.rollout import base_stock_levels
@@ -483,8 +636,11 @@ def run_ours(args):
             for i in range(SEG):
                 if env.timestep >= env.episode_length:
                     env.reset(obs_out=obs_buf[0])
-                env.base_stock_actions(lvl, out=act_buf)
-                env.step(act_buf, obs_out=obs_buf[i & 1], rewards_out=rewards[i])
+                if compact:                            # K4 writes lines, K1a' evaluates the heuristic itself
+                    env.step(None, obs_out=obs_buf[i & 1], rewards_out=rewards[i], base_stock_level=lvl)
+                else:
+                    env.base_stock_actions(lvl, out=act_buf)
+                    env.step(act_buf, obs_out=obs_buf[i & 1], rewards_out=rewards[i])
             compute_gae(rewards, values, GAMMA, LAM, adv_out=adv, targets_out=tgt)
 
         env.reset(obs_out=obs_buf[0])
@@ -503,8 +659,16 @@ def run_ours(args):
             dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
             ms = float(tmx.item())
         on_device = dict(value=E * W * SEG * 3 * world / (ms * 1e-3), unit=UNIT, ms_per_step=ms / 3,
-                         pipeline="per env step: marlsc_policy_base_stock (K5) -> marlsc_demand_sample (K4) -> marlsc_env_step (K1); "
-                                  "no host input at all", demand_overflow=env.demand_overflowed())
+                         pipeline=("per env step: marlsc_demand_sample_lines (K4, writes the sparse lines the step consumes) -> "
+                                   "marlsc_env_step with base_stock_level (the heuristic evaluated inside K1a'); no host input at all"
+                                   if compact else
+                                   "per env step: marlsc_policy_base_stock (K5) -> marlsc_demand_sample (K4) -> marlsc_env_step (K1); "
+                                   "no host input at all"), demand_overflow=env.demand_overflowed())
+
+    # ---- the path's only collective: the learner's gradient all-reduce (multi-GPU runs) -----------------------------
+    learner_ar = None
+    if world > 1:
+        learner_ar = learner_allreduce_record(dev, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -568,14 +732,24 @@ def run_ours(args):
                         frac=gae_bytes / (k2_avg * 1e-3) / 1e9 / peak, k2_ms_per_launch=k2_avg, bytes_per_launch=gae_bytes,
                         note="%.0f MB per launch: fits the 126 MB L2 only partly" % (gae_bytes / 1e6))
 
-    # ---- CPU baseline: the oracle port on a bounded sample, one core -------------------------------
+    # ---- CPU baseline on a bounded sample, one core: the reference itself (oracle/_ref) when present, else the port ----
     cpu = None
     if not args.no_cpu:
         large = args.workload == "large"
-        n_env, seg = (48, 100) if large else (256, 100)      # ~10-20 s of single-core work
-        v, n, wall = cpu_port(env_dict, n_env, seg, 1)
-        cpu = dict(value=v, unit=UNIT, cores=1, kind="port",
-                   sample=f"{n_env} envs x {seg} env steps + NumPy GAE, oracle/inventory_oracle.py, 1 process, {wall:.1f}s")
+        kind = reference_kind()
+        if kind == "reference":
+            n_env, seg = (24, SEG) if large else (128, 100)  # ~15 s of single-core work
+        else:
+            n_env, seg = (48, 100) if large else (256, 100)
+        v, n, wall = cpu_port(env_dict, n_env, seg, 1, kind, args.z)
+        src = ("the reference's own InventoryEnvironment (oracle/_ref, unmodified copy) under the base-stock heuristic"
+               if kind == "reference" else "oracle/inventory_oracle.py")
+        cpu = dict(value=v, unit=UNIT, cores=1, kind=kind,
+                   sample=f"{n_env} envs x {seg} env steps + NumPy GAE, {src}, 1 process, {wall:.1f}s")
+        if kind == "reference" and large:                   # the port's number as a second key (round-1 baseline)
+            v2, _, wall2 = cpu_port(env_dict, 24, SEG, 1, "port")
+            cpu["port_value"] = v2
+            cpu["port_sample"] = f"24 envs x {SEG} env steps, oracle/inventory_oracle.py, 1 process, {wall2:.1f}s"
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -591,7 +765,7 @@ def run_ours(args):
                             else "small working set; L2 resident (launch-latency bound)",
                             distinct_input_steps=n_in),
                 roofline=roofline, roofline_gae=roofline_gae, cpu_baseline=cpu, e2e=e2e, e2e_with_observations=e2e_obs,
-                on_device_pipeline=on_device, gpu_launches=int(launches), clocks=clk)
+                on_device_pipeline=on_device, parity_spot_check=spot, learner_allreduce=learner_ar, gpu_launches=int(launches), clocks=clk)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -692,6 +866,7 @@ def main():
     ap.add_argument("--z", type=float, default=2.0, help="base-stock safety factor")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-spot-check", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -29,7 +29,18 @@ def _build(registry: Dict[str, Type], label: str, field: str, env_config: Enviro
     return registry[kind](context, component_config)
 
 
+def _check_component(kind: str, name: str, cls: Type) -> None:
+    """A registered component is a device component spec: the step runs in CUDA kernels, so a class cannot bring its
+    own arithmetic (the reference's ``allocate`` / ``calculate_lost_sales`` / ``calculate`` hooks) - it contributes an
+    enum plus parameter tables through ``spec_fields()`` and may only select among the behaviours the kernels implement."""
+    if not isinstance(cls, type) or not callable(getattr(cls, "spec_fields", None)):
+        raise TypeError(f"{kind} '{name}': {getattr(cls, '__name__', cls)} must be a class with a spec_fields() method "
+                        "(subclass marlsc_b200.components.base.DeviceComponent or one of the registered components); "
+                        "host-side callables cannot run inside the CUDA step")
+
+
 def register_demand_sampler(name: str, sampler_class: Type):
+    _check_component("demand sampler", name, sampler_class)
     DEMAND_SAMPLER_REGISTRY[name] = sampler_class
 
 
@@ -38,6 +49,7 @@ def get_demand_sampler(env_config: EnvironmentConfig, context: Optional[Environm
 
 
 def register_demand_allocator(name: str, allocator_class: Type):
+    _check_component("demand allocator", name, allocator_class)
     DEMAND_ALLOCATOR_REGISTRY[name] = allocator_class
 
 
@@ -46,6 +58,7 @@ def get_demand_allocator(env_config: EnvironmentConfig, context: Optional[Enviro
 
 
 def register_lead_time_sampler(name: str, sampler_class: Type):
+    _check_component("lead time sampler", name, sampler_class)
     LEAD_TIME_SAMPLER_REGISTRY[name] = sampler_class
 
 
@@ -54,6 +67,7 @@ def get_lead_time_sampler(env_config: EnvironmentConfig, context: Optional[Envir
 
 
 def register_lost_sales_handler(name: str, handler_class: Type):
+    _check_component("lost sales handler", name, handler_class)
     LOST_SALES_HANDLER_REGISTRY[name] = handler_class
 
 
@@ -62,6 +76,7 @@ def get_lost_sales_handler(env_config: EnvironmentConfig, context: Optional[Envi
 
 
 def register_reward_calculator(name: str, calculator_class: Type):
+    _check_component("reward calculator", name, calculator_class)
     REWARD_CALCULATOR_REGISTRY[name] = calculator_class
 
 

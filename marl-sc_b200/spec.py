@@ -79,6 +79,13 @@ def build_env_spec(env_config: EnvironmentConfig, obs_normalization: str = "off"
                    seed_manager=None, data_mode: str = "train", preprocessed_data=None) -> EnvSpec:
     if obs_normalization not in _capi.NORM:
         raise ValueError(f"Unknown obs_normalization: {obs_normalization}. Available: {list(_capi.NORM)}")
+    if obs_normalization == "meanstd":
+        # like the reference's env, this mode leaves the observations raw (multi_env.py:700-702 only knows the fixed
+        # statistics); the running filter lives outside the env - RLlib's MeanStdFilter connector there (ippo.py:173-176),
+        # marlsc_b200.rollout.MeanStdFilter (RolloutCollector(obs_filter=...)) here. Say so instead of silently doing nothing.
+        import warnings
+        warnings.warn("obs_normalization='meanstd': the env emits raw observations; apply the running filter in the rollout "
+                      "(marlsc_b200.rollout.MeanStdFilter via RolloutCollector(obs_filter=...))", stacklevel=2)
     empirical = env_config.components.demand_sampler.type == "empirical"
     ctx = context or create_environment_context(env_config, seed_manager=seed_manager, data_mode=data_mode,
                                                 preprocessed_data=preprocessed_data,

@@ -26,8 +26,22 @@ import os
 import sys
 from typing import Any, Dict, List, Optional
 
-REF_ROOT = os.environ.get("MARLSC_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "ref_shim")
+
+
+def _find_root() -> str:
+    """The reference tree: MARLSC_REFERENCE_ROOT, else /root/reference (build container), else oracle/_ref - the
+    unmodified copy of the env path that oracle/make_ref.py makes so that the reference itself can be timed on the GPU
+    box's host cores (git-ignored, travels with gpurun)."""
+    cands = [os.environ.get("MARLSC_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "src", "environment")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 STABLE_SORT_ENV = {
     "NPY_DISABLE_CPU_FEATURES": "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2 FMA3"

@@ -416,3 +416,49 @@ def test_empirical_sampler_replays_reference_orders():
                                cfg.components.demand_sampler)
     with pytest.raises(ValueError, match="requires preprocessed_data"):
         EmpiricalDemandSampler(create_environment_context(cfg), cfg.components.demand_sampler)
+
+
+# ------------------------------------------------------------------ boundary hygiene
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/marlsc_b200.h as the C compiler lays them out against the ctypes
+    mirrors in _capi.py (a binding that is a field short reads garbage; INTEGRATION.md's stub is generated from these)."""
+    import subprocess
+    from marlsc_b200 import _capi
+    structs = {"marlsc_env_spec_t": _capi.EnvSpecC, "marlsc_env_state_t": _capi.EnvStateC, "marlsc_step_io_t": _capi.StepIOC,
+               "marlsc_host_step_t": _capi.HostStepC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "marlsc_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    # and the header has no field the mirrors lack
+    hdr = open(os.path.join(ROOT, "include", "marlsc_b200.h")).read()
+    for cname, cls in structs.items():
+        body = re.search(r"typedef struct \w+ \{([^}]*)\} " + cname + ";", hdr).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = re.findall(r"(\w+)\s*;", body)
+        assert names == [f for f, _ in cls._fields_], cname
+
+
+def test_registry_rejects_classes_without_spec_fields_and_meanstd_warns():
+    class HostOnlyAllocator:                     # the reference's kind of component: arithmetic in Python
+        def allocate(self, orders, inventories):
+            return None
+    with pytest.raises(TypeError, match="spec_fields"):
+        registry.register_demand_allocator("host_only", HostOnlyAllocator)
+    assert "host_only" not in registry.DEMAND_ALLOCATOR_REGISTRY
+    from marlsc_b200.spec import build_env_spec
+    cfg = environment_config_from_dict(small_default())
+    with pytest.warns(UserWarning, match="running filter"):
+        spec = build_env_spec(cfg, obs_normalization="meanstd")
+    assert spec.scalars["obs_norm"] == 0
