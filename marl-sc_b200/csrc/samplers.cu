@@ -66,8 +66,9 @@ constexpr int kCdf = 16;     // tabulated Poisson CDF entries per (region, SKU):
 struct DemandParams {
   const float* lam_orders;   // [R]
   const float* prob;         // [R]
-  const float* lam_qty;      // [R,S]
-  const float* cdf_qty;      // [R,S,kCdf]
+  const float* lam_qty;      // [R,S], or [R] when the rate does not vary over the SKUs of a region (sku_stride 0)
+  const float* cdf_qty;      // [R,S,kCdf], or [R,kCdf]: 3 KB that stay in L1 instead of 320 KB of L2 lookups
+  int region_stride, sku_stride;   // cell (r, s) of lam_qty / cdf_qty is entry r * region_stride + s * sku_stride
 };
 
 // Quantity max(1, Poisson(lambda)) by inversion: the smallest k with u <= P(X <= k), found by a four-step search of the
@@ -142,7 +143,7 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
               const float uq = (float)(c[j] >> 12) * (1.0f / 1048576.0f);
               int q = 0;
               if (ub < p) {
-                q = quantity_from(dp.cdf_qty + (size_t)(rr * S + s) * kCdf, dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
+                q = quantity_from(dp.cdf_qty + (size_t)(rr * dp.region_stride + s * dp.sku_stride) * kCdf, dp.lam_qty[rr * dp.region_stride + s * dp.sku_stride], uq, ub * (1.0f / p));
                 q = q < 1 ? 1 : (q > 255 ? 255 : q);
               }
               qty_e[(long long)row * S + s] = (uint8_t)q;
@@ -193,7 +194,7 @@ sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t 
               const float ub = (float)(c[j] & 0xfffu) * (1.0f / 4096.0f);
               const float uq = (float)(c[j] >> 12) * (1.0f / 1048576.0f);
               if (ub < p) {
-                int q = quantity_from(dp.cdf_qty + (size_t)(rr * S + s) * kCdf, dp.lam_qty[rr * S + s], uq, ub * (1.0f / p));
+                int q = quantity_from(dp.cdf_qty + (size_t)(rr * dp.region_stride + s * dp.sku_stride) * kCdf, dp.lam_qty[rr * dp.region_stride + s * dp.sku_stride], uq, ub * (1.0f / p));
                 q = q < 1 ? 1 : (q > 255 ? 255 : q);
                 if (cnt < stride) out[(long long)(cnt >> 1) * 64 + (cnt & 1)] = (uint16_t)(q | (rm << 8) | (j << 14));
                 else over = true;
@@ -243,7 +244,7 @@ sample_demand_thread_kernel(DemandParams dp, int R, int S, long long E, uint64_t
         const float uq = (float)(d[j] >> 12) * (1.0f / 1048576.0f);
         int q = 0;
         if (ub < p) {
-          q = quantity_from(dp.cdf_qty + (size_t)(r * S + s) * kCdf, dp.lam_qty[r * S + s], uq, ub * (1.0f / p));
+          q = quantity_from(dp.cdf_qty + (size_t)(r * dp.region_stride + s * dp.sku_stride) * kCdf, dp.lam_qty[r * dp.region_stride + s * dp.sku_stride], uq, ub * (1.0f / p));
           q = q < 1 ? 1 : (q > 255 ? 255 : q);
         }
         qty_e[(long long)row * S + s] = (uint8_t)q;
@@ -357,7 +358,16 @@ int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda
                          const double* lambda_quantity, int device, marlsc_demand_t** out) {
   if (!out || !lambda_orders || !probability_skus || !lambda_quantity) return set_error(MARLSC_EINVAL, "null argument");
   if (n_regions < 1 || n_skus < 1) return set_error(MARLSC_EINVAL, "n_regions and n_skus must be positive");
-  const size_t n_cells = (size_t)n_regions * n_skus;
+  // rates that do not vary over the SKUs of a region (the reference's scalar and per-region forms): one CDF row per region
+  bool per_region = true;
+  for (int r = 0; r < n_regions && per_region; ++r)
+    for (int s = 1; s < n_skus; ++s)
+      if (lambda_quantity[(size_t)r * n_skus + s] != lambda_quantity[(size_t)r * n_skus]) {
+        per_region = false;
+        break;
+      }
+  const int cols = per_region ? 1 : n_skus;
+  const size_t n_cells = (size_t)n_regions * cols;
   std::vector<float> host((size_t)2 * n_regions + n_cells * (1 + kCdf));
   for (int r = 0; r < n_regions; ++r) {
     if (!(lambda_orders[r] >= 0.0) || !(probability_skus[r] >= 0.0 && probability_skus[r] <= 1.0))
@@ -365,11 +375,13 @@ int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda
     host[r] = (float)lambda_orders[r];
     host[n_regions + r] = (float)probability_skus[r];
   }
-  for (size_t i = 0; i < (size_t)n_regions * n_skus; ++i) {
+  for (size_t i = 0; i < (size_t)n_regions * n_skus; ++i)
     if (!(lambda_quantity[i] >= 0.0)) return set_error(MARLSC_EINVAL, "lambda_quantity must be >= 0");
-    host[2 * n_regions + i] = (float)lambda_quantity[i];
+  for (size_t i = 0; i < n_cells; ++i) {
+    const double lq = lambda_quantity[per_region ? i * n_skus : i];
+    host[2 * n_regions + i] = (float)lq;
     // P(X <= k) for the float32 rate the kernel sees, accumulated in double
-    const double lam = (double)(float)lambda_quantity[i];
+    const double lam = (double)(float)lq;
     double pk = std::exp(-lam), F = pk;
     for (int k = 0; k < kCdf; ++k) {
       if (k > 0) {
@@ -396,6 +408,8 @@ int marlsc_demand_create(int32_t n_regions, int32_t n_skus, const double* lambda
   d->dp.prob = d->blob + n_regions;
   d->dp.lam_qty = d->blob + 2 * n_regions;
   d->dp.cdf_qty = d->blob + 2 * n_regions + n_cells;
+  d->dp.region_stride = cols;
+  d->dp.sku_stride = per_region ? 0 : 1;
   *out = d;
   return MARLSC_OK;
 }
