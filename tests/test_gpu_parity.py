@@ -1166,3 +1166,34 @@ def test_config2_4096_envs_100_steps_strided_oracle_check():
             assert bool(trunc) == bool(out["trunc"])
     assert bool(trunc) and not env.demand_overflowed()
     env.close()
+
+
+def test_graphed_episode_equals_eager_steps():
+    """reset + T steps captured in one CUDA graph (rollout/graph.py) must reproduce the eager step-by-step results, and a
+    replay after the actions were overwritten in place must follow the new actions."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv, DeviceOrders
+    from marlsc_b200.rollout import GraphedEpisode
+    g = Golden("small_default")
+    cfg = environment_config_from_dict(small_default())
+    E, T = g.N, 30
+    orders = [DeviceOrders.from_host(step_orders(g, t), "cuda:0") for t in range(T)]
+    act = torch.from_numpy(np.ascontiguousarray(g["actions"][:, :T].transpose(1, 0, 2, 3))).cuda()
+    init = torch.from_numpy(g["init_inventory"])
+    env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False)
+    ep = GraphedEpisode(env, act, orders, init_inventory=init)
+    rew = ep.replay().clone()
+    torch.cuda.synchronize()
+    for t in range(T):
+        np.testing.assert_allclose(rew[t].cpu().numpy(), g["rewards"][:, t], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ep.obs[t + 1].cpu().numpy(), g["obs_local"][:, t], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(env.inventory.cpu().numpy(), g["inventory"][:, T - 1])
+    act.mul_(0.5)                                     # new actions in the same buffer: the replay must pick them up
+    rew2 = ep.replay().clone()
+    ref = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False)
+    ref.reset(init_inventory=init)
+    for t in range(T):
+        _, r, _ = ref.step(act[t], orders=orders[t])
+        assert torch.equal(r, rew2[t])
+    assert not torch.equal(rew, rew2)
