@@ -314,6 +314,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------- host placement
+def bind_to_gpu_cpus(index: int):
+    """Pin this process to the CPU cores NVML reports as local to GPU ``index`` (same NUMA node / PCIe root). Pinned host
+    buffers are placed by first touch, so the end-to-end arm's staging memory ends up next to the GPU it feeds: eight ranks
+    streaming from one socket's memory was what held round 1's 8-GPU end-to-end number at 0.42 of linear."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1 and 64 * i + b < n_cpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return dict(cpus=len(cpus), first=cpus[0], last=cpus[-1])
+    except Exception as ex:                          # no NVML, restricted cpuset: keep the default placement
+        return dict(error=str(ex)[:80])
+    return None
+
+
 # --------------------------------------------------------------------------------------- learner collective
 def learner_allreduce_record(dev, world, rank, minibatch_envs=8192):
     """The only collective of the path: one MAPPO-sized PPO minibatch - actor [14->256->256->2], centralised
@@ -392,6 +412,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local)                   # pinned staging buffers then live next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     env_dict, cfg_desc = workload(args.workload)
@@ -574,7 +595,7 @@ def run_ours(args):
         dt = timed(host_segment, e2e_steps)
         e2e = dict(value=E * W * SEG * e2e_steps * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d_seg),
                    d2h_bytes_per_step=int(d2h_seg), ms_per_step=1e3 * dt / e2e_steps,
-                   h2d_gbs_per_gpu=h2d_seg * e2e_steps / dt / 1e9, api=api,
+                   h2d_gbs_per_gpu=h2d_seg * e2e_steps / dt / 1e9, api=api, host_cpu_binding=numa,
                    segments=e2e_steps, gpu_launches=int(L.marlsc_launch_count() - launches_e2e0))
         # the same with every step's observations copied back to the host (what a host-side policy would need):
         # 4*W*obs_dim bytes per env step device->host, PCIe-bound by construction
