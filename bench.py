@@ -742,7 +742,14 @@ def run_ours(args):
     if per_launch:
         ms = [statistics.mean(x[i] for x in per_launch) for i in range(n_launch)]
         WS, Lmax, od = W * S, env.max_expected_lead_time, env.obs_dim
-        if split:
+        if split and compact:
+            # the compact split step (csrc/env_compact.cu): bytes each launch needs per env step with the layout's element
+            # sizes; inventory and the home-demand plane pass through HBM between the kernels
+            parts = [("compact_place_kernel (K1a')", WS * (4 + 2 + 2 + Lmax + 1 + 2) + 4 * W * Lmax * S + 8 * W, "hbm"),
+                     ("compact_alloc_kernel (K1b')", WS * (2 + 2) + 2 * mean_lines + 4 + 8 * W, "issue"),
+                     ("compact_feature_kernel (K1c')", WS * (2 + 2 + 2) + 4 * W * (od - Lmax * S) + 20 * W + 1, "hbm"),
+                     ("(K1d: rewards are written by K1c' with agent-scope rewards)", 0, "-")]
+        elif split:
             # algorithmic bytes per env step of each launch (int32 state, fp32 obs), including what the split itself adds
             # (inventory and the home-demand plane pass through HBM between the kernels)
             parts = [("env_place_kernel (K1a)", 4 * WS * (2 * Lmax + 6), "hbm"),
@@ -754,10 +761,14 @@ def run_ours(args):
         else:
             parts = [("env_step_kernel (fused K1)", b_env, "hbm")]
         for (name, b, bound), t_ms in zip(parts, ms):
+            if b == 0:
+                continue
             kernels.append(dict(kernel=name, ms_per_launch=t_ms, bound=bound, algorithmic_bytes_per_env_step=b,
                                 achieved=b * E / (t_ms * 1e-3) / 1e9, frac=b * E / (t_ms * 1e-3) / 1e9 / peak))
     roofline = dict(bound="hbm",
-                    kernel=("env step K1 = place + allocate + features + rewards launches (csrc/env_split.cuh)" if split
+                    kernel=("env step K1 = compact_place + compact_alloc + compact_feature launches over the compact layout "
+                            "(csrc/env_compact.cu)" if (split and compact)
+                            else "env step K1 = place + allocate + features + rewards launches (csrc/env_split.cuh)" if split
                             else "env_step_compact_kernel (K1, one fused launch per env step, csrc/env_compact.cu)" if compact
                             else "env_step_kernel (K1)"),
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
@@ -875,10 +886,55 @@ def run_rollout(args):
         tm = torch.tensor([ms], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
+    # the learner's minibatch step on its own (MAPPO): forward + K6 + backward with the bucketed all-reduce, max over ranks
+    learner_rec = None
+    if mappo:
+        sl = (slice(0, 1), slice(0, min(E, 65536)))
+        for _ in range(3):
+            learner.minibatch_step(ro, *sl)
+        barrier()
+        la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bytes0 = learner.all_reduce_grads()
+        la.record()
+        for _ in range(10):
+            learner.minibatch_step(ro, *sl)
+        lb.record()
+        barrier()
+        lms = la.elapsed_time(lb) / 10
+        if world > 1:
+            tl = torch.tensor([lms], device=dev)
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            lms = float(tl.item())
+        learner_rec = dict(ms_minibatch_step=lms, minibatch_agent_samples=min(E, 65536) * 3,
+                           allreduce_bytes_per_step=(learner.all_reduce_grads() - bytes0) // 10,
+                           buckets=len(learner.buckets.buckets), ranks=world)
+    # K1 at this shape: the library's own events around the step's launches
+    k1 = None
+    if rank == 0:
+        env.set_timing(True)
+        obs_t, times = col.obs[0], []
+        env.reset(obs_out=obs_t)
+        act0 = torch.zeros((E, 3, 2), device=dev)
+        for _ in range(8):
+            env.step(act0, obs_out=obs_t, rewards_out=col.rewards[0])
+            times.append(sum(env.last_step_timing()))
+        env.set_timing(False)
+        k1_ms = statistics.mean(times[2:])
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+        b_env = algorithmic_bytes_per_env_step(3, 2, env.max_expected_lead_time, env.obs_dim, 0.0)   # demand drawn on the device
+        k1 = dict(bound="hbm", kernel="env_step_kernel (K1, thread per environment)", k1_ms_per_launch=k1_ms,
+                  algorithmic_bytes_per_env_step=b_env, achieved=b_env * E / (k1_ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                  frac=b_env * E / (k1_ms * 1e-3) / 1e9 / peak, traffic=None,
+                  note="the step of this shape is a small part of the rollout: the MLP forwards (cuBLAS) dominate")
     if rank == 0:
         value = E * 3 * T * args.steps * world / (ms * 1e-3)
         r_host = ro.rewards.mean().item()                       # device->host read of the rollout's result
         print(json.dumps(dict(
+            roofline=k1, learner_allreduce=learner_rec,
+            e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=4,
+                     note="the whole rollout runs on the device (policy, demand, env, buffer, GAE); the only host traffic is "
+                          "the 4-byte mean reward read back per rollout"),
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
             higher_is_better=True, scaling="strong" if mappo else "weak", vs_baseline=None, dtype="int32 state / fp32 obs, MLPs, GAE",
             data="synthetic", gpu_launches=int(L.marlsc_launch_count() - l0),

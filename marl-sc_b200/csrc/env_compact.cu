@@ -977,14 +977,14 @@ int launch_step_nch(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cuda
   const size_t smem = (size_t)lay.t_bytes + (size_t)kCompactWarps * lay.warp_bytes;
   if ((int)smem > a.max_smem_optin)
     return set_error(MARLSC_EUNSUPPORTED, "compact step: shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit");
-  static int configured_for[64] = {0};                // per device: the attributes belong to the device's context
+  static int configured_for[kMaxDevices] = {0};       // per device: the attributes belong to the device's context
   int dev = 0;
   MARLSC_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && configured_for[dev] < (int)smem) {
+  if (dev >= kMaxDevices || configured_for[dev] < (int)smem) {
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_compact_kernel<NCH, MS, FS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_compact_kernel<NCH, MS, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_for[dev] = (int)smem;
+    if (dev < kMaxDevices) configured_for[dev] = (int)smem;
   }
   const unsigned grid = (unsigned)((a.st.num_envs + kCompactWarps - 1) / kCompactWarps);
   // bulk L2 prefetches of an environment's state blocks need 16-byte aligned addresses and sizes
@@ -1002,14 +1002,14 @@ int launch_split_nch(const LaunchArgs& a, const marlsc_step_io_t& io, const Spli
   const size_t smem = (size_t)lay.t_bytes + (size_t)kCompactWarps * lay.warp_bytes;
   if ((int)smem > a.max_smem_optin)
     return set_error(MARLSC_EUNSUPPORTED, "compact step: shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit");
-  static int configured_for[64] = {0};                // per device: the attributes belong to the device's context
+  static int configured_for[kMaxDevices] = {0};       // per device: the attributes belong to the device's context
   int dev = 0;
   MARLSC_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && configured_for[dev] < (int)smem) {
+  if (dev >= kMaxDevices || configured_for[dev] < (int)smem) {
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)compact_alloc_kernel<NCH, FS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)compact_alloc_kernel<NCH, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_for[dev] = (int)smem;
+    if (dev < kMaxDevices) configured_for[dev] = (int)smem;
   }
   const int64_t rows = a.st.num_envs * a.ds.W;
   const unsigned grid_rows = (unsigned)((rows + 7) / 8);

@@ -108,16 +108,20 @@ int launch_step_caps(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cud
   const size_t smem = step_smem_bytes(a.ds, G);
   if ((int)smem > a.max_smem_optin)
     return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
-  static thread_local size_t configured = 0;
-  static thread_local bool carveout = false;
-  if (!carveout) {   // the scratch is what bounds residency: ask for the largest shared-memory carveout
+  // kernel attributes belong to the device (context) they were set on: cache per device, not per thread
+  static std::atomic<size_t> configured[kMaxDevices];
+  static std::atomic<bool> carveout[kMaxDevices];
+  int dev = 0;
+  MARLSC_CUDA(cudaGetDevice(&dev));
+  const int di = dev < kMaxDevices ? dev : kMaxDevices - 1;
+  if (dev >= kMaxDevices || !carveout[di].load()) {   // the scratch is what bounds residency: ask for the largest shared-memory carveout
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_kernel<G, SPL, CAPS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
-    carveout = true;
+    carveout[di].store(true);
   }
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024 && (dev >= kMaxDevices || smem > configured[di].load())) {
     MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_step_kernel<G, SPL, CAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[di].store(smem);
   }
   const unsigned grid = (unsigned)((a.st.num_envs + teams - 1) / teams);
   env_step_kernel<G, SPL, CAPS><<<grid, Block<G>::threads, smem, s>>>(a.ds, a.st, io, t);

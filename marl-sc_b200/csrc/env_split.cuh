@@ -319,7 +319,8 @@ env_reward_kernel(const __grid_constant__ DevSpec sp, int64_t num_envs, const do
                   const double* __restrict__ cost_rows, float* __restrict__ rewards, uint8_t* __restrict__ truncated, int t);
 
 // K1b for one-warp teams (env_alloc.cu): 1 = launched, 0 = not applicable (the caller launches env_alloc_kernel), < 0 = error
-int launch_alloc_warp(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, double* cost_alloc, int t, cudaStream_t s);
+int launch_alloc_warp(int spl, const LaunchArgs& a, const marlsc_step_io_t& io, double* cost_alloc, int t, cudaStream_t s,
+                      bool prepare_only = false);
 
 // One launcher per (G, SPL); defined through MARLSC_DEFINE_SPLIT in the per-width translation units.
 template <int G, int SPL>
@@ -328,36 +329,43 @@ int launch_split_t(const LaunchArgs& a, const marlsc_step_io_t& io, const SplitW
   constexpr int SPLR = G > 32 ? SPL * (G / 32) : SPL;
   const int64_t rows = a.st.num_envs * a.ds.W;
   const unsigned grid_rows = (unsigned)((rows + 128 / GR - 1) / (128 / GR));
+  // every check and attribute call of the allocation launch first: a failure must not leave the state half-stepped
+  bool warp_chains = false;
+  if constexpr (G == 32) {
+    const int rc = launch_alloc_warp(SPL, a, io, wk.cost_alloc, t, s, true);
+    if (rc < 0) return rc;
+    warp_chains = rc == 1;
+  }
+  const size_t smem = step_smem_bytes(a.ds, G);
+  if (!warp_chains) {
+    if ((int)smem > a.max_smem_optin)
+      return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
+    static std::atomic<size_t> configured[kMaxDevices];   // per device: the attributes belong to the device's context
+    static std::atomic<bool> carveout[kMaxDevices];
+    int dev = 0;
+    MARLSC_CUDA(cudaGetDevice(&dev));
+    const int di = dev < kMaxDevices ? dev : kMaxDevices - 1;
+    if (dev >= kMaxDevices || !carveout[di].load()) {
+      MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_alloc_kernel<G, SPL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+      carveout[di].store(true);
+    }
+    if (smem > 48 * 1024 && (dev >= kMaxDevices || smem > configured[di].load())) {
+      MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_alloc_kernel<G, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[di].store(smem);
+    }
+  }
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[0], s));
   env_place_kernel<GR, SPLR><<<grid_rows, 128, 0, s>>>(a.ds, a.st, io, t);
   MARLSC_CUDA(cudaGetLastError());
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[1], s));
-
-  // one-warp teams allocate through the whole-step lane chains of env_alloc.cuh when their scratch fits
-  bool warp_chains = false;
-  if constexpr (G == 32) {
+  if (warp_chains) {
     const int rc = launch_alloc_warp(SPL, a, io, wk.cost_alloc, t, s);
     if (rc < 0) return rc;
-    warp_chains = rc == 1;
-  }
-  if (!warp_chains) {
-  const size_t smem = step_smem_bytes(a.ds, G);
-  if ((int)smem > a.max_smem_optin)
-    return set_error(MARLSC_EUNSUPPORTED, "shared-memory scratch of " + std::to_string(smem) + " bytes per CTA does not fit; use a wider team");
-  static thread_local size_t configured = 0;
-  static thread_local bool carveout = false;
-  if (!carveout) {
-    MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_alloc_kernel<G, SPL>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (int)cudaSharedmemCarveoutMaxShared));
-    carveout = true;
-  }
-  if (smem > 48 * 1024 && smem > configured) {
-    MARLSC_CUDA(cudaFuncSetAttribute((const void*)env_alloc_kernel<G, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const unsigned grid_envs = (unsigned)((a.st.num_envs + Block<G>::teams - 1) / Block<G>::teams);
-  env_alloc_kernel<G, SPL><<<grid_envs, Block<G>::threads, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
-  MARLSC_CUDA(cudaGetLastError());
+  } else {
+    const unsigned grid_envs = (unsigned)((a.st.num_envs + Block<G>::teams - 1) / Block<G>::teams);
+    env_alloc_kernel<G, SPL><<<grid_envs, Block<G>::threads, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
+    MARLSC_CUDA(cudaGetLastError());
   }
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[2], s));
 

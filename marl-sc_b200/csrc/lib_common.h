@@ -8,6 +8,7 @@
 #include "../../include/marlsc_b200.h"
 
 namespace marlsc {
+constexpr int kMaxDevices = 64;   // per-device caches of kernel attributes
 extern thread_local std::string g_last_error;
 extern std::atomic<long long> g_launches;
 int set_error(int code, const std::string& msg);

@@ -462,3 +462,21 @@ def test_registry_rejects_classes_without_spec_fields_and_meanstd_warns():
     with pytest.warns(UserWarning, match="running filter"):
         spec = build_env_spec(cfg, obs_normalization="meanstd")
     assert spec.scalars["obs_norm"] == 0
+
+
+def test_integration_md_stub_structs_match_the_binding():
+    """The reference-side ctypes stub printed in INTEGRATION.md must lay its structs out exactly like the binding the
+    tests use (round 1's stub was two fields short of marlsc_step_io_t)."""
+    from marlsc_b200 import _capi
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = md[md.index("# src/environment/envs/_b200.py"):]
+    block = block[:block.index("def make_env")]
+    block = "\n".join(l for l in block.splitlines() if not l.startswith("lib = "))
+    ns = {}
+    exec(block, ns)
+    for mine, theirs in ((ns["Spec"], _capi.EnvSpecC), (ns["State"], _capi.EnvStateC), (ns["StepIO"], _capi.StepIOC)):
+        assert [f for f, _ in mine._fields_] == [f for f, _ in theirs._fields_]
+        assert ctypes.sizeof(mine) == ctypes.sizeof(theirs)
+        for f, _ in mine._fields_:
+            assert getattr(mine, f).offset == getattr(theirs, f).offset, f
+    assert "abi_version=2" in md and _capi.ABI_VERSION == 2
