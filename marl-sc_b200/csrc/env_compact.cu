@@ -515,25 +515,30 @@ env_step_compact_kernel(const __grid_constant__ DevSpec sp, const __grid_constan
 // their slots there (slot lead-1), and the image goes out twice: back to the ring as whole 32-bit words (the first
 // version stored single bytes: each touched a 32-byte sector of its own, 25 L1 wavefronts per instruction), and to the
 // observation as floats, lane l taking bytes l + 32 j so that every store instruction covers 128 consecutive bytes.
-template <bool MS, int FS>
+// POLICY: the base-stock heuristic evaluated in place of given actions (its own instantiation: the extra live values cost
+// the ordinary one a resident CTA per SM)
+// LT: the lead-time horizon L as a compile-time constant (1..16; the plane loops then unroll without predicates: the
+// runtime-L form spent 16 instructions per plane load on them), 0 = read it from the spec.
+template <bool MS, bool POLICY, int LT>
 __global__ void __launch_bounds__(256)
 compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                      const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_rows, int t) {
   extern __shared__ __align__(16) unsigned char smem[];           // [8 warps][L * S] row images
-  __shared__ int s_poff[kCompactMaxL];
-  const int W = sp.W, S = sp.S, L = sp.L, WS = W * S;
-  if (threadIdx.x < kCompactMaxL) s_poff[threadIdx.x] = (int)((unsigned)(t + 1 + threadIdx.x) % (unsigned)L) * (S >> 2);
-  __syncthreads();
+  constexpr int KMAX = LT ? LT : kCompactMaxL;
+  const int W = sp.W, S = sp.S, L = LT ? LT : sp.L, WS = W * S;
   const int lane = threadIdx.x & 31;
   const unsigned row = blockIdx.x * 8u + (threadIdx.x >> 5);
   if (row >= (unsigned)st.num_envs * (unsigned)W) return;
   const unsigned eu = row / (unsigned)W;
   const int w = (int)(row - eu * (unsigned)W);
   const int64_t e = eu;
-  const bool tail = lane < S - 32 * FS;
   const bool mine = 4 * lane < S;
   const int c4 = mine ? lane : 0;
   const int S4 = S >> 2, pa = t % L;
+  // 32-bit word offset of pipeline slot k's plane inside the ring row: plane (t + 1 + k) % L, walked with one add per slot
+  const int LS4 = L * S4;
+  int po0 = (pa + 1) * S4;
+  po0 = po0 == LS4 ? 0 : po0;
   const bool need_hist = sp.need_hist != 0;
   uint32_t* const row4 = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(st.ring_qty) + (e * WS + (int64_t)w * S) * L) + c4;
   // every load of the row first
@@ -541,25 +546,30 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
   uint32_t aqw = 0u, arr4 = 0u, le4 = 0x01010101u;
   uint2 iv = make_uint2(0u, 0u);
   uint2* const inv4 = reinterpret_cast<uint2*>(static_cast<uint16_t*>(st.inventory) + e * WS + w * S) + c4;
-  uint32_t x[kCompactMaxL - 1];
+  uint32_t x[KMAX > 1 ? KMAX - 1 : 1];
   if (mine) {
     if (io.action_qty) aqw = reinterpret_cast<const uint32_t*>(io.action_qty + e * WS + w * S)[c4];
     else if (io.actions) a4 = reinterpret_cast<const float4*>(io.actions + e * WS + w * S)[c4];
     iv = *inv4;
     arr4 = row4[pa * S4];
     le4 = reinterpret_cast<const uint32_t*>(sp.lead_u8 + w * S)[c4];
+    int po = po0;
 #pragma unroll
-    for (int k = 0; k < kCompactMaxL - 1; ++k)
-      if (k < L - 1) x[k] = row4[s_poff[k]];
+    for (int k = 0; k < KMAX - 1; ++k)
+      if (k < L - 1) {
+        x[k] = row4[po];
+        po += S4;
+        po = po == LS4 ? 0 : po;
+      }
   }
-  const bool policy = !io.actions && !io.action_qty;  // base-stock heuristic in place of given actions (marlsc_step_io.base_stock_level)
+  constexpr bool policy = POLICY;                     // base-stock heuristic in place of given actions (marlsc_step_io.base_stock_level)
   float4 lv4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (policy && mine)
     lv4 = reinterpret_cast<const float4*>(io.base_stock_level + (io.base_stock_per_env ? e * WS : 0) + w * S)[c4];
   const uint32_t img = sm_addr(smem) + (threadIdx.x >> 5) * (uint32_t)(L * S);   // this warp's row image, slot-major
   if (mine) {
 #pragma unroll
-    for (int k = 0; k < kCompactMaxL - 1; ++k)
+    for (int k = 0; k < KMAX - 1; ++k)
       if (k < L - 1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(img + (uint32_t)(k * S + 4 * lane)), "r"(x[k]) : "memory");
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(img + (uint32_t)((L - 1) * S + 4 * lane)), "r"(0u) : "memory");
   }
@@ -573,7 +583,7 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
     for (int j = 0; j < 4; ++j) {
       uint32_t pend = (arr4 >> (8 * j)) & 0xffu;
 #pragma unroll
-      for (int k = 0; k < kCompactMaxL - 1; ++k)
+      for (int k = 0; k < KMAX - 1; ++k)
         if (k < L - 1) pend += (x[k] >> (8 * j)) & 0xffu;
       const double mxd = sp.action_max[4 * lane + j];
       double qd = (double)lv[j] - (double)ivv[j] - (double)pend;
@@ -620,12 +630,15 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
   }
   __syncwarp();                                       // image complete
   if (mine) {                                         // the ring row, every plane as whole words
+    int po = po0;
 #pragma unroll
-    for (int k = 0; k < kCompactMaxL; ++k)
+    for (int k = 0; k < KMAX; ++k)
       if (k < L) {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(img + (uint32_t)(k * S + 4 * lane)));
-        row4[s_poff[k]] = v;                          // s_poff[L-1] is the arrival plane
+        row4[po] = v;                                 // slot L-1 is the arrival plane
+        po += S4;
+        po = po == LS4 ? 0 : po;
       }
   }
   // the pipeline block of the observation row
@@ -1015,7 +1028,24 @@ int launch_split_nch(const LaunchArgs& a, const marlsc_step_io_t& io, const Spli
   const unsigned grid_rows = (unsigned)((rows + 7) / 8);
   const unsigned grid_envs = (unsigned)((a.st.num_envs + kCompactWarps - 1) / kCompactWarps);
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[0], s));
-  compact_place_kernel<MS, FS><<<grid_rows, 256, (size_t)8 * a.ds.L * a.ds.S, s>>>(a.ds, a.st, io, wk.cost_rows, t);
+  {
+    const bool policy = !io.actions && !io.action_qty;
+    const size_t img = (size_t)8 * a.ds.L * a.ds.S;
+#define MARLSC_PLACE_L(LT)                                                                                          \
+  case LT:                                                                                                          \
+    if (policy) compact_place_kernel<MS, true, LT><<<grid_rows, 256, img, s>>>(a.ds, a.st, io, wk.cost_rows, t);     \
+    else compact_place_kernel<MS, false, LT><<<grid_rows, 256, img, s>>>(a.ds, a.st, io, wk.cost_rows, t);           \
+    break;
+    switch (a.ds.L) {
+      MARLSC_PLACE_L(1) MARLSC_PLACE_L(2) MARLSC_PLACE_L(3) MARLSC_PLACE_L(4) MARLSC_PLACE_L(5) MARLSC_PLACE_L(6)
+      MARLSC_PLACE_L(7) MARLSC_PLACE_L(8) MARLSC_PLACE_L(9) MARLSC_PLACE_L(10) MARLSC_PLACE_L(11) MARLSC_PLACE_L(12)
+      MARLSC_PLACE_L(13) MARLSC_PLACE_L(14) MARLSC_PLACE_L(15) MARLSC_PLACE_L(16)
+      default:
+        if (policy) compact_place_kernel<MS, true, 0><<<grid_rows, 256, img, s>>>(a.ds, a.st, io, wk.cost_rows, t);
+        else compact_place_kernel<MS, false, 0><<<grid_rows, 256, img, s>>>(a.ds, a.st, io, wk.cost_rows, t);
+    }
+#undef MARLSC_PLACE_L
+  }
   MARLSC_CUDA(cudaGetLastError());
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[1], s));
   compact_alloc_kernel<NCH, FS><<<grid_envs, kCompactWarps * 32, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
