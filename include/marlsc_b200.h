@@ -178,17 +178,23 @@ typedef struct marlsc_step_io {
   const int32_t* order_counts;   /* [E] or NULL */
   int32_t order_stride;
   /* Sparse demand ("lines"), the native input of the COMPACT layout: the non-zero (order, SKU) cells of the step's orders
-   * (region ids already mapped through region_map), regrouped into 32 streams per environment. Stream l holds the cells
-   * of SKUs s with s % 32 == l in the order the reference allocator meets them (order index ascending, then SKU); entry =
-   * quantity (1..255) | region << 8 | (s / 32) << 14, 0 = padding. A "round" is one entry of each of the 32 streams
+   * (region ids already mapped through region_map), regrouped into 32 streams per environment. A stream carries the cells
+   * of up to four SKUs - "slots" 0..3 - and each SKU belongs to exactly one (stream, slot). Entries 0 and 1 of a stream are
+   * its SKU map: four bytes, byte k = the SKU slot k stands for, 255 = none. The other entries are lines:
+   * quantity (1..255) | region << 8 | slot << 14; 0 = padding. The lines of one SKU must appear in the order the reference
+   * allocator meets them (order index ascending, demand_allocator.py:150-208); how different SKUs of a stream interleave
+   * is free (their allocations never meet). The packers rank an environment's SKUs by line count and deal them to the
+   * streams in a snake so that the 32 streams end within a few entries of each other: the allocation kernel runs as long
+   * as the longest stream, and the block is as many rounds long. A "round" is one entry of each of the 32 streams
    * (64 bytes); rounds come in pairs: entries 2i and 2i+1 of stream l are the low and high half of 32-bit word l of pair
    * i, i.e. entry p of stream l is uint16 lines[(r0 + (p & ~1)) * 32 + 2 l + (p & 1)] for an environment whose rounds
    * start at r0. An environment owns the (even number of) rounds [line_offsets[e], line_offsets[e+1]) - or, in the
-   * padded layout (line_counts != NULL, line_stride even), rounds [e*line_stride, e*line_stride + line_counts[e]).
-   * Streams shorter than the environment's round count are padded with 0 at their end. When lines != NULL the order_* fields are ignored; a COMPACT handle given dense orders converts
-   * them with marlsc_lines_from_orders into a library-owned buffer first. WIDE handles take dense orders only.
-   * Build lines on the host with marlsc_b200.demand.pack_lines, on the device with marlsc_lines_from_orders or
-   * marlsc_demand_sample_lines. */
+   * padded layout (line_counts != NULL, line_stride even), rounds [e*line_stride, e*line_stride + line_counts[e]); an
+   * environment without demand owns no rounds (no map either). Streams shorter than the environment's round count are
+   * padded with 0 at their end. When lines != NULL the order_* fields are ignored; a COMPACT handle given dense orders
+   * converts them with marlsc_lines_from_orders into a library-owned buffer first. WIDE handles take dense orders only.
+   * Build lines on the host with marlsc_b200.demand.pack_lines, on the device with marlsc_lines_from_orders (both
+   * balanced, byte-identical) or marlsc_demand_sample_lines (SKU s on stream s % 32, slot s / 32). */
   const uint16_t* lines;         /* [n_rounds, 32] or NULL */
   const int32_t* line_offsets;   /* [E+1] */
   const int32_t* line_counts;    /* [E] or NULL */

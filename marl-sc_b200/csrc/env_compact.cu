@@ -13,6 +13,9 @@
 #include "env_compact.cuh"
 #include "env_split.cuh"
 
+#ifndef MARLSC_ALLOC_CTAS
+#define MARLSC_ALLOC_CTAS 4
+#endif
 namespace marlsc {
 namespace {
 
@@ -25,6 +28,15 @@ __device__ __forceinline__ uint32_t ld_s_u8(uint32_t a) { uint32_t v; asm volati
 __device__ __forceinline__ uint32_t ld_s_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void st_s_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_s_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_s_add_f64(uint32_t a, double v) {   // shared-memory double add (compare-and-swap loop, like atomicAdd)
+  unsigned long long old, seen;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(old) : "r"(a) : "memory");
+  do {
+    seen = old;
+    const unsigned long long want = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen) + v);
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(seen), "l"(want) : "memory");
+  } while (old != seen);
+}
 __device__ __forceinline__ void red_g_add(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_nc_u16(const uint16_t* p) { uint32_t v; asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ld_cg_u16(const uint16_t* p) { uint32_t v; asm volatile("ld.global.cg.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
@@ -35,23 +47,25 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 __device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 // A lane's line stream (marlsc_step_io.lines): two consecutive entries per 32-bit word, words of one round pair side
-// by side for the 32 lanes. Three words are kept requested ahead of the one being consumed. (A cp.async ring in shared
-// memory with eight words in flight per lane was measured too: it removes the waits on the next word but its
-// request / commit / wait instructions cost more than the waits did in this issue-bound loop: 0.73 against 0.66 ms.)
+// by side for the 32 lanes. The first word of a lane is its SKU map (byte k = the SKU its slot k stands for, 255 = none;
+// the packers deal SKUs to lanes by line count so the 32 streams of an environment end at about the same round). Three
+// words are kept requested ahead of the one being consumed. (A cp.async ring in shared memory with eight words in
+// flight per lane was measured too: it removes the waits on the next word but its request / commit / wait instructions
+// cost more than the waits did in this issue-bound loop: 0.73 against 0.66 ms.)
 struct LineStream {
-  const uint32_t* p;
-  const uint32_t* end;
-  uint32_t cur, w1, w2, w3;
-  __device__ __forceinline__ void init(const uint16_t* lines, int64_t round0, int n_rounds, int lane, uint32_t) {
-    p = reinterpret_cast<const uint32_t*>(lines) + (round0 >> 1) * 32 + lane;
-    end = p + (int64_t)(n_rounds >> 1) * 32;
-    cur = p < end ? ld_nc_u32(p) : 0u;
-    w1 = p + 32 < end ? ld_nc_u32(p + 32) : 0u;
-    w2 = p + 64 < end ? ld_nc_u32(p + 64) : 0u;
-    w3 = p + 96 < end ? ld_nc_u32(p + 96) : 0u;
-    p += 128;
+  const uint32_t* base;                               // the lane's first word; word i of the lane is base[32 i]
+  uint32_t at, n;                                     // next word to request (x 32), words of the block (x 32)
+  uint32_t map, cur, w1, w2, w3;
+  __device__ __forceinline__ void init(const uint16_t* lines, int64_t round0, int n_rounds, int lane) {
+    base = reinterpret_cast<const uint32_t*>(lines) + (round0 >> 1) * 32 + lane;
+    n = (uint32_t)(n_rounds >> 1) * 32u;
+    map = 0u < n ? ld_nc_u32(base) : 0xffffffffu;
+    cur = 32u < n ? ld_nc_u32(base + 32) : 0u;
+    w1 = 64u < n ? ld_nc_u32(base + 64) : 0u;
+    w2 = 96u < n ? ld_nc_u32(base + 96) : 0u;
+    w3 = 128u < n ? ld_nc_u32(base + 128) : 0u;
+    at = 160u;
   }
-  __device__ __forceinline__ void first() {}
   __device__ __forceinline__ uint32_t next() const { return cur & 0xffffu; }   // 0: the stream has ended
   __device__ __forceinline__ void pop() {
     cur >>= 16;
@@ -59,11 +73,36 @@ struct LineStream {
       cur = w1;
       w1 = w2;
       w2 = w3;
-      w3 = p < end ? ld_nc_u32(p) : 0u;
-      p += 32;
+      w3 = at < n ? ld_nc_u32(base + at) : 0u;
+      at += 32u;
     }
   }
 };
+
+// The SKU a lane's slot stands for (byte `slot` of its map word).
+__device__ __forceinline__ uint32_t map_sku(uint32_t map, uint32_t slot) { return __byte_perm(map, 0u, 0x4440u + slot); }
+
+// Availability masks of a lane's SKUs from the staged stock [W,S] uint16 at shared address a_inv: bit w + 16 (k & 1) of
+// (k & 2 ? avhi : avlo) says warehouse w holds the SKU of slot k. Map bytes that name no SKU (255, or anything >= S in a
+// malformed stream) are pointed at SKU S-1 with an empty mask: their lines, if any, count as lost and touch no memory
+// outside the stock image.
+__device__ __forceinline__ void owner_masks(uint32_t& map, uint32_t a_inv, int W, int S, uint32_t& avlo, uint32_t& avhi) {
+  avlo = avhi = 0u;
+  uint32_t fixed = 0u;
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    uint32_t sku = (map >> (8 * k)) & 0xffu;
+    const bool named = sku < (uint32_t)S;
+    if (!named) sku = (uint32_t)S - 1u;
+    fixed |= sku << (8 * k);
+    uint32_t m = 0u;
+    const uint32_t a = a_inv + 2u * sku;
+    for (int w = 0; w < W; ++w) m |= (ld_s_u16(a + (uint32_t)w * 2u * (uint32_t)S) != 0u ? 1u : 0u) << w;
+    if (!named) m = 0u;
+    if (k & 2) avhi |= m << (16 * (k & 1)); else avlo |= m << (16 * (k & 1));
+  }
+  map = fixed;
+}
 
 // observation element j of a warehouse's vector (after the id prefix) with the fixed mean/std normalisation of
 // multi_env.py:700-702 when enabled (reset kernel; the step kernel walks pointers instead)
@@ -75,14 +114,15 @@ __device__ __forceinline__ void put(const DevSpec& sp, bool ms, float* __restric
 // The allocation chains of one environment (demand_allocator.py:150-208) over its line streams. A trip of the loop: if
 // the lane's current line is done, take the next entry of its stream; then one shipment from the cheapest warehouse that
 // holds the SKU, or the lost-sales bookkeeping when none does. Lanes only meet in the exit vote. Stock [W,S] uint16,
-// shipped units [W,R] and lost units [R] live in shared memory, a lane's availability masks in two registers.
+// shipped units [W,R] and lost units [R] live in shared memory, a lane's availability masks in two registers. The cells
+// of the SKUs named by the lane's map belong to this lane alone for the duration of the chains.
 template <int NCH>
 __device__ __forceinline__ void allocation_chains(const DevSpec& sp, LineStream& ls, uint32_t a_perm, uint32_t a_prio, uint32_t a_home,
-                                                  uint32_t a_inv, uint32_t a_shipq, uint32_t a_lostU, uint32_t& avlo, uint32_t& avhi,
-                                                  double* s_lostP, uint32_t* hist32, int lane) {
-  const uint32_t S = sp.S, S2 = 2u * S, R4 = 4u * sp.R;
+                                                  uint32_t a_inv, uint32_t a_shipq, uint32_t a_lostU, uint32_t a_lostP, uint32_t& avlo,
+                                                  uint32_t& avhi, uint32_t* hist32) {
+  const uint32_t S = sp.S, S2 = 2u * S, R4 = 4u * sp.R, map = ls.map;
   const bool pen_uniform = sp.pen_uniform != 0;
-  uint32_t rem = 0u, r = 0u, sl = 0u, cand = 0u;      // units left of the current line, its region, SKU slot, candidate bits
+  uint32_t rem = 0u, r = 0u, sl = 0u, sku2 = 0u, cand = 0u;   // units left of the current line, its region, SKU slot, 2 x SKU, candidate bits
   while (true) {
     const uint32_t n0 = ls.next();
     if (rem == 0u && n0 != 0u) {
@@ -90,6 +130,7 @@ __device__ __forceinline__ void allocation_chains(const DevSpec& sp, LineStream&
       rem = n0 & 0xffu;
       r = (n0 >> 8) & 0x3fu;
       sl = n0 >> 14;
+      sku2 = 2u * map_sku(map, sl);
       // which warehouses hold the SKU (bit w), then the same bits in the region's priority order
       const uint32_t am = ((sl & 2u ? avhi : avlo) >> (16u * (sl & 1u))) & 0xffffu;
       const uint32_t pm = a_perm + r * (NCH * 64u);
@@ -100,7 +141,7 @@ __device__ __forceinline__ void allocation_chains(const DevSpec& sp, LineStream&
       if (hist32) {                                   // home-region demand of this step (multi_env.py:763-768)
         const uint32_t hw = ld_s_u8(a_home + r);
         if (hw != 255u) {
-          const uint32_t s = lane + 32u * sl;
+          const uint32_t s = sku2 >> 1;
           if (hw != 254u) {                           // two uint16 cells share a word: add into the cell's half, nobody waits
             const uint32_t c = hw * S + s;
             red_g_add(hist32 + (c >> 1), rem << (16u * (c & 1u)));
@@ -120,7 +161,7 @@ __device__ __forceinline__ void allocation_chains(const DevSpec& sp, LineStream&
         const uint32_t v = (uint32_t)lowest_bit(cand);
         cand &= cand - 1;
         const uint32_t w = ld_s_u8(a_prio + r * 16u + v);
-        const uint32_t cell = a_inv + w * S2 + 64u * sl;
+        const uint32_t cell = a_inv + w * S2 + sku2;
         const uint32_t a = ld_s_u16(cell);            // the cells of a SKU belong to this lane
         const uint32_t f = rem < a ? rem : a;
         st_s_u16(cell, a - f);
@@ -135,7 +176,7 @@ __device__ __forceinline__ void allocation_chains(const DevSpec& sp, LineStream&
         // no warehouse can supply the rest: lost (demand_allocator.py:205-208); units are enough when every SKU
         // carries the same penalty rate
         red_s_add(a_lostU + 4u * r, rem);
-        if (!pen_uniform) atomicAdd(&s_lostP[r], (double)rem * sp.pen_rate[lane + 32u * sl]);
+        if (!pen_uniform) red_s_add_f64(a_lostP + 8u * r, (double)rem * sp.pen_rate[sku2 >> 1]);
         rem = 0u;
       }
     }
@@ -230,7 +271,6 @@ env_step_compact_kernel(const __grid_constant__ DevSpec sp, const __grid_constan
   // patched into the row right after the copy, while its sectors are still in L2 (patching a whole phase later made L2
   // re-fetch every patched sector: +37 KB of DRAM traffic per env-step). Slot L-1 is the arrival plane itself, which
   // after this step only holds the new orders of lead L.
-  uint32_t avlo = 0u, avhi = 0u;                      // which warehouses hold SKU slot k: bits 16 (k & 1) .. of (k & 2 ? avhi : avlo)
   int rowQ = 0, rowPos = 0;                           // lane w keeps row w's ordered units / ordered cells
   double rowInb = 0.0;                                // ... or its inbound cost when the rates vary over the row
   {
@@ -249,7 +289,6 @@ env_step_compact_kernel(const __grid_constant__ DevSpec sp, const __grid_constan
     int mx[4];                                        // order maxima are whole numbers <= 255 in this layout
 #pragma unroll
     for (int j = 0; j < 4; ++j) mx[j] = mine ? (int)sp.action_max[4 * lane + j] : 0;
-    uint32_t avc01 = 0u, avc23 = 0u;                  // bit w (+16 for the odd cell): warehouse w holds the lane's cell j
     const int sub = lane & 3, src0 = lane >> 2;       // where lane l's element of store group j lives: lane 8j + l/4, byte l%4
 #pragma unroll 1
     for (int w = 0; w < W; ++w) {
@@ -286,8 +325,6 @@ env_step_compact_kernel(const __grid_constant__ DevSpec sp, const __grid_constan
             q[j] = 0;
             if (mine) q[j] = aq4 ? imin((int)((aqw >> (8 * j)) & 0xffu), mx[j]) : rescale_action<kCapsLean>(sp, af[j], (double)mx[j], 0, 0);
             ni[j] = ivv[j] + ((arr4 >> (8 * j)) & 0xffu);
-            const uint32_t bit = (ni[j] > 0u ? 1u : 0u) << (w + 16 * (j & 1));
-            if (j & 2) avc23 |= bit; else avc01 |= bit;
             if (le[j] == L) newarr |= (uint32_t)q[j] << (8 * j);
             nQ += q[j];
             nPos += q[j] > 0 ? 1 : 0;
@@ -352,26 +389,18 @@ env_step_compact_kernel(const __grid_constant__ DevSpec sp, const __grid_constan
       outc += obs_dim;
       a_sinv += 2u * S;
     }
-    // availability masks for the allocation's ownership (lane l: SKUs l + 32 k): SKU l + 32 k is cell l % 4 of lane 8 k + l / 4
-#pragma unroll
-    for (int k = 0; k < kSlots; ++k) {
-      const uint32_t lo = __shfl_sync(FULL, avc01, 8 * k + src0), hi = __shfl_sync(FULL, avc23, 8 * k + src0);
-      const uint32_t m = (((sub & 2) ? hi : lo) >> (16 * (sub & 1))) & 0xffffu;
-      if (VALID(k)) {
-        if (k & 2) avhi |= m << (16 * (k & 1)); else avlo |= m << (16 * (k & 1));
-      }
-    }
   }
   __syncwarp();                                       // stock staged, history plane cleared
 
   // ---- phase 2: greedy allocation of this step's lines (demand_allocator.py:150-208) -----------------------------
   {
     LineStream ls;
-    ls.init(io.lines, round0, n_rounds, lane, sm_addr(wbase + lay.ring));
-    ls.first();
+    ls.init(io.lines, round0, n_rounds, lane);
+    uint32_t avlo, avhi;
+    owner_masks(ls.map, sm_addr(s_inv), W, S, avlo, avhi);
     allocation_chains<NCH>(sp, ls, sm_addr(smem + lay.t_perm), sm_addr(smem + lay.t_prio), sm_addr(smem + lay.t_home),
-                           sm_addr(s_inv) + 2u * lane, sm_addr(s_shipq), sm_addr(s_lostU), avlo, avhi, s_lostP,
-                           need_hist ? reinterpret_cast<uint32_t*>(hist_now - lane) : nullptr, lane);
+                           sm_addr(s_inv), sm_addr(s_shipq), sm_addr(s_lostU), sm_addr(s_lostP), avlo, avhi,
+                           need_hist ? reinterpret_cast<uint32_t*>(hist_now - lane) : nullptr);
   }
   __syncwarp();
 
@@ -656,12 +685,12 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
 // K1b': one warp per environment - stock into shared memory, allocation chains over the environment's lines, stock back,
 // outbound + lost-sales cost per warehouse to cost_alloc. Lane l owns SKUs l + 32 k.
 template <int NCH, int FS>
-__global__ void __launch_bounds__(kCompactWarps * 32, 5)
+__global__ void __launch_bounds__(kCompactWarps * 32, MARLSC_ALLOC_CTAS)
 compact_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
-                     const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_alloc, int t) {
+                     const __grid_constant__ marlsc_step_io_t io, const __grid_constant__ CompactSmem lay,
+                     double* __restrict__ cost_alloc, int t) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int W = sp.W, S = sp.S, R = sp.R, WS = W * S;
-  const CompactSmem lay = compact_smem(W, S, R, NCH, sp.pen_uniform);
   {
     const int n_perm = (R * NCH * 32) >> 1, n_prio = (R * 16) >> 2, n_home = (R + 3) >> 2;
     for (int i = threadIdx.x; i < n_perm + n_prio + n_home; i += blockDim.x) {
@@ -680,7 +709,7 @@ compact_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
   if (lane == 0 && n_rounds > 0) prefetch_l2_bulk(io.lines + round0 * 32, (uint32_t)n_rounds * 64u);   // the whole block, one request
   unsigned char* const wbase = smem + lay.t_bytes + (size_t)wid * lay.warp_bytes;
   LineStream ls;
-  ls.init(io.lines, round0, n_rounds, lane, sm_addr(wbase + lay.ring));   // on their way while the stock is staged
+  ls.init(io.lines, round0, n_rounds, lane);          // on their way while the stock is staged
   uint16_t* const s_inv = reinterpret_cast<uint16_t*>(wbase + lay.inv);
   uint32_t* const s_shipq = reinterpret_cast<uint32_t*>(wbase + lay.shipq);
   uint32_t* const s_lostU = reinterpret_cast<uint32_t*>(wbase + lay.lostU);
@@ -691,9 +720,8 @@ compact_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
     s_lostU[i] = 0u;
     if (!pen_uniform) s_lostP[i] = 0.0;
   }
-  // stock in: five rows in flight per lane; bit w of a SKU slot's availability mask says warehouse w holds it
+  // stock in: five rows in flight per lane
   uint16_t* const g_inv = pinned(static_cast<uint16_t*>(st.inventory) + e * WS + lane);
-  uint32_t avlo = 0u, avhi = 0u;
   for (int w0 = 0; w0 < W; w0 += 5) {
     uint32_t v[5][kSlots];
 #pragma unroll
@@ -704,17 +732,20 @@ compact_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
     for (int d = 0; d < 5; ++d)
 #pragma unroll
       for (int k = 0; k < kSlots; ++k)
-        if (w0 + d < W && VALID(k)) {
-          s_inv[(w0 + d) * S + lane + 32 * k] = (uint16_t)v[d][k];
-          const uint32_t bit = (v[d][k] > 0u ? 1u : 0u) << (w0 + d + 16 * (k & 1));
-          if (k & 2) avhi |= bit; else avlo |= bit;
-        }
+        if (w0 + d < W && VALID(k)) s_inv[(w0 + d) * S + lane + 32 * k] = (uint16_t)v[d][k];
   }
+  __syncwarp();
+  uint32_t avlo, avhi;                                // which warehouses hold the SKUs this lane's streams name
+  owner_masks(ls.map, sm_addr(s_inv), W, S, avlo, avhi);
   const bool need_hist = sp.need_hist != 0;
   uint32_t* const hist32 = need_hist ? reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(st.demand_hist) + e * (int64_t)kWindow * WS + (t % kWindow) * WS) : nullptr;
-  ls.first();
-  allocation_chains<NCH>(sp, ls, sm_addr(smem + lay.t_perm), sm_addr(smem + lay.t_prio), sm_addr(smem + lay.t_home),
-                         sm_addr(s_inv) + 2u * lane, sm_addr(s_shipq), sm_addr(s_lostU), avlo, avhi, s_lostP, hist32, lane);
+  {
+    // every shared address the chains use is one of two bases plus a launch constant (the layout is a kernel parameter)
+    const uint32_t a_cta = sm_addr(smem), a_warp = a_cta + (uint32_t)lay.t_bytes + (uint32_t)wid * (uint32_t)lay.warp_bytes;
+    allocation_chains<NCH>(sp, ls, a_cta + (uint32_t)lay.t_perm, a_cta + (uint32_t)lay.t_prio, a_cta + (uint32_t)lay.t_home,
+                           a_warp + (uint32_t)lay.inv, a_warp + (uint32_t)lay.shipq, a_warp + (uint32_t)lay.lostU,
+                           a_warp + (uint32_t)lay.lostP, avlo, avhi, hist32);
+  }
   __syncwarp();
   for (int w0 = 0; w0 < W; ++w0)                       // stock out (multi_env.py:307; never negative)
 #pragma unroll
@@ -941,19 +972,88 @@ base_stock_compact_kernel(const __grid_constant__ DevSpec sp, const __grid_const
   actions[idx] = (float)(2.0 * q / mx - 1.0);
 }
 
-// Dense order rows -> lines (padded layout): one warp per environment, lane l appends the non-zero cells of its SKUs
-// order by order, so every stream keeps the order sequence the allocation needs.
+// Dense order rows -> lines (padded layout): one warp per environment. Pass 1 counts the non-zero cells of every SKU;
+// the SKUs are then ranked by that count (descending, ties by SKU id) and dealt to the 32 lanes in a snake (rank 0..31
+// to lanes 0..31 as slot 0, ranks 32..63 to lanes 31..0 as slot 1, ...), so the streams of an environment end within a
+// few entries of each other - the allocation kernel runs as long as the longest stream. Pass 2 writes the entries: a
+// stream holds all lines of its slot-0 SKU, then of its slot-1 SKU, ..., each in order sequence (the chains of different
+// SKUs never meet, demand_allocator.py:150-208, so only the sequence inside a SKU matters). Entry 0/1 of every lane is
+// its SKU map. demand.pack_lines builds the same bytes on the host.
 __global__ void __launch_bounds__(128)
 lines_from_orders_kernel(const __grid_constant__ DevSpec sp, long long E, const __grid_constant__ marlsc_step_io_t io,
                          int stride, uint16_t* __restrict__ lines, int32_t* __restrict__ counts, int32_t* __restrict__ overflow) {
-  const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  __shared__ uint16_t s_cnt[4][128];     // lines of SKU s
+  __shared__ uint16_t s_base[4][128];    // first entry of SKU s inside its stream
+  __shared__ uint8_t s_dst[4][128];      // stream of SKU s: lane | slot << 5
+  __shared__ uint8_t s_map[4][128];      // SKU of (lane, slot): index 4 lane + slot
+  __shared__ uint16_t s_dcnt[4][128];    // its line count
+  const int wid = threadIdx.x >> 5;
+  const long long e = (long long)blockIdx.x * 4 + wid;
   if (e >= E) return;
   const int lane = threadIdx.x & 31, S = sp.S;
   const long long o_begin = io.order_counts ? e * (long long)io.order_stride : (long long)io.order_offsets[e];
   const int n_orders = io.order_counts ? io.order_counts[e] : io.order_offsets[e + 1] - (int)o_begin;
   const uint8_t* qty = static_cast<const uint8_t*>(io.order_qty) + o_begin * S + lane;
-  uint16_t* out = lines + e * (long long)stride * 32 + 2 * lane;     // entry p of this lane: out[(p >> 1) * 64 + (p & 1)]
-  int cnt = 0;
+  uint16_t* const env_lines = lines + e * (long long)stride * 32;    // entry p of lane l: env_lines[(p >> 1) * 64 + 2 l + (p & 1)]
+  // pass 1: lines per SKU
+  int c[kSlots];
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) c[k] = 0;
+  for (int j0 = 0; j0 < n_orders; j0 += 4) {
+    uint32_t v[4][kSlots];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) v[jj][k] = (j0 + jj < n_orders && lane + 32 * k < S) ? (uint32_t)qty[(long long)(j0 + jj) * S + 32 * k] : 0u;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) c[k] += v[jj][k] != 0u ? 1 : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    s_cnt[wid][lane + 32 * k] = (uint16_t)c[k];
+    s_map[wid][lane + 32 * k] = 255;
+    s_dcnt[wid][lane + 32 * k] = 0;
+  }
+  __syncwarp();
+  // rank -> (lane, slot)
+  int rank[kSlots];
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) rank[k] = 0;
+  for (int s2 = 0; s2 < S; ++s2) {
+    const int c2 = s_cnt[wid][s2];
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) rank[k] += (c2 > c[k] || (c2 == c[k] && s2 < lane + 32 * k)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k)
+    if (lane + 32 * k < S) {
+      const int row = rank[k] >> 5, col = rank[k] & 31, dl = (row & 1) ? 31 - col : col;
+      s_dst[wid][lane + 32 * k] = (uint8_t)(dl | (row << 5));
+      s_map[wid][4 * dl + row] = (uint8_t)(lane + 32 * k);
+      s_dcnt[wid][4 * dl + row] = (uint16_t)c[k];
+    }
+  __syncwarp();
+  uint32_t map = 0u;
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    const uint32_t sk = s_map[wid][4 * lane + k];
+    map |= sk << (8 * k);
+    if (sk != 255u) s_base[wid][sk] = (uint16_t)total;
+    total += s_dcnt[wid][4 * lane + k];
+  }
+  __syncwarp();
+  // pass 2: entries
+  int at[kSlots], dl[kSlots], ds[kSlots];
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    const bool named = lane + 32 * k < S;
+    at[k] = named ? 2 + (int)s_base[wid][lane + 32 * k] : 0;        // entries 0, 1 hold the map
+    dl[k] = named ? s_dst[wid][lane + 32 * k] & 31 : 0;
+    ds[k] = named ? s_dst[wid][lane + 32 * k] >> 5 : 0;
+  }
   bool over = false;
   for (int j0 = 0; j0 < n_orders; j0 += 4) {          // four orders' cells in flight per lane
     uint32_t v[4][kSlots];
@@ -971,15 +1071,22 @@ lines_from_orders_kernel(const __grid_constant__ DevSpec sp, long long E, const 
 #pragma unroll
       for (int k = 0; k < kSlots; ++k)
         if (v[jj][k] != 0u) {
-          if (cnt < stride) out[(long long)(cnt >> 1) * 64 + (cnt & 1)] = line_entry((int)v[jj][k], r, k);
+          if (at[k] < stride) env_lines[(long long)(at[k] >> 1) * 64 + 2 * dl[k] + (at[k] & 1)] = line_entry((int)v[jj][k], r, ds[k]);
           else over = true;
-          ++cnt;
+          ++at[k];
         }
     }
   }
-  cnt = imin(cnt, stride);
-  const int rounds = (__reduce_max_sync(FULL, cnt) + 1) & ~1;         // whole round pairs
-  for (int c = cnt; c < rounds; ++c) out[(long long)(c >> 1) * 64 + (c & 1)] = 0;     // pad this stream to the environment's round count
+  const int longest = __reduce_max_sync(FULL, total);
+  int rounds = 0;
+  if (longest > 0) {                                  // an environment without demand has no rounds at all
+    const int mine = imin(total + 2, stride);
+    rounds = (imin(longest + 2, stride) + 1) & ~1;    // whole round pairs
+    uint16_t* const out = env_lines + 2 * lane;
+    out[0] = (uint16_t)(map & 0xffffu);
+    out[1] = (uint16_t)(map >> 16);
+    for (int p = mine; p < rounds; ++p) out[(long long)(p >> 1) * 64 + (p & 1)] = 0;     // pad this stream to the environment's round count
+  }
   if (lane == 0) counts[e] = rounds;
   if (over) atomicExch(overflow, 1);
 }
@@ -1048,7 +1155,7 @@ int launch_split_nch(const LaunchArgs& a, const marlsc_step_io_t& io, const Spli
   }
   MARLSC_CUDA(cudaGetLastError());
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[1], s));
-  compact_alloc_kernel<NCH, FS><<<grid_envs, kCompactWarps * 32, smem, s>>>(a.ds, a.st, io, wk.cost_alloc, t);
+  compact_alloc_kernel<NCH, FS><<<grid_envs, kCompactWarps * 32, smem, s>>>(a.ds, a.st, io, lay, wk.cost_alloc, t);
   MARLSC_CUDA(cudaGetLastError());
   if (wk.marks) MARLSC_CUDA(cudaEventRecord(wk.marks[2], s));
   const int agent_scope = a.ds.scope == MARLSC_SCOPE_AGENT;

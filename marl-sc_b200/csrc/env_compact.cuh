@@ -55,8 +55,16 @@ __host__ __device__ inline CompactSmem compact_smem(int W, int S, int R, int nch
   return l;
 }
 
-// entry of a line stream: quantity (1..255) | region << 8 | SKU slot << 14; 0 pads a stream to the environment's round count
+// entry of a line stream: quantity (1..255) | region << 8 | SKU slot << 14; 0 pads a stream to the environment's round count.
+// Entries 0 and 1 of a lane (its first 32-bit word) are the lane's SKU map: byte k = the SKU slot k stands for, 255 = none.
 __host__ __device__ inline uint16_t line_entry(int qty, int region, int slot) { return (uint16_t)(qty | (region << 8) | (slot << 14)); }
+
+// the map word of lane l when SKUs are dealt round-robin (SKU s on lane s % 32, slot s / 32)
+__host__ __device__ inline uint32_t identity_map_word(int lane, int S) {
+  uint32_t m = 0u;
+  for (int k = 0; k < 4; ++k) m |= (uint32_t)(lane + 32 * k < S ? lane + 32 * k : 255) << (8 * k);
+  return m;
+}
 
 int launch_step_compact(const LaunchArgs& a, const marlsc_step_io_t& io, int t, cudaStream_t s);
 struct SplitWork;

@@ -159,7 +159,9 @@ sample_demand_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, 
 
 // K4 writing lines (the compact layout's demand format, include/marlsc_b200.h): the same draws as sample_demand_kernel
 // (same Philox counters), but every lane appends the non-zero cells of its SKUs to its own stream instead of filling
-// dense rows - the allocation kernel then walks the streams without ever scanning the 80 % zero cells.
+// dense rows - the allocation kernel then walks the streams without ever scanning the 80 % zero cells. SKUs stay dealt
+// round-robin (lane s % 32, slot s / 32: the lane's map word says so); ranking them by line count as the packers of
+// recorded demand do would need the counts before the first entry is written, i.e. every draw twice.
 __global__ void __launch_bounds__(128)
 sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t seed, long long step, int stride,
                            const int32_t* __restrict__ region_map, uint16_t* __restrict__ lines, int32_t* __restrict__ counts,
@@ -168,7 +170,7 @@ sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t 
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
   uint16_t* out = lines + e * (long long)stride * 32 + 2 * lane;     // entry p of this lane: out[(p >> 1) * 64 + (p & 1)]
-  int row = 0, cnt = 0;
+  int row = 0, cnt = 2;                               // entries 0, 1: the lane's SKU map
   bool over = false;
   for (int r0 = 0; r0 < R; r0 += 32) {
     const int r = r0 + lane;
@@ -208,8 +210,17 @@ sample_demand_lines_kernel(DemandParams dp, int R, int S, long long E, uint64_t 
     }
   }
   cnt = cnt < stride ? cnt : stride;
-  const int rounds = (__reduce_max_sync(0xffffffffu, cnt) + 1) & ~1;  // whole round pairs
-  for (int c = cnt; c < rounds; ++c) out[(long long)(c >> 1) * 64 + (c & 1)] = 0;     // pad this stream to the environment's round count
+  const int longest = __reduce_max_sync(0xffffffffu, cnt);
+  int rounds = 0;
+  if (longest > 2) {                                  // an environment without demand has no rounds at all
+    rounds = (longest + 1) & ~1;                      // whole round pairs
+    uint32_t map = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) map |= (uint32_t)(lane + 32 * k < S ? lane + 32 * k : 255) << (8 * k);
+    out[0] = (uint16_t)(map & 0xffffu);
+    out[1] = (uint16_t)(map >> 16);
+    for (int c = cnt; c < rounds; ++c) out[(long long)(c >> 1) * 64 + (c & 1)] = 0;   // pad this stream to the environment's round count
+  }
   if (lane == 0) counts[e] = rounds;
   if (over) atomicExch(overflow, 1);
 }

@@ -1037,6 +1037,33 @@ def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi,
     env.close()
 
 
+def test_lines_from_orders_matches_host_packer():
+    """marlsc_lines_from_orders (device) and demand.pack_lines (host) build byte-identical blocks: same ranking of SKUs by
+    line count, same snake dealing, same sequence inside a stream - for ragged SKU counts, an empty environment and
+    with a region map."""
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.demand import pack_lines, pack_orders
+    from marlsc_b200.envs import BatchedInventoryEnv, DeviceOrders
+    for S, R, W in ((100, 50, 10), (68, 9, 7), (128, 64, 16)):
+        E = 13
+        rng = np.random.default_rng(S)
+        cfg = environment_config_from_dict(dict(_lean_env_dict(rng, W, S, R, "shipment", True, 6), allow_region_mismatch=True))
+        env = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, layout="compact")
+        per_env = []
+        for e in range(E):
+            n = 0 if e == 5 else int(rng.integers(1, 90))
+            per_env.append(sorted(((int(rng.integers(0, R)), np.where(rng.random(S) < 0.25, rng.integers(1, 200, S), 0).astype(float))
+                                   for _ in range(n)), key=lambda x: x[0]))
+        batch = pack_orders(per_env, S)
+        host = pack_lines(batch)
+        dev = env.lines_from_orders(DeviceOrders.from_host(batch, "cuda:0"))
+        assert np.array_equal(dev.offsets.cpu().numpy(), host.offsets)
+        n = host.n_rounds
+        assert np.array_equal(dev.lines.cpu().numpy().view(np.uint16)[:n], host.lines[:n])
+        assert dev.n_lines == host.n_lines
+        env.close()
+
+
 def test_compact_device_demand_lines_and_in_step_base_stock():
     """All-device pipeline on the compact layout: (i) the sampler writing lines (marlsc_demand_sample_lines) draws the
     orders the dense sampler draws for the same (seed, step) - an environment fed the dense rows ends in the same state;

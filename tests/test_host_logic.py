@@ -480,3 +480,43 @@ def test_integration_md_stub_structs_match_the_binding():
         for f, _ in mine._fields_:
             assert getattr(mine, f).offset == getattr(theirs, f).offset, f
     assert "abi_version=2" in md and _capi.ABI_VERSION == 2
+
+
+def test_pack_lines_roundtrip_and_balance():
+    """Sparse demand lines (include/marlsc_b200.h, marlsc_step_io.lines): every (order, SKU) cell appears once, the lines
+    of a SKU keep the order sequence the reference allocator meets them in (demand_allocator.py:150-208), every SKU has
+    one (stream, slot), and the balanced dealing shortens an environment's block."""
+    from marlsc_b200.demand import pack_lines, pack_orders, unpack_lines
+    rng = np.random.default_rng(3)
+    S, E = 100, 9
+    per_env = []
+    for e in range(E):
+        n = 0 if e == 4 else int(rng.integers(1, 70))
+        orders = sorted(((int(rng.integers(0, 50)), ((rng.random(S) < 0.2) * rng.integers(1, 9, S)).astype(np.int64)) for _ in range(n)),
+                        key=lambda x: x[0])
+        per_env.append(orders)
+    batch = pack_orders(per_env, S)
+    region_map = [(r * 7) % 50 for r in range(50)]
+    rounds = {}
+    for balance in (True, False):
+        lb = pack_lines(batch, region_map=region_map, balance=balance)
+        rounds[balance] = np.diff(lb.offsets)
+        assert np.all(rounds[balance] % 2 == 0) and lb.lines.shape[1] == 32 and lb.lines.dtype == np.uint16
+        total = 0
+        for e in range(E):
+            exp = {}
+            for r, q in per_env[e]:
+                for sku in np.nonzero(q)[0]:
+                    exp.setdefault(int(sku), []).append((region_map[r], int(q[sku])))
+            assert unpack_lines(lb, e) == exp, (e, balance)
+            total += sum(len(v) for v in exp.values())
+            r0, r1 = lb.offsets[e], lb.offsets[e + 1]
+            if r1 > r0:                                   # SKU maps: every SKU named exactly once
+                hdr = lb.lines[r0:r0 + 2].reshape(1, 32, 2)[0]       # entries 0, 1 of every lane
+                ids = np.concatenate([hdr[:, 0] & 0xff, hdr[:, 0] >> 8, hdr[:, 1] & 0xff, hdr[:, 1] >> 8])
+                assert sorted(ids[ids != 255].tolist()) == list(range(S))
+        assert lb.n_lines == total
+        assert rounds[balance][4] == 0                    # an environment without demand owns no rounds
+    assert rounds[True].sum() < rounds[False].sum()
+    longest = [max(sum(len(v) for k, v in unpack_lines(pack_lines(batch, balance=False), e).items() if k % 32 == l) for l in range(32)) for e in range(E)]
+    assert np.array_equal(rounds[False], np.where(np.array(longest) > 0, (np.array(longest) + 3) & ~1, 0))
