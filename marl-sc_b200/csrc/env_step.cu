@@ -48,6 +48,7 @@ struct marlsc_env {
   int device = 0;
   int team = 1;        // lanes per environment in use
   int team_auto = 1;
+  int tiny_fallback = 0;   // team_auto is 8 for a tiny SKU count: launches outside the split step run thread-per-environment
   int spl = 1;         // SKUs per lane of the instantiation in use
   void* d_blob = nullptr;  // one allocation holding every device table
   int max_smem_optin = 0;
@@ -154,6 +155,8 @@ int ensure_work(marlsc_env* env, int64_t num_envs) {
 
 // The split step covers what the lean instantiation covers, for teams of at least 8 lanes (and the SKUs-per-lane
 // values the automatic team choice produces).
+constexpr int64_t kTinySplitMaxEnvs = 131072;
+
 bool split_ok(const marlsc_env* env) {
   if (env->force_fused) return false;
   const int g = env->team, k = env->spl;   // instantiated pairs, see MARLSC_DEFINE_SPLIT in env_inst_g*.cu
@@ -234,6 +237,14 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   }
   env->device = device;
   env->team_auto = auto_team_size(env->ds.S);
+  // Tiny SKU counts: a thread per environment is one long chain of dependent, uncoalesced accesses (165 us per step at
+  // 4,096 environments of the 3 x 2 network); the split step with 8-lane teams runs the same step in 48 us there
+  // (37 us inside a CUDA graph) and ties at 262,144 environments. Launches the split step does not cover (diagnostic
+  // outputs, generic capabilities, the fused-kernel switch) still go thread-per-environment, see marlsc_env_step.
+  if (env->team_auto == 1 && (required_caps(env->ds, env->tb, nullptr) & ~kCapsLean) == 0 && pick_spl(8, env->ds.S) == 1) {
+    env->team_auto = 8;
+    env->tiny_fallback = 1;
+  }
   if (set_team(env, env->team_auto) != MARLSC_OK) {
     const std::string msg = g_last_error;
     delete env;
@@ -473,7 +484,11 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   const bool lean = !env->force_generic && (required_caps(env->ds, env->tb, io) & ~kCapsLean) == 0;
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
   // the row kernels of the split step index (environment, warehouse) rows with 32 bits
-  if (lean && split_ok(env) && state->num_envs * (int64_t)env->ds.W < (int64_t)0xffffffffLL) {
+  // automatic 8-lane teams of a tiny SKU count: past ~130k environments the machine is full either way and the
+  // thread-per-environment kernel's single launch wins (IPPO shape, 262,144 environments: 0.42 against 0.65 ms)
+  const bool tiny = env->tiny_fallback && env->team == env->team_auto;
+  const bool tiny_split = !tiny || state->num_envs <= kTinySplitMaxEnvs;
+  if (lean && tiny_split && split_ok(env) && state->num_envs * (int64_t)env->ds.W < (int64_t)0xffffffffLL) {
     rc = ensure_work(env, state->num_envs);
     if (rc) return rc;
     const SplitWork wk{env->d_work, env->d_work + (size_t)env->work_envs * env->ds.W, env->timing ? env->marks : nullptr};
@@ -488,8 +503,8 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   }
   // two-warp teams exist for the lean instantiation only; generic launches fall back to 32 lanes
   const bool narrow = env->team > 32 && !lean;
-  const int team = narrow ? 32 : env->team;
-  const int spl = narrow ? pick_spl(32, env->ds.S) : env->spl;
+  const int team = narrow ? 32 : (tiny ? 1 : env->team);
+  const int spl = narrow ? pick_spl(32, env->ds.S) : (tiny ? pick_spl(1, env->ds.S) : env->spl);
   if (env->timing) {
     MARLSC_CUDA(cudaEventRecord(env->marks[0], s));
     rc = [&]() -> int { MARLSC_DISPATCH_G(team, launch_step_g, spl, la, *io, t, s) }();

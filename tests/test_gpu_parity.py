@@ -86,6 +86,33 @@ def test_cuda_split_step_small_shapes(name, team):
     _run(Golden(name), team_size=team, diagnostics=False)
 
 
+def test_tiny_network_takes_the_split_step_automatically():
+    """A network with a handful of SKUs (BASELINE configs[1]: 3 warehouses x 2 SKUs) runs the split step with 8-lane teams
+    by default (a thread per environment is 3x slower below ~100k environments); launches the split step does not cover
+    (here: the fused-kernel switch) fall back to a thread per environment. Both paths against the golden trajectory, and
+    against each other on a ragged batch."""
+    from golden.scenarios import small_default
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    g = Golden("small_default")
+    _run(g, diagnostics=False)                       # automatic choice
+    _run(g, diagnostics=False, fused=True)           # thread per environment
+    cfg = environment_config_from_dict(small_default())
+    E = 301
+    a = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, device_demand=True, demand_seed=3)
+    b = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, device_demand=True, demand_seed=3, team_size=1)
+    assert a.team_size == 8 and b.team_size == 1 and a.layout == b.layout == "wide"
+    assert torch.equal(a.reset(), b.reset())
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    for t in range(40):
+        act = torch.rand((E, a.n_warehouses, a.n_skus), device="cuda:0", generator=gen) * 2 - 1
+        oa, ra, _ = a.step(act)
+        ob, rb, _ = b.step(act)
+        assert torch.equal(a.inventory, b.inventory) and torch.equal(a.ring_qty, b.ring_qty), t
+        np.testing.assert_allclose(ra.cpu().numpy(), rb.cpu().numpy(), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(oa.cpu().numpy(), ob.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("team", [0, 64])
 @pytest.mark.parametrize("fixed_cost", [0.0, 2.0])
