@@ -123,6 +123,7 @@ struct DevSpec {
   unsigned long long home_bits; // bit r: region r (< 64) is some warehouse's home region
   int compact_ok;              // the configuration fits the compact state layout and its fused kernel
   int compact_prefetch;        // the per-environment state blocks are 16-byte granular: bulk L2 prefetches are legal
+  int feature_bulk;            // K1c' may fetch an environment's stock / history blocks with cp.async.bulk (W S % 8 == 0)
   int row_rates_uniform;       // holding / weight / inbound rates do not vary over the SKUs of a warehouse
   const float* obs_mean;
   const float* obs_std;        // holds 1/std (precomputed on the host in float32)

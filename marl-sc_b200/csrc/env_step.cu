@@ -303,6 +303,7 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   // cp.async.bulk.prefetch.L2 wants 16-byte aligned addresses and sizes: true for every environment's block when the
   // smallest one (W*S bytes of uint8 quantities) is a multiple of 16 (MARLSC_NO_PREFETCH=1 switches them off for A/B runs)
   env->ds.compact_prefetch = ((env->ds.W * env->ds.S) % 16 == 0 && !std::getenv("MARLSC_NO_PREFETCH")) ? 1 : 0;
+  env->ds.feature_bulk = ((env->ds.W * env->ds.S) % 8 == 0 && std::getenv("MARLSC_FEATURE_BULK")) ? 1 : 0;   // opt-in: measured slower
   env->layout = env->ds.compact_ok ? MARLSC_LAYOUT_COMPACT : MARLSC_LAYOUT_WIDE;
   *out = env;
   return MARLSC_OK;

@@ -1064,6 +1064,31 @@ def test_compact_step_vs_oracle(W, S, R, lost, pen_uniform, max_orders, lead_hi,
     env.close()
 
 
+def test_feature_kernel_bulk_copy_variant_is_bit_identical(monkeypatch):
+    """K1c' has an opt-in variant that fetches an environment's stock and history blocks with cp.async.bulk + mbarriers
+    (MARLSC_FEATURE_BULK=1, csrc/env_compact.cu compact_feature_bulk_kernel; measured slower, kept for audit): same
+    observations, rewards and state as the default register version, including a batch that does not fill the grid."""
+    from marlsc_b200.config import environment_config_from_dict
+    from marlsc_b200.envs import BatchedInventoryEnv
+    rng = np.random.default_rng(11)
+    cfg = environment_config_from_dict(dict(_lean_env_dict(rng, 10, 100, 50, "shipment", True, 6, demand_home=True), allow_region_mismatch=True))
+    E = 777
+    a = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, device_demand=True, demand_seed=9, layout="compact")
+    monkeypatch.setenv("MARLSC_FEATURE_BULK", "1")
+    b = BatchedInventoryEnv(cfg, E, device="cuda:0", host_samplers=False, device_demand=True, demand_seed=9, layout="compact")
+    monkeypatch.delenv("MARLSC_FEATURE_BULK")
+    assert torch.equal(a.reset(), b.reset())
+    gen = torch.Generator(device="cuda:0").manual_seed(1)
+    for t in range(12):
+        act = torch.rand((E, 10, 100), device="cuda:0", generator=gen) * 2 - 1
+        oa, ra, _ = a.step(act)
+        ob, rb, _ = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb), t
+        assert torch.equal(a.inventory, b.inventory) and torch.equal(a.demand_hist, b.demand_hist)
+    a.close()
+    b.close()
+
+
 def test_lines_from_orders_matches_host_packer():
     """marlsc_lines_from_orders (device) and demand.pack_lines (host) build byte-identical blocks: same ranking of SKUs by
     line count, same snake dealing, same sequence inside a stream - for ragged SKU counts, an empty environment and
