@@ -811,8 +811,11 @@ compact_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
 // the row's inbound cost; with agent-scope rewards also the reward itself (no K1d launch). Like K1a', lane q loads the
 // four consecutive cells 4q .. 4q+3 of each plane with one vector load (six loads per lane instead of 24 two-byte ones),
 // the block values go through a small shared-memory image and leave as 128-byte coalesced float stores.
+#ifndef MARLSC_FEAT_CTAS
+#define MARLSC_FEAT_CTAS 8
+#endif
 template <bool MS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MARLSC_FEAT_CTAS)
 compact_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
                        const __grid_constant__ marlsc_step_io_t io, double* __restrict__ cost_rows,
                        const double* __restrict__ cost_alloc, int t, int write_rewards) {
@@ -833,6 +836,11 @@ compact_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant
   uint2 iv = make_uint2(0u, 0u), hn = make_uint2(0u, 0u), ho[kWindow - 1];
 #pragma unroll
   for (int back = 1; back < kWindow; ++back) ho[back - 1] = make_uint2(0u, 0u);
+  double cost_in = 0.0, cost_al = 0.0;                // the row's cost so far: requested with everything else, used last
+  if (lane == 0) {
+    cost_in = cost_rows[row];
+    if (write_rewards) cost_al = cost_alloc[row];
+  }
   if (mine) {                                         // every load of the row first
     iv = *inv4;
     if (need_hist) {
@@ -884,9 +892,9 @@ compact_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant
   }
   float* const obs_w = io.obs + (size_t)row * sp.obs_dim;
   if (lane == 0) {
-    cost += cost_rows[row];                           // + the inbound cost K1a' left there
+    cost += cost_in;                                  // + the inbound cost K1a' left there
     if (write_rewards) {                              // agent scope (multi_env.py:316-327): no reward kernel needed
-      io.rewards[row] = (float)(-((cost + cost_alloc[row]) * sp.scale));
+      io.rewards[row] = (float)(-((cost + cost_al) * sp.scale));
       if (io.truncated && w == 0) io.truncated[e] = (uint8_t)(t + 1 >= sp.episode_length);
     } else {
       cost_rows[row] = cost;
