@@ -915,8 +915,9 @@ compact_feature_kernel(const __grid_constant__ DevSpec sp, const __grid_constant
     const float* src = img + b * S + lane;
     const float* const mean_l = MS ? sp.obs_mean + offs[b] + lane : nullptr;
     const float* const istd_l = MS ? sp.obs_std + offs[b] + lane : nullptr;
-    for (int i = 0; i < S; i += 32)
-      if (i + lane < S) out[offs[b] + i] = nrm<MS>(src[i], mean_l, istd_l, i);
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k)                  // S <= 32 kSlots: four predicated stores, no loop scaffolding
+      if (32 * k + lane < S) out[offs[b] + 32 * k] = nrm<MS>(src[32 * k], mean_l, istd_l, 32 * k);
   }
 }
 
