@@ -164,9 +164,11 @@ struct Team {
   // G  > 32: G/32 whole warps; team-wide steps go through a named barrier (id 1 + team index in the CTA)
   //          and a few doubles of static shared memory (xs) for the cross-warp sums.
   unsigned gmask;
+  unsigned live;   // lanes of this warp whose team has an environment (teams narrower than a warp, see converge())
   int bar;
   double* xs;
-  __device__ __forceinline__ void init(double* xchg = nullptr) {
+  __device__ __forceinline__ void init(double* xchg = nullptr, unsigned live_lanes = 0xffffffffu) {
+    live = live_lanes;
     gl = threadIdx.x % G;
     const int wl = threadIdx.x & 31;
     gmask = (G >= 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (wl & ~(G - 1)));
@@ -176,6 +178,14 @@ struct Team {
   __device__ __forceinline__ void sync() const {
     if (G > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(G) : "memory");
     else if (G > 1) __syncwarp(gmask);
+  }
+  // Teams narrower than a warp: the teams of a warp run data-dependent loops of different lengths, and nothing brings
+  // them back together afterwards - measured on the thread-per-environment kernel, 2.1 of 32 lanes were active per
+  // instruction in the straight-line code after the allocation. converge() is a team sync that also reconverges the warp;
+  // it may only stand where every live lane of the warp passes (the top level of the step).
+  __device__ __forceinline__ void converge() const {
+    if (G >= 32) sync();
+    else __syncwarp(live);
   }
   __device__ __forceinline__ bool any(bool p) const {
     if (G == 1) return p;
@@ -221,8 +231,9 @@ struct Team {
   __device__ __forceinline__ float sum(float v) const { return sum_t(v); }
   __device__ __forceinline__ double sum(double v) const { return sum_t(v); }
 #else
-  void init(double* = nullptr) { gl = 0; }
+  void init(double* = nullptr, unsigned = 0) { gl = 0; }
   void sync() const {}
+  void converge() const {}
   bool any(bool p) const { return p; }
   bool warp_any(bool p) const { return p; }
   unsigned ballot(bool p) const { return p ? 1u : 0u; }
@@ -1153,11 +1164,11 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
     s_lostW[i] = 0.0;
     s_lostP[i] = 0.0;
   }
-  tm.sync();
+  tm.converge();
 
   // ---- phase 2: sequential greedy allocation of this step's orders (demand_allocator.py:150-208)
   allocate_orders<G, SPL, CAPS>(sp, tb, tm, sc, p, io, e, dh_acc, dh_mode);
-  tm.sync();
+  tm.converge();
 
   // ---- phase 3: per warehouse - state write-back, feature buffers, costs, observation row ----------
   const int hist_n = imin(t + 1, kWindow);
@@ -1250,7 +1261,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
     write_obs_row<G, SPL, CAPS>(sp, tb, tm, p, io.obs + (e * W + w) * (int64_t)sp.obs_dim, w, t, hist_n, vI, vdh, vsh, vst,
                           vrm, vfc);
   }
-  tm.sync();
+  tm.converge();
 
   // ---- phase 4: rewards (multi_env.py:316-327) ------------------------------------------------------
   for (int w = tm.gl; w < W; w += G) {

@@ -70,9 +70,10 @@ env_step_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marl
   __syncthreads();
   const int team = threadIdx.x / G;
   const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
+  const unsigned live = __ballot_sync(0xffffffffu, e < st.num_envs);
   if (e >= st.num_envs) return;   // whole teams leave together; everything below is team-local
   Team<G> tm;
-  tm.init(xchg);
+  tm.init(xchg, live);
   Scratch sc;
   unsigned char* base = smem + sp.t_bytes;
   sc.d = reinterpret_cast<double*>(base) + (size_t)team * sp.d_words;

@@ -146,9 +146,10 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
   __syncthreads();
   const int team = threadIdx.x / G;
   const int64_t e = (int64_t)blockIdx.x * TEAMS + team;
+  const unsigned live = __ballot_sync(0xffffffffu, e < st.num_envs);
   if (e >= st.num_envs) return;
   Team<G> tm;
-  tm.init(xchg);
+  tm.init(xchg, live);
   Scratch sc;
   unsigned char* sbase = smem + sp.t_bytes;
   sc.d = reinterpret_cast<double*>(sbase) + (size_t)team * sp.d_words;
@@ -185,7 +186,7 @@ env_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ mar
   const int dh_mode = sp.dh_mode == 1 ? 1 : 0;
   int32_t* const dh_acc = dh_mode ? pinned(p.hist + (t % kWindow) * WS) : nullptr;
   allocate_orders<G, SPL, CAPS>(sp, tb, tm, sc, p, io, e, dh_acc, dh_mode);
-  tm.sync();
+  tm.converge();                                                // the teams of a warp meet again here
 
   for (int i = tm.gl; i < WS; i += G) p.inv[i] = s_inv[i];      // multi_env.py:307 (never negative)
   tm.sync();
