@@ -55,8 +55,11 @@ constexpr bool has_lean(int G, int SPL) {
 // Multi-warp teams exist for the lean instantiation only (the generic allocation votes across the team per
 // warehouse visit, which does not pay across warps); the host falls back to 32 lanes for generic launches.
 constexpr bool has_generic(int G) { return G <= 32; }
+#ifndef MARLSC_G1_MIN_BLOCKS
+#define MARLSC_G1_MIN_BLOCKS 6
+#endif
 constexpr int min_blocks(int G, uint32_t CAPS) {
-  return CAPS != kCapsLean ? 1 : (G == 32 ? 6 : (G > 32 ? 4 : 1));   // two-warp teams: 64 registers beat a fifth CTA
+  return CAPS != kCapsLean ? 1 : (G == 32 ? 6 : (G > 32 ? 4 : (G == 1 ? MARLSC_G1_MIN_BLOCKS : 1)));   // two-warp teams: 64 registers beat a fifth CTA
 }
 
 template <int G, int SPL, uint32_t CAPS>
