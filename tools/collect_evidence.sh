@@ -19,5 +19,6 @@ STEPS=40 PLAIN=1 ncu --set full --import-source on --clock-control none -k 'rege
     -f -o $OUT/${TAG}_k1_compact python tools/step_timings.py > $OUT/${TAG}_ncu_full.log 2>&1
 STEPS=40 python tools/step_timings.py > $OUT/${TAG}_step_timings.log 2>&1
 python tools/pipeline_timings.py > $OUT/${TAG}_pipeline_timings.log 2>&1
+ENVS="4096 16384 32768 262144" TEAMS="1 8" bash tools/small_team_sweep.sh > $OUT/${TAG}_small_team_sweep.log 2>&1
 cat $OUT/${TAG}_pytest_gpu.log
 head -c 600 $OUT/bench_default.json

@@ -64,7 +64,7 @@ def main(rep, tag="r2"):
         src = os.path.join(G, name + ".json")
         if os.path.exists(src):
             shutil.copy(src, os.path.join(P, f"{tag}_{name}.json"))
-    for name in (f"{tag}_step_timings.log", f"{tag}_pipeline_timings.log", f"{tag}_pytest_gpu.log"):
+    for name in (f"{tag}_step_timings.log", f"{tag}_pipeline_timings.log", f"{tag}_pytest_gpu.log", f"{tag}_small_team_sweep.log"):
         if os.path.exists(os.path.join(G, name)):
             shutil.copy(os.path.join(G, name), os.path.join(P, name))
     print("\n".join(lines))
