@@ -940,7 +940,12 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
             MARLSC_UNROLL
             for (int jj = 0; jj < SPL; ++jj) {
               const int s = tm.gl + G * jj;
-              if (s < S && rem[jj] > 0) dh_acc[w * S + s] += rem[jj];
+              if (s < S && rem[jj] > 0) {
+                // narrow teams: a fire-and-forget reduction instead of a load the next order would wait behind (the
+                // plane lives in L2; the cell belongs to this lane, phase 3 reads it back with ld.cg)
+                if (G < 32 && dh_mode == 1) global_add(&dh_acc[w * S + s], rem[jj]);
+                else dh_acc[w * S + s] += rem[jj];
+              }
             }
           }
         } else {
@@ -1188,7 +1193,7 @@ MDEV void step_env(const DevSpec& sp, const Tables& tb, const Team<G>& tm, const
       if (s < S) {
         const int i = base + s;
         vI[j] = s_inv[i];
-        if (dh_mode) vdh[j] = (LaneAlloc<G, CAPS>::value && dh_mode == 1) ? load_cg(&dh_acc[i]) : dh_acc[i];
+        if (dh_mode) vdh[j] = ((LaneAlloc<G, CAPS>::value || G < 32) && dh_mode == 1) ? load_cg(&dh_acc[i]) : dh_acc[i];
         vq[j] = ring_new[i];
         if (need_ship) {
           vsh[j] = s_sh[i];
