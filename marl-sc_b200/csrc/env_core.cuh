@@ -187,6 +187,11 @@ struct Team {
     if (G >= 32) sync();
     else __syncwarp(live);
   }
+  // the largest v over the teams of this warp (v itself for whole-warp teams): trip counts for loops that converge()
+  __device__ __forceinline__ int warp_max(int v) const {
+    if (G >= 32) return v;
+    return __reduce_max_sync(live, v);
+  }
   __device__ __forceinline__ bool any(bool p) const {
     if (G == 1) return p;
     if (G > 32) {
@@ -234,6 +239,7 @@ struct Team {
   void init(double* = nullptr, unsigned = 0) { gl = 0; }
   void sync() const {}
   void converge() const {}
+  int warp_max(int v) const { return v; }
   bool any(bool p) const { return p; }
   bool warp_any(bool p) const { return p; }
   unsigned ballot(bool p) const { return p ? 1u : 0u; }
@@ -767,9 +773,13 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
       if (tm.gl + G * k < nw) pre[k] = src_w[tm.gl + G * k];
   };
   if (prefetch && n_orders > 0) request(0);
-  for (int c0 = 0; c0 < n_orders; c0 += och) {
-    const int cn = imin(och, n_orders - c0);
-    int shift;
+  // teams narrower than a warp that allocate order by order stay in lockstep with the other teams of their warp
+  // (see one_order below): every team takes the chunk trips of the longest order list, with empty chunks at the end
+  constexpr bool kLockstep = G < 32 && !LaneAlloc<G, CAPS>::value;
+  const int n_trips = kLockstep ? tm.warp_max(n_orders) : n_orders;
+  for (int c0 = 0; c0 < n_trips; c0 += och) {
+    const int cn = imax(0, imin(och, n_orders - c0));
+    int shift = 0;
     if (prefetch) {
       if (tm.gl < cn) {
         int r = pre_r;
@@ -782,7 +792,7 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
       MARLSC_UNROLL
       for (int k = 0; k < kPre; ++k)
         if (tm.gl + G * k < nw) dst_w[tm.gl + G * k] = pre[k];
-    } else {
+    } else if (cn > 0) {
       for (int j = tm.gl; j < cn; j += G) {
         int r = io.order_region[o_begin + c0 + j];
         if ((CAPS & C_REGMAP) && sp.region_map) r = sp.region_map[r];
@@ -916,7 +926,10 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
       for (int j = tm.gl; j < cn; j += G)
         if (s_sreg[j] & 0x8000) smem_add(&s_lostN[s_sreg[j] & 0x7fff], 1);
     } else {
-      for (int j = 0; j < cn; ++j) {
+      // One order, every SKU of it walked down the region's warehouse list together. Teams narrower than a warp take
+      // the same number of trips (the longest order list among the teams of the warp) and meet after every order:
+      // the walks are data-dependent, and teams that are never brought back together run one after the other.
+      const auto one_order = [&](const int j) {
         const int r = s_sreg[j];
         const uint8_t* row = s_sqty + shift + j * row_bytes;
         int rem[SPL];
@@ -929,7 +942,7 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
           rem[jj] = d;
           dsum += d;
         }
-        if (!tm.any(dsum > 0)) continue;                         // all-zero order: nothing can ship or be lost
+        if (!tm.any(dsum > 0)) return;                           // all-zero order: nothing can ship or be lost
         // home-region demand of this step (multi_env.py:763-768)
         if (!dh_mode) {
         } else if (!(CAPS & C_BIGW) || tb.hmask) {
@@ -1069,6 +1082,11 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
             if (kDiag && io.d_lost_orders) io.d_lost_orders[e * R + r] += 1;
           }
         }
+      };
+      const int cn_trips = kLockstep ? tm.warp_max(cn) : cn;
+      for (int j = 0; j < cn_trips; ++j) {
+        if (!kLockstep || j < cn) one_order(j);
+        if (kLockstep) tm.converge();
       }
     }
     tm.sync();
