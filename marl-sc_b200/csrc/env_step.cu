@@ -155,7 +155,7 @@ int ensure_work(marlsc_env* env, int64_t num_envs) {
 
 // The split step covers what the lean instantiation covers, for teams of at least 8 lanes (and the SKUs-per-lane
 // values the automatic team choice produces).
-constexpr int64_t kTinySplitMaxEnvs = 16384;
+constexpr int64_t kTinySplitMaxEnvs = 4096;
 
 bool split_ok(const marlsc_env* env) {
   if (env->force_fused) return false;
@@ -237,10 +237,9 @@ int marlsc_env_create(const marlsc_env_spec_t* spec, int device, marlsc_env_t** 
   }
   env->device = device;
   env->team_auto = auto_team_size(env->ds.S);
-  // Tiny SKU counts: below ~16k environments a thread per environment leaves most of the machine idle behind one long
-  // dependent chain per thread (67 us per step at 4,096 environments of the 3 x 2 network); the split step with 8-lane
-  // teams runs the same step in 43 us there (32 us inside a CUDA graph). Larger batches, and launches the split step
-  // does not cover (diagnostic outputs, generic capabilities, the fused-kernel switch), go thread-per-environment, see
+  // Tiny SKU counts: small batches (up to 4,096 environments) take the split step with 8-lane teams, which spreads an
+  // environment over more lanes while most SMs would otherwise idle; larger batches, and launches the split step does
+  // not cover (diagnostic outputs, generic capabilities, the fused-kernel switch), go thread-per-environment, see
   // marlsc_env_step.
   if (env->team_auto == 1 && (required_caps(env->ds, env->tb, nullptr) & ~kCapsLean) == 0 && pick_spl(8, env->ds.S) == 1) {
     env->team_auto = 8;
@@ -486,9 +485,9 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   const bool lean = !env->force_generic && (required_caps(env->ds, env->tb, io) & ~kCapsLean) == 0;
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
   // the row kernels of the split step index (environment, warehouse) rows with 32 bits
-  // automatic 8-lane teams of a tiny SKU count: the split step wins while the batch leaves SMs idle (3 x 2 network,
-  // 8,192 environments: 48 against 70 us); from ~16k environments the thread-per-environment kernel's single launch is
-  // faster (32,768: 88 against 101 us; 262,144: 0.26 against 0.65 ms)
+  // automatic 8-lane teams of a tiny SKU count: the split step only wins while the batch leaves most SMs idle (3 x 2
+  // network, 4,096 environments: 43 against 48 us, 32 against 42 us inside a CUDA graph); beyond that the
+  // thread-per-environment kernel's single launch is faster (8,192: 49 against 52 us; 16,384: 52 against 69 us)
   const bool tiny = env->tiny_fallback && env->team == env->team_auto;
   const bool tiny_split = !tiny || state->num_envs <= kTinySplitMaxEnvs;
   if (lean && tiny_split && split_ok(env) && state->num_envs * (int64_t)env->ds.W < (int64_t)0xffffffffLL) {

@@ -88,7 +88,7 @@ def test_cuda_split_step_small_shapes(name, team):
 
 def test_tiny_network_takes_the_split_step_automatically():
     """A network with a handful of SKUs (BASELINE configs[1]: 3 warehouses x 2 SKUs) runs the split step with 8-lane teams
-    by default (below ~16k environments; larger batches keep the thread-per-environment kernel); launches the split step does not cover
+    by default (up to 4,096 environments; larger batches keep the thread-per-environment kernel); launches the split step does not cover
     (here: the fused-kernel switch) fall back to a thread per environment. Both paths against the golden trajectory, and
     against each other on a ragged batch."""
     from golden.scenarios import small_default
