@@ -194,7 +194,7 @@ __device__ __forceinline__ float nrm(float x, const float* __restrict__ mean, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1 (compact): one warp per environment, lane l owns SKUs l + 32 k. The row loops walk pointers (one add per row or
+// K1 (compact): one warp per environment; in the allocation a lane owns the SKUs its stream's map word names. The row loops walk pointers (one add per row or
 // plane, cells at constant offsets): the first version of this kernel spent 80 % of its 39 k warp instructions per
 // env-step on index arithmetic.
 // ---------------------------------------------------------------------------------------------------------------
@@ -685,7 +685,7 @@ compact_place_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__
 }
 
 // K1b': one warp per environment - stock into shared memory, allocation chains over the environment's lines, stock back,
-// outbound + lost-sales cost per warehouse to cost_alloc. Lane l owns SKUs l + 32 k.
+// outbound + lost-sales cost per warehouse to cost_alloc. A lane owns the SKUs its stream's map word names.
 template <int NCH, int FS>
 __global__ void __launch_bounds__(kCompactWarps * 32, MARLSC_ALLOC_CTAS)
 compact_alloc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ marlsc_env_state_t st,
