@@ -187,6 +187,11 @@ struct Team {
     if (G >= 32) sync();
     else __syncwarp(live);
   }
+  // vote over every live lane of the warp (teams narrower than a warp running a loop in lockstep), else over the team
+  __device__ __forceinline__ bool lock_any(bool p) const {
+    if (G >= 32) return warp_any(p);
+    return __ballot_sync(live, p) != 0u;
+  }
   // the largest v over the teams of this warp (v itself for whole-warp teams): trip counts for loops that converge()
   __device__ __forceinline__ int warp_max(int v) const {
     if (G >= 32) return v;
@@ -240,6 +245,7 @@ struct Team {
   void sync() const {}
   void converge() const {}
   int warp_max(int v) const { return v; }
+  bool lock_any(bool p) const { return p; }
   bool any(bool p) const { return p; }
   bool warp_any(bool p) const { return p; }
   unsigned ballot(bool p) const { return p ? 1u : 0u; }
@@ -776,7 +782,7 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
   // teams narrower than a warp that allocate order by order stay in lockstep with the other teams of their warp
   // (see one_order below): every team takes the chunk trips of the longest order list, with empty chunks at the end
   constexpr bool kLockstep = G < 32 && !LaneAlloc<G, CAPS>::value;
-  const int n_trips = kLockstep ? tm.warp_max(n_orders) : n_orders;
+  const int n_trips = G < 32 ? tm.warp_max(n_orders) : n_orders;
   for (int c0 = 0; c0 < n_trips; c0 += och) {
     const int cn = imax(0, imin(och, n_orders - c0));
     int shift = 0;
@@ -831,9 +837,13 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
       constexpr int kPassOrders = 64 / NA;
       const uint8_t* rows = s_sqty + shift;
       const int Wp = (W + 3) & ~3;
-      for (int j0 = 0; j0 < cn; j0 += kPassOrders)
+      // teams narrower than a warp run their passes in lockstep with the other teams of the warp: the same number of
+      // passes (empty ones for the shorter order lists) and one exit vote for all of them, so that the chains of
+      // four or two teams advance in the same instructions instead of one team after the other
+      const int cn_pass = G < 32 ? tm.warp_max(cn) : cn;
+      for (int j0 = 0; j0 < cn_pass; j0 += kPassOrders)
       for (int q0 = 0; q0 < NS; q0 += NA) {                           // one trip unless a lane owns > 32 * NC SKUs
-        const int pn = imin(kPassOrders, cn - j0);
+        const int pn = imax(0, imin(kPassOrders, cn - j0));
         uint32_t m[2][2] = {{0u, 0u}, {0u, 0u}};                      // [chain][low / high word], order-major bits
         for (int jj = 0; jj < pn; ++jj) {
           const uint8_t* row = rows + (j0 + jj) * row_bytes;
@@ -918,7 +928,7 @@ MDEV void allocate_orders(const DevSpec& sp, const Tables& tb, const Team<G>& tm
             }
           }
           // the team's warps run their chains apart
-          if (!tm.warp_any((rem[0] | rem[1]) > 0 || (m[0][0] | m[0][1] | m[1][0] | m[1][1]) != 0)) break;
+          if (!tm.lock_any((rem[0] | rem[1]) > 0 || (m[0][0] | m[0][1] | m[1][0] | m[1][1]) != 0)) break;
         }
       }
       tm.sync();

@@ -486,7 +486,7 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   const LaunchArgs la{env->ds, *state, env->max_smem_optin, lean};
   // the row kernels of the split step index (environment, warehouse) rows with 32 bits
   // automatic 8-lane teams of a tiny SKU count: the split step only wins while the batch leaves most SMs idle (3 x 2
-  // network, 4,096 environments: 43 against 48 us, 32 against 42 us inside a CUDA graph); beyond that the
+  // network, 4,096 environments: 40 against 48 us, 27 against 42 us inside a CUDA graph); beyond that the
   // thread-per-environment kernel's single launch is faster (8,192: 49 against 52 us; 16,384: 52 against 69 us)
   const bool tiny = env->tiny_fallback && env->team == env->team_auto;
   const bool tiny_split = !tiny || state->num_envs <= kTinySplitMaxEnvs;
