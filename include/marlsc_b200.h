@@ -361,6 +361,16 @@ int marlsc_gae(const float* rewards, const float* values, const uint8_t* cut, co
 size_t marlsc_standardize_workspace_bytes(void);
 int marlsc_standardize(float* x, int64_t n, void* workspace, void* stream);
 
+/* K7 - forward pass of a one-hidden-layer MLP head over every agent-sample of a rollout step (reference:
+ * ActorCriticRLModule._forward_actor / _forward_critic over an "mlp" network with one hidden layer,
+ * src/algorithms/models/rlmodules/base.py:412-457; IPPO model sizes config_files/algorithms/ippo.yaml):
+ *   out[n, :] = W2 act(W1 x[n, :] + b1) + b2,   activation 0 = ReLU, 1 = tanh, float32 throughout.
+ * x [n_rows, in_dim], w1 [hidden, in_dim], b1 [hidden], w2 [out_dim, hidden], b2 [out_dim] (torch.nn.Linear layouts),
+ * out [n_rows, out_dim], all on the device, contiguous. in_dim <= 64, out_dim <= 3 (action means of a 2-3 SKU network, or
+ * the value); anything else: MARLSC_EUNSUPPORTED, use the library GEMMs. The hidden activations stay in registers. */
+int marlsc_mlp1_forward(const float* x, int64_t n_rows, int32_t in_dim, const float* w1, const float* b1, int32_t hidden,
+                        const float* w2, const float* b2, int32_t out_dim, int32_t activation, float* out, void* stream);
+
 /* K6 - PPO objective of one minibatch, forward and backward (RLlib PPOTorchLearner as the reference configures it,
  * src/algorithms/ippo.py:145-160; hysteretic_beta < 0 disables the weighting of learners/hysteretic_learner.py:39-42):
  *   L_p = -mean_p(min(ratio adv, clip(ratio, 1-c, 1+c) adv)) + vf_loss_coeff mean_p(min((value - target)^2, vf_clip_param))

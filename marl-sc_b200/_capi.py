@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
     L.marlsc_policy_base_stock_per_env.restype = C.c_int
     L.marlsc_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.marlsc_gae.restype = C.c_int
+    L.marlsc_mlp1_forward.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32, i32, vp, vp]
+    L.marlsc_mlp1_forward.restype = C.c_int
     L.marlsc_ppo_loss.argtypes = [vp, vp, vp, i32, C.c_float, vp, vp, vp, vp, vp, vp, C.c_float, i64, i32, C.c_float, C.c_float,
                                   C.c_float, C.c_float, vp, vp, vp, vp]
     L.marlsc_ppo_loss.restype = C.c_int

@@ -76,10 +76,33 @@ def stacked_mlp(n: int, in_dim: int, hidden: Sequence[int], out_dim: int, activa
     return nn.Sequential(*layers)
 
 
+def _fused_mlp1(mods, h: torch.Tensor) -> Optional[torch.Tensor]:
+    """K7 (``marlsc_mlp1_forward``, csrc/mlp_forward.cu): a ``Linear -> ReLU|Tanh -> Linear`` head with at most 64 inputs and
+    3 outputs (the IPPO actor / critic of the small networks) in one kernel that keeps the hidden activations in
+    registers. Returns None when the network or the tensors do not qualify."""
+    if len(mods) != 3 or not isinstance(mods[0], nn.Linear) or not isinstance(mods[2], nn.Linear):
+        return None
+    act = 0 if isinstance(mods[1], nn.ReLU) else (1 if isinstance(mods[1], nn.Tanh) else -1)
+    l1, l2 = mods[0], mods[2]
+    if (act < 0 or l1.bias is None or l2.bias is None or l1.in_features > 64 or l2.out_features > 3 or h.dtype != torch.float32
+            or any(t.dtype != torch.float32 or not t.is_contiguous() for t in (l1.weight, l1.bias, l2.weight, l2.bias))):
+        return None
+    from .. import _capi
+    h = h.contiguous()
+    out = torch.empty((h.shape[0], l2.out_features), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        stream = torch.cuda.current_stream(h.device).cuda_stream
+        _capi.check(_capi.lib().marlsc_mlp1_forward(h.data_ptr(), h.shape[0], l1.in_features, l1.weight.data_ptr(), l1.bias.data_ptr(),
+                                                    l1.out_features, l2.weight.data_ptr(), l2.bias.data_ptr(), l2.out_features, act,
+                                                    out.data_ptr(), stream))
+    return out
+
+
 def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """``seq(x)`` for an :func:`mlp`; without autograd on a CUDA tensor a Linear followed by ReLU runs as one
     cuBLASLt GEMM with the bias and the ReLU in its epilogue, so the hidden activations (800 MB per MLP at
-    262,144 small environments) cross HBM once instead of three times."""
+    262,144 small environments) cross HBM once instead of three times - and a one-hidden-layer head with few inputs and
+    outputs runs in the library's own kernel, where they do not cross HBM at all (``_fused_mlp1``)."""
     if torch.is_grad_enabled() or not x.is_cuda or not hasattr(torch, "_addmm_activation"):
         return seq(x)
     lead = x.shape[:-1]
@@ -87,6 +110,9 @@ def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     mods = list(seq)
     if any(isinstance(m, StackedLinear) for m in mods):
         return seq(x)
+    fused = _fused_mlp1(mods, h)
+    if fused is not None:
+        return fused.reshape(*lead, fused.shape[-1])
     i = 0
     while i < len(mods):
         m = mods[i]

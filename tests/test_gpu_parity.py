@@ -855,6 +855,27 @@ def test_adaptive_constant_and_random_baselines_match_reference_formulas():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("D,H,O,act,N", [(14, 256, 2, "relu", 70001), (14, 256, 1, "relu", 257), (3, 17, 3, "tanh", 1000),
+                                         (32, 64, 1, "relu", 4099), (56, 64, 1, "tanh", 513), (64, 300, 3, "relu", 130)])
+def test_fused_mlp_forward_matches_pytorch(D, H, O, act, N):
+    """K7 (marlsc_mlp1_forward: one-hidden-layer head, hidden activations in registers; reference network: mlp of
+    rlmodules/base.py:412-457) against the same nn.Sequential evaluated by PyTorch in float32 (cuBLAS TF32 off) - rows that
+    do not fill the last thread pair / CTA, every input-width instantiation, both activations."""
+    from marlsc_b200.rollout.policy import forward_mlp, mlp
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(D * 1000 + H)
+    net = mlp(D, (H,), O, act).cuda()
+    x = torch.randn((N // 3 + 1, 3, D), device="cuda:0")[: N // 3 + 1]
+    with torch.no_grad():
+        got = forward_mlp(net, x)
+        want = net(x)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-6)
+    # with autograd on, the PyTorch modules run (the learner's path)
+    y = forward_mlp(net, x[:4])
+    assert y.requires_grad
+
+
 def test_fresh_rollout_has_ratio_one_and_zero_kl():
     """The collector stores the RAW Gaussian sample the log-prob refers to and sends only its clipped copy to the env
     (RLlib clip_actions=True, reference ippo.py:183-188): on the first minibatch of a fresh rollout the probability
