@@ -21,9 +21,10 @@
 namespace marlsc {
 namespace {
 
-// DP: input width padded to whole 16-byte words (x and W1 rows zero-padded); ROWS rows per thread; ACT 0 ReLU, 1 tanh.
+// DP: input width padded to whole 16-byte words (x and W1 rows zero-padded); ROWS rows per thread (four for narrow inputs:
+// a record is read once per ROWS rows); ACT 0 ReLU, 1 tanh; NO outputs.
 // Shared-memory record of hidden unit j: DP floats of W1[j,:], then b1[j], W2[0,j], W2[1,j], W2[2,j] (O <= 3).
-template <int DP, int ROWS, int ACT>
+template <int DP, int ROWS, int ACT, int NO>
 __global__ void __launch_bounds__(128)
 mlp1_forward_kernel(const float* __restrict__ x, long long N, int D, const float* __restrict__ w1, const float* __restrict__ b1, int H,
                     const float* __restrict__ w2, const float* __restrict__ b2, int O, float* __restrict__ out) {
@@ -74,8 +75,8 @@ mlp1_forward_kernel(const float* __restrict__ x, long long N, int D, const float
         for (int d = 0; d < DP; ++d) h = fmaf(xr[r][d], w[d], h);
         h = ACT == 0 ? fmaxf(h, 0.0f) : tanhf(h);
         acc[r][0] = fmaf(h, tail.y, acc[r][0]);
-        acc[r][1] = fmaf(h, tail.z, acc[r][1]);
-        acc[r][2] = fmaf(h, tail.w, acc[r][2]);
+        if (NO > 1) acc[r][1] = fmaf(h, tail.z, acc[r][1]);
+        if (NO > 2) acc[r][2] = fmaf(h, tail.w, acc[r][2]);
       }
     }
 #pragma unroll
@@ -94,12 +95,20 @@ int launch_mlp1(const float* x, long long N, int D, const float* w1, const float
   MARLSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   MARLSC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if ((int)smem > optin) return set_error(MARLSC_EUNSUPPORTED, "mlp1_forward: the hidden layer's weights do not fit shared memory");
-  const void* fn = act == 0 ? (const void*)mlp1_forward_kernel<DP, ROWS, 0> : (const void*)mlp1_forward_kernel<DP, ROWS, 1>;
-  if (smem > 48 * 1024) MARLSC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long want = (N + 128LL * ROWS - 1) / (128LL * ROWS);
   const unsigned grid = (unsigned)(want < (long long)sms * 8 ? (want > 0 ? want : 1) : (long long)sms * 8);
-  if (act == 0) mlp1_forward_kernel<DP, ROWS, 0><<<grid, 128, smem, s>>>(x, N, D, w1, b1, H, w2, b2, O, out);
-  else mlp1_forward_kernel<DP, ROWS, 1><<<grid, 128, smem, s>>>(x, N, D, w1, b1, H, w2, b2, O, out);
+#define MARLSC_MLP1(A, K)                                                                                                  \
+  {                                                                                                                        \
+    if (smem > 48 * 1024)                                                                                                  \
+      MARLSC_CUDA(cudaFuncSetAttribute((const void*)mlp1_forward_kernel<DP, ROWS, A, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mlp1_forward_kernel<DP, ROWS, A, K><<<grid, 128, smem, s>>>(x, N, D, w1, b1, H, w2, b2, O, out);                        \
+  }
+  if (act == 0) {
+    if (O == 1) MARLSC_MLP1(0, 1) else if (O == 2) MARLSC_MLP1(0, 2) else MARLSC_MLP1(0, 3)
+  } else {
+    if (O == 1) MARLSC_MLP1(1, 1) else if (O == 2) MARLSC_MLP1(1, 2) else MARLSC_MLP1(1, 3)
+  }
+#undef MARLSC_MLP1
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MARLSC_CUDA(cudaGetLastError());
   return MARLSC_OK;
@@ -117,7 +126,7 @@ extern "C" int marlsc_mlp1_forward(const float* x, int64_t n_rows, int32_t in_di
     return set_error(MARLSC_EUNSUPPORTED, "mlp1_forward: in_dim <= 64, out_dim <= 3, activation 0 (ReLU) or 1 (tanh)");
   if (n_rows == 0) return MARLSC_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (in_dim <= 16) return launch_mlp1<16, 2>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
+  if (in_dim <= 16) return launch_mlp1<16, 4>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
   if (in_dim <= 32) return launch_mlp1<32, 2>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
   return launch_mlp1<64, 1>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
 }
