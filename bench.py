@@ -926,7 +926,7 @@ def run_rollout(args):
         k1 = dict(bound="hbm", kernel="env_step_kernel (K1, thread per environment)", k1_ms_per_launch=k1_ms,
                   algorithmic_bytes_per_env_step=b_env, achieved=b_env * E / (k1_ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
                   frac=b_env * E / (k1_ms * 1e-3) / 1e9 / peak, traffic=None,
-                  note="the step of this shape is a small part of the rollout: the MLP forwards (cuBLAS) dominate")
+                  note="the step of this shape is one part of the rollout next to the MLP forwards (K7 for one-hidden-layer heads, library GEMMs otherwise) and the demand sampler")
     if rank == 0:
         value = E * 3 * T * args.steps * world / (ms * 1e-3)
         r_host = ro.rewards.mean().item()                       # device->host read of the rollout's result
