@@ -390,6 +390,7 @@ def learner_allreduce_record(dev, world, rank, minibatch_envs=8192):
     bus = lambda b, ms: 2.0 * (world - 1) / world * b / (ms * 1e-3) / 1e9     # noqa: E731  (ring all-reduce bus bandwidth)
     return dict(ranks=world, parameters=n_par, bytes=nbytes, buckets=len(learner.buckets.buckets),
                 minibatch_agent_samples=B * W, ms_minibatch_step_with_allreduce=ms_step, ms_allreduce_alone=ms_ar,
+                learner_agent_samples_per_s=world * B * W / (ms_step * 1e-3),
                 busbw_gbs_gradient_allreduce=bus(nbytes, ms_ar), busbw_gbs_256mb_allreduce=bus(big.numel() * 4, ms_big),
                 note="gradient all-reduce of a 0.3 MB buffer is latency-bound; the 256 MB figure shows the NVLink/NVSwitch "
                      "bandwidth NCCL reaches on this box; no collective runs on the step / GAE path")
