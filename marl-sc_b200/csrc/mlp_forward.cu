@@ -81,8 +81,10 @@ mlp1_forward_kernel(const float* __restrict__ x, long long N, int D, const float
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
-      if (row0 + r < N)
-        for (int k = 0; k < O; ++k) out[(row0 + r) * O + k] = acc[r][k];
+      if (row0 + r < N) {
+#pragma unroll
+        for (int k = 0; k < NO; ++k) out[(row0 + r) * NO + k] = acc[r][k];
+      }
   }
 }
 
