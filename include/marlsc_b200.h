@@ -371,6 +371,23 @@ int marlsc_standardize(float* x, int64_t n, void* workspace, void* stream);
 int marlsc_mlp1_forward(const float* x, int64_t n_rows, int32_t in_dim, const float* w1, const float* b1, int32_t hidden,
                         const float* w2, const float* b2, int32_t out_dim, int32_t activation, float* out, void* stream);
 
+/* K7a - input layer of a deeper MLP head during rollouts: out[n, :] = act(W x[n, :] + b), activation 0 ReLU, 1 tanh,
+ * 2 none (the first nn.Linear of the reference's "mlp" networks, rlmodules/base.py:412-457). x [n_rows, in_dim],
+ * w [hidden, in_dim], b [hidden], out [n_rows, hidden], float32, device, contiguous; in_dim <= 64, hidden <= 256 and
+ * ceil(hidden / 32) x (in_dim padded to 16 / 32 / 64) <= 128, else MARLSC_EUNSUPPORTED. */
+int marlsc_linear_in_forward(const float* x, int64_t n_rows, int32_t in_dim, const float* w, const float* b, int32_t hidden,
+                             int32_t activation, float* out, void* stream);
+
+/* K7b - output layer of a deeper MLP head during rollouts: out[n, :] = W a[n, :] + b for out_dim <= 4 (the last
+ * nn.Linear of the reference's "mlp" networks, rlmodules/base.py:412-457, e.g. MAPPO's actor [14, 256, 256, 2] and
+ * critic [56, 64, 64, 1], config_files/algorithms/mappo.yaml:43-55), where a = h, or - with pre_bias != NULL -
+ * a = relu(h + pre_bias): h is then the RAW product of the hidden layer before, whose bias [in_dim] and ReLU are applied
+ * on the way in (saves the separate epilogue pass the library GEMM runs over the activations). h [n_rows, in_dim]
+ * (in_dim a multiple of 4, <= 2048), w [out_dim, in_dim], b [out_dim], out [n_rows, out_dim], float32, device,
+ * contiguous, h / w / pre_bias 16-byte aligned. One pass over h at the HBM rate. */
+int marlsc_linear_out_forward(const float* h, int64_t n_rows, int32_t in_dim, const float* pre_bias, const float* w, const float* b,
+                              int32_t out_dim, float* out, void* stream);
+
 /* K6 - PPO objective of one minibatch, forward and backward (RLlib PPOTorchLearner as the reference configures it,
  * src/algorithms/ippo.py:145-160; hysteretic_beta < 0 disables the weighting of learners/hysteretic_learner.py:39-42):
  *   L_p = -mean_p(min(ratio adv, clip(ratio, 1-c, 1+c) adv)) + vf_loss_coeff mean_p(min((value - target)^2, vf_clip_param))

@@ -141,6 +141,10 @@ def lib() -> C.CDLL:
     L.marlsc_gae.restype = C.c_int
     L.marlsc_mlp1_forward.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32, i32, vp, vp]
     L.marlsc_mlp1_forward.restype = C.c_int
+    L.marlsc_linear_out_forward.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp, vp]
+    L.marlsc_linear_out_forward.restype = C.c_int
+    L.marlsc_linear_in_forward.argtypes = [vp, i64, i32, vp, vp, i32, i32, vp, vp]
+    L.marlsc_linear_in_forward.restype = C.c_int
     L.marlsc_ppo_loss.argtypes = [vp, vp, vp, i32, C.c_float, vp, vp, vp, vp, vp, vp, C.c_float, i64, i32, C.c_float, C.c_float,
                                   C.c_float, C.c_float, vp, vp, vp, vp]
     L.marlsc_ppo_loss.restype = C.c_int

@@ -116,6 +116,156 @@ int launch_mlp1(const float* x, long long N, int D, const float* w1, const float
   return MARLSC_OK;
 }
 
+// Output layer of a deeper head: out[n, :] = W h[n, :] + b with a handful of outputs (action means of a small network, the
+// value). The library GEMM path treats this as a [N x H] x [H x 2] product and reads the 805 MB of hidden activations at a
+// third of the HBM rate, then adds the bias in a second pass; here a warp takes a row as 16-byte words (one coalesced
+// 1 KB request per 256 floats), every lane keeps NO partial dot products, five shuffle rounds finish them. With PRE the
+// rows are the RAW product of the hidden layer before, whose bias and ReLU are applied on the way in: cuBLASLt runs the
+// "fused" bias + ReLU epilogue of its fp32 SIMT kernels as a separate pass over the activations (0.95 ms for 805 MB, as
+// long as half the GEMM), which a plain product followed by this kernel avoids.
+template <int NO, bool PRE>
+__global__ void __launch_bounds__(256)
+linear_out_kernel(const float* __restrict__ h, long long N, int H, const float* __restrict__ pre_bias, const float* __restrict__ w,
+                  const float* __restrict__ b, float* __restrict__ out) {
+  extern __shared__ float4 s_w4[];                    // [NO][H / 4], then (PRE) the producing layer's bias [H / 4]
+  const int H4 = H >> 2;
+  for (int i = threadIdx.x; i < NO * H4; i += blockDim.x) s_w4[i] = reinterpret_cast<const float4*>(w)[i];
+  if (PRE)
+    for (int i = threadIdx.x; i < H4; i += blockDim.x) s_w4[NO * H4 + i] = reinterpret_cast<const float4*>(pre_bias)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < N; row += n_warps) {
+    const float4* const hr = reinterpret_cast<const float4*>(h) + row * H4;
+    float acc[NO];
+#pragma unroll
+    for (int k = 0; k < NO; ++k) acc[k] = 0.0f;
+    for (int c = lane; c < H4; c += 32) {
+      float4 v = hr[c];
+      if (PRE) {                                      // h holds the raw product of the layer before: + bias, ReLU
+        const float4 pb = s_w4[NO * H4 + c];
+        v.x = fmaxf(v.x + pb.x, 0.0f);
+        v.y = fmaxf(v.y + pb.y, 0.0f);
+        v.z = fmaxf(v.z + pb.z, 0.0f);
+        v.w = fmaxf(v.w + pb.w, 0.0f);
+      }
+#pragma unroll
+      for (int k = 0; k < NO; ++k) {
+        const float4 q = s_w4[k * H4 + c];
+        acc[k] = fmaf(v.x, q.x, acc[k]);
+        acc[k] = fmaf(v.y, q.y, acc[k]);
+        acc[k] = fmaf(v.z, q.z, acc[k]);
+        acc[k] = fmaf(v.w, q.w, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NO; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NO; ++k) out[row * NO + k] = acc[k] + b[k];
+    }
+  }
+}
+
+// Input layer of a deeper head: h[n, :] = act(W x[n, :] + b) for narrow inputs (14 or 56 observation floats) and up to
+// 256 hidden units. The library picks unaligned small-K GEMM kernels for these shapes (0.4-0.6 ms for an 805 MB or
+// 201 MB result); here a lane keeps the weight rows of its UPL hidden units in registers (unit j = lane + 32 k). A warp
+// takes kInRows rows of x at a time: the rows are contiguous, so the batch is a few coalesced loads per lane, requested one
+// batch ahead, parked in shared memory and read back as broadcast 16-byte words; the rows of h leave as UPL coalesced
+// 128-byte stores each.
+constexpr int kInRows = 4;
+
+template <int UPL, int DP, int ACT>
+__global__ void __launch_bounds__(256)
+linear_in_kernel(const float* __restrict__ x, long long N, int D, const float* __restrict__ w, const float* __restrict__ b, int H,
+                 float* __restrict__ out) {
+  __shared__ __align__(16) float s_x[8][kInRows * DP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float wr[UPL][DP], bias[UPL];
+#pragma unroll
+  for (int k = 0; k < UPL; ++k) {
+    const int j = lane + 32 * k;
+    bias[k] = j < H ? b[j] : 0.0f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) wr[k][d] = (j < H && d < D) ? w[(long long)j * D + d] : 0.0f;
+  }
+  float* const xs = s_x[wid];
+  for (int i = lane; i < kInRows * DP; i += 32) xs[i] = 0.0f;     // the padding columns stay zero
+  constexpr int kLd = (kInRows * DP + 31) / 32;                   // loads per lane and batch (D <= DP)
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_batches = (N + kInRows - 1) / kInRows;
+  float pre[kLd];
+  const auto request = [&](long long batch) {                     // the batch's kInRows x D contiguous floats
+    const long long first = batch * kInRows * D, last = N * D;
+#pragma unroll
+    for (int q = 0; q < kLd; ++q) {
+      const int i = lane + 32 * q;
+      pre[q] = (i < kInRows * D && first + i < last) ? x[first + i] : 0.0f;
+    }
+  };
+  if (warp < n_batches) request(warp);
+  for (long long batch = warp; batch < n_batches; batch += n_warps) {
+    __syncwarp();                                                 // the previous batch has been read out
+#pragma unroll
+    for (int q = 0; q < kLd; ++q) {
+      const int i = lane + 32 * q;
+      if (i < kInRows * D) xs[(i / D) * DP + (i % D)] = pre[q];
+    }
+    __syncwarp();
+    if (batch + n_warps < n_batches) request(batch + n_warps);    // in flight while this batch is computed
+    float h[kInRows][UPL];                                        // kInRows x UPL independent chains
+#pragma unroll
+    for (int r = 0; r < kInRows; ++r)
+#pragma unroll
+      for (int k = 0; k < UPL; ++k) h[r][k] = bias[k];
+#pragma unroll
+    for (int d4 = 0; d4 < DP / 4; ++d4) {
+#pragma unroll
+      for (int r = 0; r < kInRows; ++r) {
+        const float4 v = reinterpret_cast<const float4*>(xs + r * DP)[d4];
+#pragma unroll
+        for (int k = 0; k < UPL; ++k) {
+          h[r][k] = fmaf(v.x, wr[k][4 * d4], h[r][k]);
+          h[r][k] = fmaf(v.y, wr[k][4 * d4 + 1], h[r][k]);
+          h[r][k] = fmaf(v.z, wr[k][4 * d4 + 2], h[r][k]);
+          h[r][k] = fmaf(v.w, wr[k][4 * d4 + 3], h[r][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kInRows; ++r) {
+      const long long row = batch * kInRows + r;
+      if (row < N) {
+        float* const o = out + row * H + lane;
+#pragma unroll
+        for (int k = 0; k < UPL; ++k) {
+          float y = h[r][k];
+          if (ACT == 0) y = fmaxf(y, 0.0f);
+          if (ACT == 1) y = tanhf(y);
+          if (lane + 32 * k < H) o[32 * k] = y;
+        }
+      }
+    }
+  }
+}
+
+template <int UPL, int DP>
+int launch_linear_in(const float* x, long long N, int D, const float* w, const float* b, int H, int act, float* out, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  MARLSC_CUDA(cudaGetDevice(&dev));
+  MARLSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long want = (N + 7) / 8;
+  const unsigned grid = (unsigned)(want < (long long)sms * 4 ? want : (long long)sms * 4);
+  if (act == 0) linear_in_kernel<UPL, DP, 0><<<grid, 256, 0, s>>>(x, N, D, w, b, H, out);
+  else if (act == 1) linear_in_kernel<UPL, DP, 1><<<grid, 256, 0, s>>>(x, N, D, w, b, H, out);
+  else linear_in_kernel<UPL, DP, 2><<<grid, 256, 0, s>>>(x, N, D, w, b, H, out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
 }  // namespace
 }  // namespace marlsc
 
@@ -131,4 +281,59 @@ extern "C" int marlsc_mlp1_forward(const float* x, int64_t n_rows, int32_t in_di
   if (in_dim <= 16) return launch_mlp1<16, 4>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
   if (in_dim <= 32) return launch_mlp1<32, 2>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
   return launch_mlp1<64, 1>(x, n_rows, in_dim, w1, b1, hidden, w2, b2, out_dim, activation, out, s);
+}
+
+extern "C" int marlsc_linear_out_forward(const float* h, int64_t n_rows, int32_t in_dim, const float* pre_bias, const float* w,
+                                         const float* b, int32_t out_dim, float* out, void* stream) {
+  if (!h || !w || !b || !out) return set_error(MARLSC_EINVAL, "linear_out_forward: null pointer");
+  if (n_rows < 0 || in_dim < 4 || (in_dim & 3) || in_dim > 2048 || out_dim < 1 || out_dim > 4 ||
+      ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(pre_bias)) & 15u))
+    return set_error(MARLSC_EUNSUPPORTED, "linear_out_forward: in_dim a multiple of 4 (<= 2048), out_dim <= 4, 16-byte aligned h, w, pre_bias");
+  if (n_rows == 0) return MARLSC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  MARLSC_CUDA(cudaGetDevice(&dev));
+  MARLSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = (size_t)(out_dim + (pre_bias ? 1 : 0)) * in_dim * sizeof(float);
+  const long long want = (n_rows + 7) / 8;
+  const unsigned grid = (unsigned)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+#define MARLSC_LOUT(K)                                                                                      \
+  if (pre_bias) linear_out_kernel<K, true><<<grid, 256, smem, s>>>(h, n_rows, in_dim, pre_bias, w, b, out);  \
+  else linear_out_kernel<K, false><<<grid, 256, smem, s>>>(h, n_rows, in_dim, pre_bias, w, b, out);
+  switch (out_dim) {
+    case 1: MARLSC_LOUT(1) break;
+    case 2: MARLSC_LOUT(2) break;
+    case 3: MARLSC_LOUT(3) break;
+    default: MARLSC_LOUT(4) break;
+  }
+#undef MARLSC_LOUT
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MARLSC_CUDA(cudaGetLastError());
+  return MARLSC_OK;
+}
+
+extern "C" int marlsc_linear_in_forward(const float* x, int64_t n_rows, int32_t in_dim, const float* w, const float* b, int32_t hidden,
+                                        int32_t activation, float* out, void* stream) {
+  if (!x || !w || !b || !out) return set_error(MARLSC_EINVAL, "linear_in_forward: null pointer");
+  const int dp = in_dim <= 16 ? 16 : (in_dim <= 32 ? 32 : 64);
+  const int upl = hidden <= 32 ? 1 : (hidden <= 64 ? 2 : (hidden <= 128 ? 4 : 8));
+  if (n_rows < 0 || in_dim < 1 || in_dim > 64 || hidden < 1 || hidden > 256 || upl * dp > 128 || activation < 0 || activation > 2)
+    return set_error(MARLSC_EUNSUPPORTED, "linear_in_forward: in_dim <= 64, hidden <= 256, ceil(hidden / 32) x padded in_dim <= 128");
+  if (n_rows == 0) return MARLSC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define MARLSC_LIN(U, P) return launch_linear_in<U, P>(x, n_rows, in_dim, w, b, hidden, activation, out, s)
+  if (dp == 16) {
+    if (upl == 1) MARLSC_LIN(1, 16);
+    if (upl == 2) MARLSC_LIN(2, 16);
+    if (upl == 4) MARLSC_LIN(4, 16);
+    MARLSC_LIN(8, 16);
+  }
+  if (dp == 32) {
+    if (upl == 1) MARLSC_LIN(1, 32);
+    if (upl == 2) MARLSC_LIN(2, 32);
+    MARLSC_LIN(4, 32);
+  }
+  if (upl == 1) MARLSC_LIN(1, 64);
+  MARLSC_LIN(2, 64);
+#undef MARLSC_LIN
 }

@@ -98,6 +98,35 @@ def _fused_mlp1(mods, h: torch.Tensor) -> Optional[torch.Tensor]:
     return out
 
 
+def _linear_out_ok(m, h: torch.Tensor) -> bool:
+    """Shapes ``marlsc_linear_out_forward`` takes: a multiple of 4 inputs (<= 2048), at most 4 outputs."""
+    return (isinstance(m, nn.Linear) and m.bias is not None and m.out_features <= 4 and m.in_features % 4 == 0
+            and 4 <= m.in_features <= 2048 and h.dtype == torch.float32 and m.weight.dtype == torch.float32
+            and m.weight.is_contiguous() and m.bias.is_contiguous())
+
+
+def _linear_out(h: torch.Tensor, m: nn.Linear, pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    from .. import _capi
+    h = h.contiguous()
+    out = torch.empty((h.shape[0], m.out_features), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        _capi.check(_capi.lib().marlsc_linear_out_forward(h.data_ptr(), h.shape[0], m.in_features,
+                                                          pre_bias.data_ptr() if pre_bias is not None else None,
+                                                          m.weight.data_ptr(), m.bias.data_ptr(), m.out_features, out.data_ptr(),
+                                                          torch.cuda.current_stream(h.device).cuda_stream))
+    return out
+
+
+def _linear_in_ok(m, h: torch.Tensor) -> bool:
+    """Shapes ``marlsc_linear_in_forward`` takes: <= 64 inputs, <= 256 units, ceil(units / 32) x padded inputs <= 128."""
+    if not isinstance(m, nn.Linear) or m.bias is None or m.in_features > 64 or m.out_features > 256:
+        return False
+    dp = 16 if m.in_features <= 16 else (32 if m.in_features <= 32 else 64)
+    upl = 1 if m.out_features <= 32 else (2 if m.out_features <= 64 else (4 if m.out_features <= 128 else 8))
+    return (upl * dp <= 128 and h.dtype == torch.float32 and m.weight.dtype == torch.float32 and m.weight.is_contiguous()
+            and m.bias.is_contiguous())
+
+
 def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """``seq(x)`` for an :func:`mlp`; without autograd on a CUDA tensor a Linear followed by ReLU runs as one
     cuBLASLt GEMM with the bias and the ReLU in its epilogue, so the hidden activations (800 MB per MLP at
@@ -116,9 +145,31 @@ def forward_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     i = 0
     while i < len(mods):
         m = mods[i]
-        if isinstance(m, nn.Linear) and m.bias is not None and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+        if i == 0 and _linear_in_ok(m, h):
+            # K7a: the input layer (few inputs, up to 256 units) with its activation (csrc/mlp_forward.cu)
+            nxt = mods[1] if len(mods) > 1 else None
+            act = 0 if isinstance(nxt, nn.ReLU) else (1 if isinstance(nxt, nn.Tanh) else 2)
+            from .. import _capi
+            h = h.contiguous()
+            out = torch.empty((h.shape[0], m.out_features), dtype=torch.float32, device=h.device)
+            with torch.cuda.device(h.device):
+                _capi.check(_capi.lib().marlsc_linear_in_forward(h.data_ptr(), h.shape[0], m.in_features, m.weight.data_ptr(),
+                                                                 m.bias.data_ptr(), m.out_features, act, out.data_ptr(),
+                                                                 torch.cuda.current_stream(h.device).cuda_stream))
+            h = out
+            i += 1 if act == 2 else 2
+        elif (isinstance(m, nn.Linear) and m.bias is not None and i + 2 == len(mods) - 1 and isinstance(mods[i + 1], nn.ReLU)
+              and _linear_out_ok(mods[i + 2], h) and m.out_features == mods[i + 2].in_features and m.bias.is_contiguous()):
+            # last hidden layer + output layer: a plain product, then K7b applies this layer's bias and ReLU on the way in
+            # (the library's "fused" bias + ReLU epilogue is a second pass over the activations for fp32)
+            h = _linear_out(torch.mm(h, m.weight.t()), mods[i + 2], pre_bias=m.bias)
+            i += 3
+        elif isinstance(m, nn.Linear) and m.bias is not None and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
             h = torch._addmm_activation(m.bias, h, m.weight.t())
             i += 2
+        elif isinstance(m, nn.Linear) and i == len(mods) - 1 and _linear_out_ok(m, h):
+            h = _linear_out(h, m)                                  # K7b: the output layer in one pass over the activations
+            i += 1
         else:
             h = m(h)
             i += 1
@@ -173,6 +224,11 @@ class ActorCritic(nn.Module):
             return forward_mlp(self.critic, obs).squeeze(-1)
         E, W, D = obs.shape
         first = self.critic[0]
+        if self.parameter_sharing and not torch.is_grad_enabled() and obs.is_cuda and _linear_in_ok(first, obs):
+            # rollouts: [local | global] rows written once (E x W x (D + W D) floats), then the whole critic through the
+            # library's own layer kernels
+            xcat = torch.cat([obs, obs.reshape(E, 1, W * D).expand(E, W, W * D)], dim=-1)
+            return forward_mlp(self.critic, xcat).squeeze(-1)
         if self.parameter_sharing:
             wl, wg = first.weight[:, :D], first.weight[:, D:]
             h = obs @ wl.t() + (obs.reshape(E, W * D) @ wg.t()).unsqueeze(1) + first.bias

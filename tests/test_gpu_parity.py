@@ -876,6 +876,40 @@ def test_fused_mlp_forward_matches_pytorch(D, H, O, act, N):
     assert y.requires_grad
 
 
+@pytest.mark.parametrize("D,hidden,O,N", [(14, (256, 256), 2, 50001), (56, (64, 64), 1, 4097), (10, (32, 20, 8), 4, 333),
+                                          (30, (100, 64), 3, 1000), (64, (48, 16), 1, 77), (3, (250, 4), 2, 999)])
+def test_deeper_mlp_rollout_forward_matches_pytorch(D, hidden, O, N):
+    """Heads with more than one hidden layer (MAPPO's actor and critic, mappo.yaml:43-55): hidden layers through the library
+    GEMM with bias + ReLU in its epilogue, the input layer through K7a (marlsc_linear_in_forward, every register
+    tiling it instantiates) and the output layer through K7b (marlsc_linear_out_forward) - against the same nn.Sequential
+    in PyTorch float32."""
+    from marlsc_b200.rollout.policy import forward_mlp, mlp
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(D + N)
+    net = mlp(D, hidden, O, "relu").cuda()
+    x = torch.randn((N, D), device="cuda:0")
+    with torch.no_grad():
+        got, want = forward_mlp(net, x), net(x)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-6)
+
+
+def test_global_critic_rollout_path_matches_autograd_path():
+    """MAPPO's centralised critic (critic_obs_type 'global', mappo.py:142-157): without autograd the value runs through the
+    library's layer kernels over [local | global] rows, with autograd through PyTorch's split first layer - same numbers."""
+    from marlsc_b200.rollout import ActorCritic
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(5)
+    pol = ActorCritic(14, 3, 2, actor_hidden=(256, 256), critic_hidden=(64, 64), critic_obs_type="global", parameter_sharing=True).cuda()
+    obs = torch.randn((1001, 3, 14), device="cuda:0")
+    with torch.no_grad():
+        fast = pol.value(obs)
+        mean_fast = pol.action_mean(obs)
+    slow, mean_slow = pol.value(obs), pol.action_mean(obs)
+    assert slow.requires_grad and not fast.requires_grad
+    torch.testing.assert_close(fast, slow.detach(), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(mean_fast, mean_slow.detach(), rtol=1e-5, atol=2e-6)
+
+
 def test_fresh_rollout_has_ratio_one_and_zero_kl():
     """The collector stores the RAW Gaussian sample the log-prob refers to and sends only its clipped copy to the env
     (RLlib clip_actions=True, reference ippo.py:183-188): on the first minibatch of a fresh rollout the probability
