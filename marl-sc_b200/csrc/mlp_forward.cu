@@ -172,15 +172,15 @@ linear_out_kernel(const float* __restrict__ h, long long N, int H, const float* 
 // Input layer of a deeper head: h[n, :] = act(W x[n, :] + b) for narrow inputs (14 or 56 observation floats) and up to
 // 256 hidden units. The library picks unaligned small-K GEMM kernels for these shapes (0.4-0.6 ms for an 805 MB or
 // 201 MB result); here a lane keeps the weight rows of its UPL hidden units in registers (unit j = lane + 32 k). A warp
-// takes kInRows rows of x at a time: the rows are contiguous, so the batch is a few coalesced loads per lane, requested one
+// takes four or eight rows of x at a time: the rows are contiguous, so the batch is a few coalesced loads per lane, requested one
 // batch ahead, parked in shared memory and read back as broadcast 16-byte words; the rows of h leave as UPL coalesced
 // 128-byte stores each.
-constexpr int kInRows = 4;
 
 template <int UPL, int DP, int ACT>
 __global__ void __launch_bounds__(256)
 linear_in_kernel(const float* __restrict__ x, long long N, int D, const float* __restrict__ w, const float* __restrict__ b, int H,
                  float* __restrict__ out) {
+  constexpr int kInRows = UPL <= 2 ? 8 : 4;                       // rows per batch: at least 16 independent FMA chains per lane
   __shared__ __align__(16) float s_x[8][kInRows * DP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float wr[UPL][DP], bias[UPL];
