@@ -105,6 +105,9 @@ def algorithmic_bytes_per_env_step(W, S, L, obs_dim, mean_orders, qty_bytes=1, l
 
 # --------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU during the timed region: NVML polled from a thread every 20 ms (first
+    sample taken synchronously in start(), last in stop(), so even a 100 ms region has samples); `nvidia-smi -lms` as the
+    fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -112,8 +115,42 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, threading.Event(), None
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_sample(self):
+        n, h = self.nvml, self.handle
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
+        try:
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = int(get(h))
+        except Exception:
+            return
+        for name, const in (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+                            ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap")):
+            mask = getattr(n, "nvmlClocksEventReason" + const, None) or getattr(n, "nvmlClocksThrottleReason" + const, 0)
+            if bits & int(mask):
+                self.reasons.add(name)
+
+    def _nvml_loop(self):
+        while not self.stop_flag.wait(0.02):
+            try:
+                self._nvml_sample()
+            except Exception:
+                return
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nvml_sample()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -127,6 +164,18 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            try:
+                self._nvml_sample()
+            except Exception:
+                pass
+            if not self.sm:
+                return None
+            return dict(sm_mhz=statistics.median(self.sm), sm_max_mhz=max(self.mx), reasons=sorted(self.reasons),
+                        samples=len(self.sm), source="nvml")
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -143,7 +192,7 @@ class ClockSampler:
                 continue
         if not sm:
             return None
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
 
 
 # --------------------------------------------------------------------------------------- synthetic data (device)
