@@ -2,6 +2,7 @@
 order packing, spec building, policy modules and the C ABI's exported symbols."""
 import ctypes
 import os
+import pathlib
 import re
 
 import numpy as np
@@ -520,3 +521,25 @@ def test_pack_lines_roundtrip_and_balance():
     assert rounds[True].sum() < rounds[False].sum()
     longest = [max(sum(len(v) for k, v in unpack_lines(pack_lines(batch, balance=False), e).items() if k % 32 == l) for l in range(32)) for e in range(E)]
     assert np.array_equal(rounds[False], np.where(np.array(longest) > 0, (np.array(longest) + 3) & ~1, 0))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (no GPU needed): one JSON line with the reference arm's keys - the same metric / unit /
+    config as the GPU arm, `impl`, a `cpu_baseline` describing this run and an `e2e` object with zero copy bytes. Runs the
+    reference's own env modules when oracle/_ref is populated (build() does that where /root/reference is mounted), else
+    the oracle port."""
+    import json
+    import subprocess
+    import sys
+    root = pathlib.Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "agent_steps_per_sec_env_step_plus_gae"
+    assert line["unit"] == "agent-steps/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["steps"] == 1 and line["warmup"] == 1 and line["n_gpus"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == dict(value=line["value"], unit=line["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert "BASELINE configs[2]" in line["config"]["workload"]
