@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from golden_io import NAMES, Golden
+from parity_common import _lean_env_dict  # noqa: F401  (shared with the CPU tests)
 from parity_common import compare_step, spec_for, step_orders
 
 pytestmark = pytest.mark.gpu
@@ -1000,34 +1001,6 @@ def test_poisson_inversion_survives_the_largest_uniform():
                                                    torch.cuda.current_stream().cuda_stream))
     ref = poisson.ppf(u2.cpu().numpy().astype(np.float64), lam2.cpu().numpy().astype(np.float64))
     assert (out.cpu().numpy() != ref).mean() < 2e-3        # only draws within float32 rounding of a CDF step differ
-
-
-def _lean_env_dict(rng, W, S, R, lost, pen_uniform, lead_hi, scope="agent", demand_home=False, qmax_hi=30):
-    out_var = np.stack([rng.permutation(W) for _ in range(R)], 1) * 0.05 + 0.05          # tie-free -> static priority
-    pen = 4.0 if pen_uniform else [float(x) for x in rng.integers(1, 9, S)]
-    lead = rng.integers(1, lead_hi + 1, (W, S))
-    lead[0, 0] = lead_hi                                                                  # some cell has the longest lead
-    return dict(
-        action_space=dict(type="direct", params=dict(max_order_quantities=[int(x) for x in rng.integers(5, qmax_hi, S)])),
-        n_warehouses=W, n_skus=S, n_regions=R, episode_length=9, max_wh_capacities=[1e7] * W,
-        initial_inventory=dict(type="custom", params=dict(values=6)),
-        cost_structure=dict(
-            holding_cost=0.5, penalty_cost=pen,
-            shipment_cost=dict(outbound_fixed=np.zeros((W, R)).tolist(), outbound_variable=out_var.tolist(),
-                               inbound_fixed=np.full((W, S), 0.5).tolist(), inbound_variable=np.full((W, S), 0.25).tolist()),
-            sku_weights=[1.0] * S, distances=(rng.integers(10, 500, (W, R)) * 1.0).tolist()),
-        components=dict(
-            demand_sampler=dict(type="poisson", params=dict(lambda_orders=1.0, probability_skus=0.3, lambda_quantity=5.0)),
-            demand_allocator=dict(type="greedy", params=dict(max_splits=W - 1)),
-            lead_time_sampler=dict(type="fixed", params=dict(expected_lead_times=lead.tolist())),
-            lost_sales_handler=dict(type=lost, params=None),
-            reward_calculator=dict(type="cost", params=dict(scope=scope, scale_factor=0.1, cost_weights=[0.25] * 4))),
-        data_source=dict(type="custom"),
-        features=dict(inventory=True, pipeline=True, incoming_demand_home=demand_home, units_shipped_home=False, units_shipped_away=False,
-                      stockout=False, rolling_demand_mean=True, demand_forecast=False, days_of_supply=False,
-                      net_inventory_position=False, demand_variability=False, demand_history=False, inventory_aggregate=True,
-                      pipeline_aggregate=False, incoming_demand_home_aggregate=False, units_shipped_away_aggregate=False,
-                      rolling_demand_mean_aggregate=False, demand_forecast_aggregate=False))
 
 
 @pytest.mark.parametrize("W,S,R,lost,pen_uniform,max_orders,lead_hi,variant", [

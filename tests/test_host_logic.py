@@ -543,3 +543,40 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == dict(value=line["value"], unit=line["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert "BASELINE configs[2]" in line["config"]["workload"]
+
+
+def test_line_streams_carry_the_allocation_the_oracle_computes():
+    """The contract of the sparse demand format (include/marlsc_b200.h): with the lean capability set the greedy allocation
+    of one SKU never looks at another SKU, so walking every SKU's lines - in stream sequence, down the region's warehouse
+    priority list - gives the stock the sequential allocator of the reference ends with (demand_allocator.py:150-208,
+    as restated in the oracle). Checked on the CPU from `pack_lines` output alone, balanced and round-robin dealing."""
+    from marlsc_b200.demand import pack_lines, pack_orders, unpack_lines
+    from oracle.inventory_oracle import OracleEnv
+    from parity_common import _lean_env_dict
+    rng = np.random.default_rng(21)
+    W, S, R = 6, 40, 9
+    env_dict = _lean_env_dict(rng, W, S, R, "shipment", True, 3)
+    out_var = np.asarray(env_dict["cost_structure"]["shipment_cost"]["outbound_variable"])       # [W, R]
+    E = 5
+    per_env = []
+    for e in range(E):
+        orders = [(int(rng.integers(0, R)), np.where(rng.random(S) < 0.4, rng.integers(1, 9, S), 0).astype(float))
+                  for _ in range(int(rng.integers(0, 25)))]
+        per_env.append(orders)
+    batch = pack_orders(per_env, S)
+    for balance in (True, False):
+        lines = pack_lines(batch, balance=balance)
+        for e in range(E):
+            o = OracleEnv(env_dict)
+            o.reset(np.full((W, S), 5))
+            want = o.step(np.full((W, S), -1.0, dtype=np.float32), per_env[e])        # action -1: nothing is ordered
+            stock = np.full((W, S), 5, dtype=np.int64)                                 # leads >= 1: nothing arrives at t = 0
+            for sku, seq in unpack_lines(lines, e).items():
+                for region, qty in seq:
+                    for w in np.argsort(out_var[:, region], kind="stable"):            # cheapest warehouse first
+                        take = min(qty, stock[w, sku])
+                        stock[w, sku] -= take
+                        qty -= take
+                        if qty == 0:
+                            break
+            assert np.array_equal(stock, want["inventory"]), (e, balance)
