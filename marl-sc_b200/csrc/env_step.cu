@@ -49,6 +49,7 @@ struct marlsc_env {
   int team = 1;        // lanes per environment in use
   int team_auto = 1;
   int tiny_fallback = 0;   // team_auto is 8 for a tiny SKU count: launches outside the split step run thread-per-environment
+  int team_explicit = 0;   // marlsc_env_set_team_size chose the width: no automatic fallback
   int spl = 1;         // SKUs per lane of the instantiation in use
   void* d_blob = nullptr;  // one allocation holding every device table
   int max_smem_optin = 0;
@@ -362,9 +363,14 @@ int marlsc_env_set_team_size(marlsc_env_t* env, int32_t tpe) {
   if (!env) return set_error(MARLSC_EINVAL, "null handle");
   if (env->layout == MARLSC_LAYOUT_COMPACT && tpe != 0)
     return set_error(MARLSC_EINVAL, "the compact layout runs one warp per environment; force MARLSC_LAYOUT_WIDE to choose a team size");
-  if (tpe == 0) return set_team(env, env->team_auto);
+  if (tpe == 0) {
+    env->team_explicit = 0;
+    return set_team(env, env->team_auto);
+  }
   if (tpe < 1 || tpe > 64 || (tpe & (tpe - 1))) return set_error(MARLSC_EINVAL, "team size must be a power of two in [1,64]");
-  return set_team(env, tpe);
+  const int rc = set_team(env, tpe);
+  if (rc == MARLSC_OK) env->team_explicit = 1;
+  return rc;
 }
 
 int marlsc_env_set_generic(marlsc_env_t* env, int32_t on) {
@@ -488,7 +494,7 @@ int marlsc_env_step(marlsc_env_t* env, const marlsc_env_state_t* state, const ma
   // automatic 8-lane teams of a tiny SKU count: the split step only wins while the batch leaves most SMs idle (3 x 2
   // network, 4,096 environments: 40 against 48 us, 27 against 42 us inside a CUDA graph); beyond that the
   // thread-per-environment kernel's single launch is faster (8,192: 49 against 52 us; 16,384: 52 against 69 us)
-  const bool tiny = env->tiny_fallback && env->team == env->team_auto;
+  const bool tiny = env->tiny_fallback && !env->team_explicit;
   const bool tiny_split = !tiny || state->num_envs <= kTinySplitMaxEnvs;
   if (lean && tiny_split && split_ok(env) && state->num_envs * (int64_t)env->ds.W < (int64_t)0xffffffffLL) {
     rc = ensure_work(env, state->num_envs);
